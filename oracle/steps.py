@@ -1,0 +1,218 @@
+"""fp32 restatement of the reference's per-batch train-step recipes.
+
+TEST INFRASTRUCTURE (see oracle/__init__.py).  The reference's experiment
+scripts cannot be imported (they import the broken ``lib.models.loss``,
+SURVEY.md D7), so the orchestration is restated here over ``oracle.nets`` with
+these explicit, documented deviations:
+
+* WGAN backward seeds are ``+1`` / ``-1`` (the reference uses an uninitialised
+  ``torch.FloatTensor(1)``, wgan_l1.py:74-78 — SURVEY.md D10);
+* dropout is an explicit keep-mask argument;
+* the PatchGAN head is sized ``(R/16-3)**2``.
+
+Every step function mutates the parameter dicts / optimizers in place (like the
+reference) and returns a dict of the scalars and tensors the parity tests
+compare: losses, ``inpainted``, and the parameter gradients *as they were when
+the optimizer consumed them*.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import losses, nets
+
+Params = Dict[str, torch.Tensor]
+
+
+def leaves(p: Params):
+    """Trainable leaves in state_dict order (== module.parameters() order)."""
+    return [v for v in nets.trainable(p).values()]
+
+
+def enable_grad(p: Params):
+    for k, v in nets.trainable(p).items():
+        v.requires_grad_(True)
+    return p
+
+
+def set_requires_grad(param_dicts, flag: bool):
+    """util.set_requires_grad — util.py:19-22."""
+    for p in param_dicts:
+        for v in nets.trainable(p).values():
+            v.requires_grad_(flag)
+
+
+def make_optimizer(kind: str, *param_dicts: Params):
+    """'rmsprop': wgan_l1.py:64-65 (lr 5e-5, alpha .99, eps 1e-8).
+    'adam': minimaxgan_rmse.py:64-65 / experiment1…:122-123 (lr 2e-4, betas (.5,.999))."""
+    ps = [v for p in param_dicts for v in leaves(p)]
+    if kind == "rmsprop":
+        return torch.optim.RMSprop(ps, lr=0.00005)
+    if kind == "adam":
+        return torch.optim.Adam(ps, lr=0.0002, betas=(0.5, 0.999))
+    raise ValueError(kind)
+
+
+def grads_of(p: Params) -> Params:
+    return {k: (v.grad.detach().clone() if v.grad is not None else None) for k, v in nets.trainable(p).items()}
+
+
+def _recon(kind: str, ground, inpainted):
+    if kind == "l1":  # nn.L1Loss()(ground, inpainted) — wgan_l1.py:62,180
+        return (ground - inpainted).abs().mean()
+    if kind == "rmse":  # RMSELoss()(ground, inpainted) — minimaxgan_rmse.py:166, wgan_rmse.py:180
+        return losses.rmse(ground, inpainted)
+    raise ValueError(kind)
+
+
+def prepare(ground, mask, ceil_mask: bool = True):
+    """wgan_l1.py:113-117: mask = ceil(mask); masked = ground * (1 - mask)."""
+    if ceil_mask:
+        mask = torch.ceil(mask)
+    return mask, ground * (1 - mask)
+
+
+def composite(masked, g_out, mask):
+    """wgan_l1.py:122: inpainted = masked + G(masked) * mask."""
+    return masked + g_out * mask
+
+
+def inference(G: Params, ground, mask, train_mode: bool = False):
+    """visualize.py:69-76 / evaluate.py:127-136 (config 5): ceil -> mask out -> G -> composite."""
+    with torch.no_grad():
+        mask, masked = prepare(ground, mask)
+        return composite(masked, nets.unet_forward(G, masked, train=train_mode), mask)
+
+
+def wgan_step(
+    G: Params,
+    D: Params,
+    g_opt,
+    d_opt,
+    ground,
+    mask,
+    recon: str = "l1",
+    update_g: bool = True,
+    dropout_masks: Optional[dict] = None,
+    clip: float = 0.01,
+):
+    """wgan_l1.py:110-186 (recon='l1') / wgan_rmse.py (recon='rmse').
+
+    ``update_g`` stands for the schedule test at wgan_l1.py:157-163."""
+    out = {}
+    mask, masked = prepare(ground, mask)
+    g_out = nets.unet_forward(G, masked, train=True, dropout_masks=dropout_masks)
+    inpainted = composite(masked, g_out, mask)
+    out["g_out"], out["inpainted"] = g_out.detach(), inpainted.detach()
+
+    # ---- D step (:128-153)
+    set_requires_grad([D], True)
+    d_opt.zero_grad()
+    d_real = nets.patchgan_forward(D, ground, train=True, sigmoid=False)
+    d_fake = nets.patchgan_forward(D, inpainted.detach(), train=True, sigmoid=False)
+    d_loss_real = d_real.mean().view(1)
+    d_loss_real.backward(torch.ones(1))  # `one`  (D10)
+    d_loss_fake = d_fake.mean().view(1)
+    d_loss_fake.backward(-torch.ones(1))  # `mone` (D10)
+    out["d_loss_real"], out["d_loss_fake"] = d_loss_real.item(), d_loss_fake.item()
+    out["d_grads"] = grads_of(D)
+    d_opt.step()
+    with torch.no_grad():
+        for v in leaves(D):  # every D parameter incl. BN gamma/beta and the Linear head (:152-153)
+            v.clamp_(-clip, clip)
+
+    # ---- G step (:169-186)
+    if update_g:
+        set_requires_grad([D], False)
+        g_opt.zero_grad()
+        d_gen = nets.patchgan_forward(D, inpainted, train=True, sigmoid=False).view(-1)
+        g_adv = d_gen.mean().view(1)
+        rec = _recon(recon, ground, inpainted)
+        g_loss = g_adv + rec
+        g_loss.backward()
+        out["g_adv"], out["recon"], out["g_loss"] = g_adv.item(), rec.item(), g_loss.item()
+        out["g_grads"] = grads_of(G)
+        g_opt.step()
+    return out
+
+
+def minimax_step(G: Params, D: Params, g_opt, d_opt, ground, mask, recon: str = "rmse", dropout_masks: Optional[dict] = None):
+    """minimaxgan_rmse.py:110-173 (recon='rmse') / minimaxgan_l1.py (recon='l1')."""
+    out = {}
+    mask, masked = prepare(ground, mask)
+    g_out = nets.unet_forward(G, masked, train=True, dropout_masks=dropout_masks)
+    inpainted = composite(masked, g_out, mask)
+    out["g_out"], out["inpainted"] = g_out.detach(), inpainted.detach()
+
+    set_requires_grad([D], True)
+    d_opt.zero_grad()
+    d_real = nets.patchgan_forward(D, ground, train=True, sigmoid=True).view(-1)
+    d_loss_real = losses.bce(d_real, 1.0)
+    d_loss_real.backward()
+    d_fake = nets.patchgan_forward(D, inpainted.detach(), train=True, sigmoid=True).view(-1)
+    d_loss_fake = losses.bce(d_fake, 0.0)
+    d_loss_fake.backward()
+    out["d_loss_real"], out["d_loss_fake"] = d_loss_real.item(), d_loss_fake.item()
+    out["d_grads"] = grads_of(D)
+    d_opt.step()
+
+    set_requires_grad([D], False)
+    g_opt.zero_grad()
+    d_gen = nets.patchgan_forward(D, inpainted, train=True, sigmoid=True).view(-1)
+    g_adv = losses.bce(d_gen, 1.0)
+    rec = _recon(recon, ground, inpainted)
+    g_loss = g_adv + rec
+    g_loss.backward()
+    out["g_adv"], out["recon"], out["g_loss"] = g_adv.item(), rec.item(), g_loss.item()
+    out["g_grads"] = grads_of(G)
+    g_opt.step()
+    return out
+
+
+def global_local_step(
+    G: Params,
+    Dg: Params,
+    Dl: Params,
+    g_opt,
+    d_opt,
+    ground,
+    mask,
+    lambda1: float = 300.0,
+    lambda2: float = 300.0,
+    dropout_masks: Optional[dict] = None,
+):
+    """experiment1_global_local_D.py:139-200.  G step first, no composite, mask not ceil'ed,
+    LSGAN heads on sigmoid outputs, ``d_opt`` is ONE Adam over chain(Dl, Dg) (:123)."""
+    out = {}
+    masked = ground * (1 - mask)
+
+    set_requires_grad([Dg, Dl], False)
+    g_opt.zero_grad()
+    inpainted = nets.unet_forward(G, masked, train=True, dropout_masks=dropout_masks)
+    out["inpainted"] = inpainted.detach()
+    pg = nets.patchgan_forward(Dg, inpainted, train=True, sigmoid=True).view(-1)
+    pl = nets.patchgan_forward(Dl, mask * inpainted, train=True, sigmoid=True).view(-1)
+    g_adv_g, g_adv_l = losses.lsgan(pg, 1.0), losses.lsgan(pl, 1.0)
+    rec_g = losses.rmse(ground, inpainted)
+    rec_l = losses.rmse(mask * ground, mask * inpainted)  # averages over ALL pixels (not LocalLoss)
+    g_loss = g_adv_g + g_adv_l + lambda1 * rec_g + lambda2 * rec_l
+    g_loss.backward()
+    out.update(g_adv_global=g_adv_g.item(), g_adv_local=g_adv_l.item(), recon_global=rec_g.item(), recon_local=rec_l.item(), g_loss=g_loss.item())
+    out["g_grads"] = grads_of(G)
+    g_opt.step()
+
+    set_requires_grad([Dg, Dl], True)
+    d_opt.zero_grad()
+    fake = inpainted.detach()
+    l_rg = losses.lsgan(nets.patchgan_forward(Dg, ground, train=True, sigmoid=True).view(-1), 1.0)
+    l_fg = losses.lsgan(nets.patchgan_forward(Dg, fake, train=True, sigmoid=True).view(-1), 0.0)
+    l_rl = losses.lsgan(nets.patchgan_forward(Dl, ground * mask, train=True, sigmoid=True).view(-1), 1.0)
+    l_fl = losses.lsgan(nets.patchgan_forward(Dl, fake * mask, train=True, sigmoid=True).view(-1), 0.0)
+    d_loss = l_rl + l_fl + l_rg + l_fg
+    d_loss.backward()
+    out["d_loss"] = d_loss.item()
+    out["dg_grads"], out["dl_grads"] = grads_of(Dg), grads_of(Dl)
+    d_opt.step()
+    return out
