@@ -7,24 +7,68 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int64, c_uint32, c_uint64, c_void_p
+from ctypes import POINTER, c_char_p, c_float, c_int, c_longlong, c_uint32, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200inpaint.so")
 
 _lib = None
+# bumped by every kernel that rewrites parameters through raw pointers (fused optimizers, clamp)
+WEIGHT_EPOCH = 0
 
 P = c_void_p  # device (or host, where stated) pointer
 S = c_void_p  # cudaStream_t
 I = c_int
+L = c_longlong
 F = c_float
+U = c_uint32
 
-# name -> argtypes (all functions return int status; 0 == OK)
+# name -> argtypes (all of these return an int status; 0 == OK).  Order == include/b200_inpaint.h.
 SIGNATURES = {
+    # ---- tcgen05 implicit-GEMM convolutions (csrc/conv_gemm.cu)
     "b200_conv_s2_gemm": [P, I, I, I, I, P, I, P, I, I, I, S],
     "b200_convt_s2_gemm": [P, I, I, I, I, I, P, I, P, I, I, I, S],
     "b200_wgrad_gemm": [P, I, I, I, I, I, P, I, P, POINTER(c_int), I, I, S],
     "b200_debug_tma_probe": [P, I, I, I, I, I, I, I, I, I, I, I, I, I, P, S],
+    # ---- weight layouts (csrc/pack.cu)
+    "b200_pack_gather": [P, I, I, P, S],
+    "b200_pack_phase": [P, I, I, P, S],
+    "b200_wgrad_reduce": [P, I, I, I, P, I, S],
+    # ---- BatchNorm + activation (csrc/norm_act.cu)
+    "b200_bn_stats": [P, L, I, P, P, P, P, P, P, F, F, P, S],
+    "b200_bn_eval_coeffs": [I, P, P, P, P, F, P, S],
+    "b200_bn_act": [P, L, I, P, P, I, P, I, I, P, I, I, I, U, S],
+    "b200_bn_act_bwd": [P, L, I, P, P, I, P, I, I, P, I, I, I, U, P, P, P, P, I, P, S],
+    # ---- single-channel-side convolutions and the discriminator head (csrc/conv_direct.cu)
+    "b200_conv_c1_fwd": [P, P, I, I, I, P, I, I, P, P, I, I, S],
+    "b200_convt_c1_fwd": [P, I, I, I, I, I, P, P, I, P, P, P, P, S],
+    "b200_wgrad_c1": [P, I, I, I, I, I, P, P, P, P, I, S],
+    "b200_head_weight": [P, P, I, I, P, S],
+    "b200_head_fwd": [P, P, I, I, P, I, P, P, P, S],
+    "b200_head_dlin": [P, P, I, I, P, S],
+    "b200_head_bwd_input": [P, P, I, I, P, S],
+    "b200_head_bwd_params": [P, P, I, I, I, P, P, P, P, P, P, I, S],
+    # ---- masks, compositing, losses (csrc/losses.cu)
+    "b200_mask_prepare": [P, P, L, I, P, P, S],
+    "b200_composite": [P, P, P, L, P, S],
+    "b200_mul": [P, P, L, P, S],
+    "b200_recon_loss": [I, P, P, P, L, F, P, P, S],
+    "b200_gstep_seed": [P, P, P, P, P, P, I, F, P, I, F, P, P, I, L, P, P, P, P, I, S],
+    "b200_adv_loss": [P, I, I, F, F, P, P, S],
+    # ---- optimizers (csrc/optim.cu)
+    "b200_rmsprop_step": [P, P, P, L, F, F, F, I, F, F, S],
+    "b200_step_inc": [P, S],
+    "b200_adam_step": [P, P, P, P, L, F, F, F, F, P, S],
+    "b200_clamp": [P, L, F, F, S],
+    "b200_absmean": [P, P, I, P, S],
+}
+# helpers that return a plain value instead of a status
+VALUE_FUNCS = {
+    "b200_abi_version": (c_int, []),
+    "b200_last_error": (c_char_p, []),
+    "b200_bn_stat_blocks": (c_int, [L, I]),
+    "b200_wgrad_c1_blocks": (c_int, []),
+    "b200_recon_scratch_floats": (c_int, []),
 }
 
 
@@ -42,9 +86,10 @@ def load():
             "(there is no CPU / PyTorch fallback for the hot path)"
         )
     lib = ctypes.CDLL(LIB_PATH)
-    lib.b200_last_error.restype = c_char_p
-    lib.b200_last_error.argtypes = []
-    lib.b200_abi_version.restype = c_int
+    for name, (res, args) in VALUE_FUNCS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
     for name, args in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError == ABI mismatch: fail loudly
         fn.restype = c_int
@@ -55,7 +100,7 @@ def load():
 
 def exported_symbols():
     """Every entry point include/b200_inpaint.h declares (used by the CPU-side ABI test)."""
-    return ["b200_last_error", "b200_abi_version"] + list(SIGNATURES)
+    return list(VALUE_FUNCS) + list(SIGNATURES)
 
 
 def call(name: str, *args):
@@ -63,6 +108,10 @@ def call(name: str, *args):
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise B200Error(f"{name} failed (status {rc}): {lib.b200_last_error().decode()}")
+
+
+def value(name: str, *args):
+    return getattr(load(), name)(*args)
 
 
 def ptr(t):

@@ -1,0 +1,422 @@
+// BatchNorm (training / eval) + activation passes over NHWC bf16 activations — the memory-bound
+// glue between the tensor-core convolutions.  All kernels are 128-bit vectorised (8 bf16 channels
+// per thread), per-channel statistics are reduced deterministically in two stages (per-block fp32
+// partials -> fp64 finalize), no atomics.
+//
+// Reference semantics: nn.BatchNorm2d(affine, track_running_stats, eps 1e-5, momentum 0.1)
+// (lib/models/networks.py:38, 341-349), LeakyReLU(0.2) / ReLU prologues applied in place on the
+// block input (networks.py:287-289), Dropout(0.5) after the two inner up-norms
+// (networks.py:313-314).
+#include "common.cuh"
+
+namespace b200 {
+
+enum { ACT_NONE = 0, ACT_LEAKY = 1, ACT_RELU = 2 };
+
+constexpr int kStatThreads = 256;
+
+// ---------------------------------------------------------------- statistics: sum, sum of squares per channel
+// partial[blk][2][C]
+__global__ void __launch_bounds__(kStatThreads) bn_stats_kernel(const __nv_bfloat16* __restrict__ y, long long P, int C, float* __restrict__ partial) {
+  const int chunks = C >> 3;               // 8-channel chunks per pixel
+  const int lanes = kStatThreads / chunks;  // pixel lanes per block (C <= 2048)
+  const int chunk = threadIdx.x % chunks;
+  const int pl = threadIdx.x / chunks;
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  if (pl < lanes) {
+    for (long long pix = (long long)blockIdx.x * lanes + pl; pix < P; pix += (long long)gridDim.x * lanes) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(y + pix * C + chunk * 8));
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_bf16x2(u[i]);
+        s[2 * i] += f.x;
+        q[2 * i] += f.x * f.x;
+        s[2 * i + 1] += f.y;
+        q[2 * i + 1] += f.y * f.y;
+      }
+    }
+  }
+  __shared__ float red[kStatThreads][17];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    red[threadIdx.x][i] = s[i];
+    red[threadIdx.x][8 + i] = q[i];
+  }
+  __syncthreads();
+  // thread t < 2*C... : channel c, stat k
+  for (int o = threadIdx.x; o < 2 * C; o += kStatThreads) {
+    const int k = o / C, c = o - k * C;
+    const int ch = c >> 3, ci = c & 7;
+    float acc = 0.f;
+    for (int l = 0; l < lanes; ++l) acc += red[l * chunks + ch][k * 8 + ci];
+    partial[((size_t)blockIdx.x * 2 + k) * C + c] = acc;
+  }
+}
+
+// mean / rstd / scale / shift (+ running-stat update) from the partials.  One thread per channel.
+// stats_out[4][C] = mean, rstd, scale = gamma*rstd, shift = beta - mean*scale
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblk, int C, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   long long* __restrict__ num_batches_tracked, float momentum, float eps, float* __restrict__ stats_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int b = 0; b < nblk; ++b) {
+    s += (double)partial[((size_t)b * 2 + 0) * C + c];
+    q += (double)partial[((size_t)b * 2 + 1) * C + c];
+  }
+  const double mean = s / count;
+  double var = q / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float g = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
+  const float scale = g * rstd;
+  stats_out[0 * C + c] = (float)mean;
+  stats_out[1 * C + c] = rstd;
+  stats_out[2 * C + c] = scale;
+  stats_out[3 * C + c] = bt - (float)mean * scale;
+  if (running_mean) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// eval-mode: scale/shift from the running statistics.
+__global__ void bn_eval_coeffs_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ running_mean,
+                                      const float* __restrict__ running_var, float eps, float* __restrict__ stats_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float rstd = 1.f / sqrtf(running_var[c] + eps);
+  const float scale = gamma[c] * rstd;
+  stats_out[0 * C + c] = running_mean[c];
+  stats_out[1 * C + c] = rstd;
+  stats_out[2 * C + c] = scale;
+  stats_out[3 * C + c] = beta[c] - running_mean[c] * scale;
+}
+
+// ---------------------------------------------------------------- apply: out = act(y*scale + shift) [dropout], optional second store relu(out)
+struct ApplyParams {
+  const __nv_bfloat16* y;
+  long long P;
+  int C;
+  const float* scale;  // may be null (identity)
+  const float* shift;
+  int act;
+  __nv_bfloat16* out1;  // may be null
+  int ld1, off1;
+  __nv_bfloat16* out2;  // relu(out) copy, may be null
+  int ld2, off2;
+  int dropout;  // 1 -> keep-mask from (seed, element index), kept values x2
+  uint32_t seed;
+};
+
+__global__ void __launch_bounds__(256) bn_act_kernel(const ApplyParams p) {
+  const int chunks = p.C >> 3;
+  const long long total = p.P * chunks;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long pix = idx / chunks;
+    const int c0 = (int)(idx - pix * chunks) * 8;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.y + pix * p.C + c0));
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = unpack_bf16x2(u[i]);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+    if (p.scale) {
+      const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + c0)), s1 = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + 4));
+      const float4 h0 = __ldg(reinterpret_cast<const float4*>(p.shift + c0)), h1 = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + 4));
+      const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+      const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], sc[i], sh[i]);
+    }
+    if (p.dropout) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = dropout_keep(p.seed, (uint64_t)(pix * p.C + c0 + i)) ? 2.f * f[i] : 0.f;
+    }
+    if (p.act == ACT_LEAKY) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = f[i] > 0.f ? f[i] : 0.2f * f[i];
+    } else if (p.act == ACT_RELU) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+    }
+    if (p.out1) {
+      uint4 o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+      *reinterpret_cast<uint4*>(p.out1 + pix * p.ld1 + p.off1 + c0) = o;
+    }
+    if (p.out2) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+      uint4 o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+      *reinterpret_cast<uint4*>(p.out2 + pix * p.ld2 + p.off2 + c0) = o;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- backward
+// dz (gradient w.r.t. the pre-activation z = y*scale+shift) from up to two incoming gradients:
+//   ACT_LEAKY: dz = z>0 ? g1+g2 : 0.2*g1     (g2 = skip-connection gradient that passed a ReLU of leaky(z): only where z>0)
+//   ACT_RELU : dz = z>0 ? g1 : 0             (with dropout: dz = keep ? 2*g1*[z>0] : 0)
+//   ACT_NONE : dz = g1
+struct BwdParams {
+  const __nv_bfloat16* y;  // raw conv output
+  long long P;
+  int C;
+  const float* scale;  // forward scale/shift (null: identity)
+  const float* shift;
+  int act;
+  const __nv_bfloat16* g1;
+  int ldg1, offg1;
+  const __nv_bfloat16* g2;  // may be null
+  int ldg2, offg2;
+  int dropout;
+  uint32_t seed;
+  // reduce: partial[blk][2][C] = sum dz, sum dz*y
+  float* partial;
+  // apply: dy = kdz*dz + ky*y + k0   (coef[3][C]; null: dy = dz)
+  const float* coef;
+  __nv_bfloat16* dy;
+};
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = unpack_bf16x2(u[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+__device__ __forceinline__ void compute_dz(const BwdParams& p, long long pix, int c0, float (&yv)[8], float (&dz)[8]) {
+  load8(p.y + pix * p.C + c0, yv);
+  float g1[8];
+  load8(p.g1 + pix * p.ldg1 + p.offg1 + c0, g1);
+  float z[8];
+  if (p.scale) {
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + c0)), s1 = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + 4));
+    const float4 h0 = __ldg(reinterpret_cast<const float4*>(p.shift + c0)), h1 = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + 4));
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) z[i] = fmaf(yv[i], sc[i], sh[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) z[i] = yv[i];
+  }
+  if (p.act == ACT_LEAKY) {
+    if (p.g2) {
+      float g2[8];
+      load8(p.g2 + pix * p.ldg2 + p.offg2 + c0, g2);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dz[i] = z[i] > 0.f ? g1[i] + g2[i] : 0.2f * g1[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dz[i] = z[i] > 0.f ? g1[i] : 0.2f * g1[i];
+    }
+  } else if (p.act == ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dz[i] = z[i] > 0.f ? g1[i] : 0.f;
+    if (p.dropout) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dz[i] = dropout_keep(p.seed, (uint64_t)(pix * p.C + c0 + i)) ? 2.f * dz[i] : 0.f;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dz[i] = g1[i];
+  }
+}
+
+__global__ void __launch_bounds__(kStatThreads) bn_bwd_reduce_kernel(const BwdParams p) {
+  const int chunks = p.C >> 3;
+  const int lanes = kStatThreads / chunks;
+  const int chunk = threadIdx.x % chunks;
+  const int pl = threadIdx.x / chunks;
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  if (pl < lanes) {
+    for (long long pix = (long long)blockIdx.x * lanes + pl; pix < p.P; pix += (long long)gridDim.x * lanes) {
+      float yv[8], dz[8];
+      compute_dz(p, pix, chunk * 8, yv, dz);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += dz[i];
+        q[i] += dz[i] * yv[i];
+      }
+    }
+  }
+  __shared__ float red[kStatThreads][17];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    red[threadIdx.x][i] = s[i];
+    red[threadIdx.x][8 + i] = q[i];
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < 2 * p.C; o += kStatThreads) {
+    const int k = o / p.C, c = o - k * p.C;
+    const int ch = c >> 3, ci = c & 7;
+    float acc = 0.f;
+    for (int l = 0; l < lanes; ++l) acc += red[l * chunks + ch][k * 8 + ci];
+    p.partial[((size_t)blockIdx.x * 2 + k) * p.C + c] = acc;
+  }
+}
+
+// dgamma / dbeta (+= if accumulate) and the apply coefficients.  stats[4][C] from the forward.
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, double count, const float* __restrict__ stats,
+                                       const float* __restrict__ gamma, float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate,
+                                       float* __restrict__ coef) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double sdz = 0.0, sdzy = 0.0;
+  for (int b = 0; b < nblk; ++b) {
+    sdz += (double)partial[((size_t)b * 2 + 0) * C + c];
+    sdzy += (double)partial[((size_t)b * 2 + 1) * C + c];
+  }
+  const double mean = stats[0 * C + c], rstd = stats[1 * C + c];
+  const double dg = rstd * (sdzy - mean * sdz);  // sum dz * xhat
+  const double db = sdz;
+  if (dgamma) {
+    if (accumulate) {
+      dgamma[c] += (float)dg;
+      dbeta[c] += (float)db;
+    } else {
+      dgamma[c] = (float)dg;
+      dbeta[c] = (float)db;
+    }
+  }
+  const double a = (double)(gamma ? gamma[c] : 1.f) * rstd;
+  coef[0 * C + c] = (float)a;
+  coef[1 * C + c] = (float)(-a * rstd * dg / count);
+  coef[2 * C + c] = (float)(-a * db / count + a * rstd * mean * dg / count);
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdParams p) {
+  const int chunks = p.C >> 3;
+  const long long total = p.P * chunks;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long pix = idx / chunks;
+    const int c0 = (int)(idx - pix * chunks) * 8;
+    float yv[8], dz[8];
+    compute_dz(p, pix, c0, yv, dz);
+    if (p.coef) {
+      const float* k = p.coef;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dz[i] = fmaf(__ldg(k + c0 + i), dz[i], fmaf(__ldg(k + p.C + c0 + i), yv[i], __ldg(k + 2 * p.C + c0 + i)));
+    }
+    uint4 o = make_uint4(pack_bf16x2(dz[0], dz[1]), pack_bf16x2(dz[2], dz[3]), pack_bf16x2(dz[4], dz[5]), pack_bf16x2(dz[6], dz[7]));
+    *reinterpret_cast<uint4*>(p.dy + pix * p.C + c0) = o;
+  }
+}
+
+static int grid_for(long long work_items, int threads) {
+  long long g = (work_items + threads - 1) / threads;
+  const long long cap = 148LL * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_bn_stat_blocks(long long P, int C) {
+  const int lanes = kStatThreads / (C >> 3);
+  long long g = (P + lanes - 1) / lanes;
+  // enough pixels per block to amortise the smem reduction; at most 4 waves of 148 SMs
+  long long cap = 148 * 4;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// y[P][C] bf16 -> partial[nblk][2][C]; then finalize -> stats[4][C] (+ running stats).  training mode.
+int b200_bn_stats(const void* y, long long P, int C, void* partial, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                  long long* num_batches_tracked, float momentum, float eps, float* stats_out, cudaStream_t stream) {
+  if (C % 8 || C > 2048 || C < 8) {
+    b200_set_error("bn_stats: C must be a multiple of 8 in [8, 2048]");
+    return B200_ERR_ARG;
+  }
+  const int nblk = b200_bn_stat_blocks(P, C);
+  bn_stats_kernel<<<nblk, kStatThreads, 0, stream>>>((const __nv_bfloat16*)y, P, C, (float*)partial);
+  B200_CHECK_LAUNCH();
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>((const float*)partial, nblk, C, (double)P, gamma, beta, running_mean, running_var,
+                                                           num_batches_tracked, momentum, eps, stats_out);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+int b200_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps, float* stats_out,
+                        cudaStream_t stream) {
+  bn_eval_coeffs_kernel<<<(C + 127) / 128, 128, 0, stream>>>(C, gamma, beta, running_mean, running_var, eps, stats_out);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+int b200_bn_act(const void* y, long long P, int C, const float* scale, const float* shift, int act, void* out1, int ld1, int off1, void* out2, int ld2,
+                int off2, int dropout, unsigned seed, cudaStream_t stream) {
+  if (C % 8 || ld1 % 8 || off1 % 8 || ld2 % 8 || off2 % 8) {
+    b200_set_error("bn_act: channel counts / strides must be multiples of 8");
+    return B200_ERR_ARG;
+  }
+  ApplyParams p{(const __nv_bfloat16*)y, P, C, scale, shift, act, (__nv_bfloat16*)out1, ld1, off1, (__nv_bfloat16*)out2, ld2, off2, dropout, seed};
+  bn_act_kernel<<<grid_for(P * (C >> 3), 256), 256, 0, stream>>>(p);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+// Backward of (BN ->) [dropout ->] activation.  If `stats` is non-null (training-mode BN) the
+// per-channel reductions run, dgamma/dbeta are produced and dy carries the batch-statistics terms;
+// otherwise dy = scale * dz (eval BN) or dz (no norm).
+int b200_bn_act_bwd(const void* y, long long P, int C, const float* stats /*[4][C] or null*/, const float* gamma, int act, const void* g1, int ldg1,
+                    int offg1, const void* g2, int ldg2, int offg2, int dropout, unsigned seed, void* partial, float* coef /*[3][C] scratch*/,
+                    float* dgamma, float* dbeta, int accumulate, void* dy, cudaStream_t stream) {
+  if (C % 8 || C > 2048 || ldg1 % 8 || offg1 % 8 || ldg2 % 8 || offg2 % 8) {
+    b200_set_error("bn_act_bwd: channel counts / strides must be multiples of 8");
+    return B200_ERR_ARG;
+  }
+  BwdParams p{};
+  p.y = (const __nv_bfloat16*)y;
+  p.P = P;
+  p.C = C;
+  p.scale = stats ? stats + 2 * C : nullptr;
+  p.shift = stats ? stats + 3 * C : nullptr;
+  p.act = act;
+  p.g1 = (const __nv_bfloat16*)g1;
+  p.ldg1 = ldg1;
+  p.offg1 = offg1;
+  p.g2 = (const __nv_bfloat16*)g2;
+  p.ldg2 = ldg2;
+  p.offg2 = offg2;
+  p.dropout = dropout;
+  p.seed = seed;
+  p.partial = (float*)partial;
+  p.coef = nullptr;
+  p.dy = (__nv_bfloat16*)dy;
+  if (stats) {
+    const int nblk = b200_bn_stat_blocks(P, C);
+    bn_bwd_reduce_kernel<<<nblk, kStatThreads, 0, stream>>>(p);
+    B200_CHECK_LAUNCH();
+    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>((const float*)partial, nblk, C, (double)P, stats, gamma, dgamma, dbeta, accumulate, coef);
+    B200_CHECK_LAUNCH();
+    p.coef = coef;
+  }
+  bn_bwd_apply_kernel<<<grid_for(P * (C >> 3), 256), 256, 0, stream>>>(p);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,417 @@
+"""Host-side orchestration of the CUDA kernels for the two networks on the hot path.
+
+``GeneratorEngine``  — UnetGenerator(1, 1, num_downs, ngf=64, BatchNorm) forward / backward
+                        (reference lib/models/networks.py:216-324)
+``DiscriminatorEngine`` — PatchGANDiscriminator forward / backward (networks.py:331-363)
+
+The engines own no parameters: they read the fp32 master weights of the drop-in ``nn.Module``s
+(checkpoint layout), keep bf16 K-major operand copies for the tensor-core kernels,
+and write fp32 gradients into tensors the caller provides.  Activations are NHWC bf16; the
+1-channel images at either end stay fp32.  Every op is a call through the C-ABI
+(``_lib.call``) on the current CUDA stream; PyTorch is used for device memory only.
+
+Data flow of one generator level ``l`` (the skip tensor is the *post-LeakyReLU*
+encoder activation and the decoder applies ReLU to the whole concat):
+
+    a[l-1] --conv k4s2p1 (tcgen05)--> y[l] --BN stats--> a[l] = leaky(bn(y[l]))          (dense)
+                                                       cat[l][:, :C] = relu(bn(y[l]))    (skip half)
+    cat[l] --convT k4s2p1 (tcgen05, 4 phases)--> yu[l] --BN stats--> cat[l-1][:, C':] = relu(drop(bn(yu[l])))
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream
+
+ACT_NONE, ACT_LEAKY, ACT_RELU, ACT_TANH = 0, 1, 2, 3
+NUM_SMS = 148
+
+bf16 = torch.bfloat16
+f32 = torch.float32
+
+
+def _empty(shape, dtype, device):
+    return torch.empty(shape, dtype=dtype, device=device)
+
+
+class Scratch:
+    """Per-device scratch shared by all engines (single stream semantics)."""
+
+    _by_device: Dict[int, "Scratch"] = {}
+
+    def __init__(self, device):
+        self.device = device
+        self.bn_partial = _empty(_lib.value("b200_bn_stat_blocks", 1 << 40, 8) * 2 * 2048, f32, device)
+        self.coef = _empty(3 * 2048, f32, device)
+        self.c1_partial = _empty(_lib.value("b200_wgrad_c1_blocks") * 128 * 16, f32, device)
+        self.recon = _empty(_lib.value("b200_recon_scratch_floats"), f32, device)
+        self.wgrad: Optional[torch.Tensor] = None
+
+    @classmethod
+    def get(cls, device) -> "Scratch":
+        idx = torch.device(device).index or 0
+        if idx not in cls._by_device:
+            cls._by_device[idx] = Scratch(torch.device("cuda", idx))
+        return cls._by_device[idx]
+
+    def wgrad_buf(self, nfloats: int) -> torch.Tensor:
+        if self.wgrad is None or self.wgrad.numel() < nfloats:
+            self.wgrad = _empty(nfloats, f32, self.device)
+        return self.wgrad
+
+
+def pick_bn(m_tiles: int, cout: int, phases: int = 1) -> int:
+    """N tile of the fprop / dgrad GEMM: the widest tile that still gives every SM a CTA."""
+    for bn in (256, 128, 64, 32):
+        if cout % bn:
+            continue
+        if m_tiles * (cout // bn) * phases >= NUM_SMS:
+            return bn
+    for bn in (32, 64, 128, 256):
+        if cout % bn == 0:
+            return bn
+    return cout
+
+
+def _m_tiles(B: int, hs: int, ws: int, npix: int = 128) -> int:
+    tw = min(ws, npix)
+    th = min(hs, npix // tw)
+    nb = npix // (tw * th)
+    return (ws // tw) * (hs // th) * ((B + nb - 1) // nb)
+
+
+# ------------------------------------------------------------------------------------------------
+# thin op wrappers (shapes are NHWC; all tensors contiguous)
+# ------------------------------------------------------------------------------------------------
+def conv_s2(x, wpk, cout, out=None, ldy=None):
+    """x [B,H,W,Cin] bf16 -> [B,H/2,W/2,cout]; wpk [cout][16*Cin]."""
+    B, H, W, Cin = x.shape
+    if out is None:
+        out = _empty((B, H // 2, W // 2, cout), bf16, x.device)
+        ldy = cout
+    bn = pick_bn(_m_tiles(B, H // 2, W // 2), cout)
+    call("b200_conv_s2_gemm", ptr(x), B, H, W, Cin, ptr(wpk), cout, ptr(out), ldy, bn, 0, stream())
+    return out
+
+
+def convt_s2(z, ldz, cin, wpk, cout):
+    """z [B,Hi,Wi,>=cin] (pixel stride ldz) -> [B,2Hi,2Wi,cout]; wpk [4][cout][4*cin]."""
+    B, Hi, Wi = z.shape[:3]
+    out = _empty((B, 2 * Hi, 2 * Wi, cout), bf16, z.device)
+    bn = pick_bn(_m_tiles(B, Hi, Wi), cout, phases=4)
+    call("b200_convt_s2_gemm", ptr(z), B, Hi, Wi, cin, ldz, ptr(wpk), cout, ptr(out), cout, bn, 0, stream())
+    return out
+
+
+def wgrad(S, lds, cs, Lt, grad, accumulate, scratch: Scratch):
+    """grad[cs][cl][4][4] (+)= sum S[b,i,j,cs] * L[b,2i+kh-1,2j+kw-1,cl]."""
+    B, Hs, Ws = S.shape[:3]
+    cl = Lt.shape[3]
+    ptiles = _m_tiles(B, Hs, Ws, 64)
+    bn = 256
+    ctas = (cs // 128) * (16 * cl // bn)
+    splits = max(1, min(ptiles, (2 * NUM_SMS + ctas - 1) // ctas, 64))
+    part = scratch.wgrad_buf(splits * cs * 16 * cl)
+    sp = ctypes.c_int(splits)
+    call("b200_wgrad_gemm", ptr(S), B, Hs, Ws, cs, lds, ptr(Lt), cl, ptr(part), ctypes.byref(sp), bn, 0, stream())
+    call("b200_wgrad_reduce", ptr(part), sp.value, cs, cl, ptr(grad), int(accumulate), stream())
+
+
+def bn_stats(y, C, gamma, beta, rmean, rvar, nbt, momentum, eps, scratch: Scratch):
+    P = y.numel() // C
+    stats = _empty((4, C), f32, y.device)
+    call("b200_bn_stats", ptr(y), P, C, ptr(scratch.bn_partial), ptr(gamma), ptr(beta), ptr(rmean), ptr(rvar), ptr(nbt), float(momentum), float(eps),
+         ptr(stats), stream())
+    return stats
+
+
+def bn_eval(C, gamma, beta, rmean, rvar, eps, device):
+    stats = _empty((4, C), f32, device)
+    call("b200_bn_eval_coeffs", C, ptr(gamma), ptr(beta), ptr(rmean), ptr(rvar), float(eps), ptr(stats), stream())
+    return stats
+
+
+def bn_act(y, C, stats, act, out1=None, ld1=0, off1=0, out2=None, ld2=0, off2=0, dropout=False, seed=0):
+    P = y.numel() // C
+    scale = None if stats is None else ctypes.c_void_p(stats.data_ptr() + 2 * C * 4)
+    shift = None if stats is None else ctypes.c_void_p(stats.data_ptr() + 3 * C * 4)
+    call("b200_bn_act", ptr(y), P, C, scale, shift, act, ptr(out1), ld1, off1, ptr(out2), ld2, off2, int(dropout), int(seed) & 0xFFFFFFFF, stream())
+
+
+def bn_act_bwd(y, C, stats, gamma, act, g1, ldg1, offg1, g2, ldg2, offg2, dropout, seed, dgamma, dbeta, accumulate, scratch: Scratch):
+    P = y.numel() // C
+    dy = _empty(y.shape, bf16, y.device)
+    call("b200_bn_act_bwd", ptr(y), P, C, ptr(stats), ptr(gamma), act, ptr(g1), ldg1, offg1, ptr(g2), ldg2, offg2, int(dropout), int(seed) & 0xFFFFFFFF,
+         ptr(scratch.bn_partial), ptr(scratch.coef), ptr(dgamma), ptr(dbeta), int(accumulate), ptr(dy), stream())
+    return dy
+
+
+class _Packed:
+    """bf16 operand copies of one 4x4/s2 layer's fp32 master weight [D0, D1, 4, 4]."""
+
+    def __init__(self, w: torch.Tensor):
+        d0, d1 = w.shape[:2]
+        self.gather = _empty((d0, 16 * d1), bf16, w.device)      # n = D0, k = D1
+        self.phase = _empty((4, d1, 4 * d0), bf16, w.device)     # n = D1, k = D0
+
+    def refresh(self, w: torch.Tensor):
+        d0, d1 = w.shape[:2]
+        call("b200_pack_gather", ptr(w), d0, d1, ptr(self.gather), stream())
+        call("b200_pack_phase", ptr(w), d0, d1, ptr(self.phase), stream())
+
+
+# ================================================================================================
+# generator
+# ================================================================================================
+class GenCtx:
+    """Everything one generator forward leaves behind for its backward."""
+
+    __slots__ = ("B", "R", "x", "a", "y", "sd", "r_in", "yu", "su", "cat", "g_out", "comp", "seed", "train", "dropout")
+
+
+class GeneratorEngine:
+    def __init__(self, down_convs, down_norms, up_convs, up_norms, dropout_levels, widths):
+        """``down_convs[l-1]`` / ``up_convs[l-1]`` are the nn.Conv2d / nn.ConvTranspose2d of level l (1 = outermost);
+        ``down_norms`` / ``up_norms`` hold the nn.BatchNorm2d of that level or None."""
+        self.N = len(down_convs)
+        self.dc, self.dn, self.uc, self.un = down_convs, down_norms, up_convs, up_norms
+        self.w = [None] + list(widths)  # w[l] = channels of a[l]
+        self.dropout_levels = set(dropout_levels)
+        self.packed_d: Dict[int, _Packed] = {}
+        self.packed_u: Dict[int, _Packed] = {}
+        self._versions = None
+        self.calls = 0
+        for l in range(2, self.N + 1):
+            if self.w[l] % 128 or self.w[l - 1] % 64:
+                raise _lib.B200Error("the tcgen05 path needs ngf to be a multiple of 64 (channel plan %r)" % (widths,))
+
+    # ---- weights
+    def _weights(self):
+        return [c.weight for c in self.dc[1:]] + [c.weight for c in self.uc[1:]]
+
+    def refresh_weights(self, force=False):
+        ws = self._weights()
+        ver = (_lib.WEIGHT_EPOCH,) + tuple((w._version, w.data_ptr()) for w in ws)
+        if not force and ver == self._versions:
+            return
+        for l in range(2, self.N + 1):
+            if l not in self.packed_d or self.packed_d[l].gather.device != self.dc[l - 1].weight.device:
+                self.packed_d[l] = _Packed(self.dc[l - 1].weight)
+                self.packed_u[l] = _Packed(self.uc[l - 1].weight)
+            self.packed_d[l].refresh(self.dc[l - 1].weight.data)
+            self.packed_u[l].refresh(self.uc[l - 1].weight.data)
+        self._versions = ver
+
+    # ---- forward
+    def forward(self, x: torch.Tensor, train: bool, comp_base=None, comp_mul=None, seed: int = 0, keep: bool = True) -> GenCtx:
+        """x: fp32 [B,1,R,R] (or [B,R,R]).  Returns a context with ``g_out`` fp32 [B,1,R,R] (and ``comp``)."""
+        dev = x.device
+        B, R = x.shape[0], x.shape[-1]
+        N, w = self.N, self.w
+        if x.shape[-2] != R or R % (1 << N) or (R >> N) < 1 or (R & (R - 1)):
+            raise _lib.B200Error(f"generator input must be square with a power-of-two side >= {1 << N}, got {tuple(x.shape)}")
+        if R // 2 < 16:
+            raise _lib.B200Error("generator input side must be >= 32")
+        self.refresh_weights()
+        sc = Scratch.get(dev)
+        c = GenCtx()
+        c.B, c.R, c.x, c.train, c.seed = B, R, x, train, seed
+        c.dropout = bool(self.dropout_levels) and train
+        c.a, c.y, c.sd, c.yu, c.su, c.cat = {}, {}, {}, {}, {}, {}
+        side = lambda l: R >> l
+        for l in range(1, N):
+            c.cat[l] = _empty((B, side(l), side(l), 2 * w[l]), bf16, dev)
+        # d1: direct conv + LeakyReLU, relu copy into cat[1]
+        c.a[1] = _empty((B, side(1), side(1), w[1]), bf16, dev)
+        call("b200_conv_c1_fwd", ptr(x), None, B, R, R, ptr(self.dc[0].weight.data), w[1], ACT_LEAKY, ptr(c.a[1]), ptr(c.cat[1]), 2 * w[1], 0, stream())
+        # d2 .. dN
+        for l in range(2, N + 1):
+            c.y[l] = conv_s2(c.a[l - 1], self.packed_d[l].gather, w[l])
+            if l < N:
+                c.sd[l] = self._stats(self.dn[l - 1], c.y[l], w[l], train, sc)
+                c.a[l] = _empty(c.y[l].shape, bf16, dev)
+                bn_act(c.y[l], w[l], c.sd[l], ACT_LEAKY, c.a[l], w[l], 0, c.cat[l], 2 * w[l], 0)
+            else:
+                c.r_in = _empty(c.y[l].shape, bf16, dev)
+                bn_act(c.y[l], w[l], None, ACT_RELU, c.r_in, w[l], 0)
+        # uN .. u2
+        for l in range(N, 1, -1):
+            zin, cin = (c.r_in, w[N]) if l == N else (c.cat[l], 2 * w[l])
+            c.yu[l] = convt_s2(zin, cin, cin, self.packed_u[l].phase, w[l - 1])
+            c.su[l] = self._stats(self.un[l - 1], c.yu[l], w[l - 1], train, sc)
+            bn_act(c.yu[l], w[l - 1], c.su[l], ACT_RELU, c.cat[l - 1], 2 * w[l - 1], w[l - 1], dropout=c.dropout and l in self.dropout_levels,
+                   seed=seed * 16 + l)
+        # u1: direct transposed conv + bias + tanh (+ composite)
+        c.g_out = _empty((B, 1, R, R), f32, dev)
+        c.comp = _empty((B, 1, R, R), f32, dev) if comp_base is not None else None
+        up1 = self.uc[0]
+        call("b200_convt_c1_fwd", ptr(c.cat[1]), B, side(1), side(1), 2 * w[1], 2 * w[1], ptr(up1.weight.data), ptr(up1.bias.data if up1.bias is not None else None),
+             ACT_TANH, ptr(comp_base), ptr(comp_mul), ptr(c.g_out), ptr(c.comp), stream())
+        self.calls += 1
+        if not keep:  # inference: drop the activations
+            c.a = c.y = c.yu = c.cat = None
+        return c
+
+    def _stats(self, bn, y, C, train, sc):
+        if bn is None:
+            return None
+        if train or not bn.track_running_stats:
+            track = bn.track_running_stats and train
+            return bn_stats(y, C, bn.weight.data, bn.bias.data, bn.running_mean if track else None, bn.running_var if track else None,
+                            bn.num_batches_tracked if track else None, bn.momentum, bn.eps, sc)
+        return bn_eval(C, bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, bn.eps, y.device)
+
+    # ---- backward
+    def backward(self, c: GenCtx, dpre: torch.Tensor, grads: Dict[object, torch.Tensor], accumulate: bool = False, on_ready=None):
+        """dpre: fp32 [B,1,R,R] gradient w.r.t. the pre-tanh output.  ``grads`` maps each parameter (by
+        ``id`` of the nn.Parameter) to the fp32 tensor its gradient is written / accumulated into; the bias of
+        the last layer is handled by the caller (gstep_seed reduces it)."""
+        if not c.train:
+            raise _lib.B200Error("generator backward needs a training-mode forward (batch statistics)")
+        dev = dpre.device
+        sc = Scratch.get(dev)
+        B, R, N, w = c.B, c.R, self.N, self.w
+        side = lambda l: R >> l
+        acc = int(accumulate)
+        G = lambda p: grads[id(p)]
+        done = on_ready if on_ready is not None else (lambda p: None)  # data-parallel bucketing hook: p.grad is enqueued
+        # ---- u1
+        up1 = self.uc[0]
+        call("b200_wgrad_c1", ptr(c.cat[1]), B, side(1), side(1), 2 * w[1], 2 * w[1], ptr(dpre), None, ptr(sc.c1_partial), ptr(G(up1.weight)), acc, stream())
+        done(up1.weight)
+        dcat = _empty(c.cat[1].shape, bf16, dev)
+        call("b200_conv_c1_fwd", ptr(dpre), None, B, R, R, ptr(up1.weight.data), 2 * w[1], ACT_NONE, ptr(dcat), None, 0, 0, stream())
+        dcats = {1: dcat}
+        # ---- decoder u2 .. uN
+        for l in range(2, N + 1):
+            bn = self.un[l - 1]
+            dyu = bn_act_bwd(c.yu[l], w[l - 1], c.su[l], bn.weight.data, ACT_RELU, dcats[l - 1], 2 * w[l - 1], w[l - 1], None, 0, 0,
+                             c.dropout and l in self.dropout_levels, c.seed * 16 + l, G(bn.weight), G(bn.bias), accumulate, sc)
+            done(bn.bias)
+            zin, cin = (c.r_in, w[N]) if l == N else (c.cat[l], 2 * w[l])
+            wgrad(zin, cin, cin, dyu, G(self.uc[l - 1].weight), accumulate, sc)
+            done(self.uc[l - 1].weight)
+            dcats[l] = conv_s2(dyu, self.packed_u[l].gather, cin)
+        # ---- encoder dN .. d2
+        dy = bn_act_bwd(c.y[N], w[N], None, None, ACT_RELU, dcats[N], w[N], 0, None, 0, 0, False, 0, None, None, False, sc)
+        for l in range(N, 1, -1):
+            if l < N:
+                bn = self.dn[l - 1]
+                dy = bn_act_bwd(c.y[l], w[l], c.sd[l], bn.weight.data, ACT_LEAKY, da, w[l], 0, dcats[l], 2 * w[l], 0, False, 0, G(bn.weight), G(bn.bias),
+                                accumulate, sc)
+                done(bn.weight)
+            wgrad(dy, w[l], w[l], c.a[l - 1], G(self.dc[l - 1].weight), accumulate, sc)
+            done(self.dc[l - 1].weight)
+            da = convt_s2(dy, w[l], w[l], self.packed_d[l].phase, w[l - 1])
+        # ---- d1
+        dz1 = bn_act_bwd(c.a[1], w[1], None, None, ACT_LEAKY, da, w[1], 0, dcats[1], 2 * w[1], 0, False, 0, None, None, False, sc)
+        call("b200_wgrad_c1", ptr(dz1), B, side(1), side(1), w[1], w[1], ptr(c.x), None, ptr(sc.c1_partial), ptr(G(self.dc[0].weight)), acc, stream())
+        done(self.dc[0].weight)
+
+
+# ================================================================================================
+# discriminator
+# ================================================================================================
+class DiscCtx:
+    __slots__ = ("B", "R", "x", "xmul", "a", "y", "st", "lin", "pred", "train", "sigmoid")
+
+
+class DiscriminatorEngine:
+    def __init__(self, convs, norms, head_conv, head_linear):
+        """convs: the four k4s2p1 nn.Conv2d; norms: [None, bn2, bn3, bn4]; head_conv: Conv2d(512,1,4,1,0); head_linear: nn.Linear."""
+        self.convs, self.norms, self.hc, self.hl = convs, norms, head_conv, head_linear
+        self.packed: Dict[int, _Packed] = {}
+        self._versions = None
+        self.E = None
+        self.calls = 0
+
+    def refresh_weights(self, force=False):
+        ws = [c.weight for c in self.convs[1:]] + [self.hc.weight, self.hl.weight]
+        ver = (_lib.WEIGHT_EPOCH,) + tuple((w._version, w.data_ptr()) for w in ws)
+        if not force and ver == self._versions:
+            return
+        for i in range(1, 4):
+            if i not in self.packed or self.packed[i].gather.device != self.convs[i].weight.device:
+                self.packed[i] = _Packed(self.convs[i].weight)
+            self.packed[i].refresh(self.convs[i].weight.data)
+        n = int(round(self.hl.in_features ** 0.5))
+        S, C = n + 3, self.hc.in_channels
+        if self.E is None or self.E.numel() != S * S * C:
+            self.E = _empty((S, S, C), f32, self.hc.weight.device)
+        call("b200_head_weight", ptr(self.hc.weight.data), ptr(self.hl.weight.data), S, C, ptr(self.E), stream())
+        self._versions = ver
+
+    def forward(self, x: torch.Tensor, train: bool, sigmoid: bool, xmul: Optional[torch.Tensor] = None) -> DiscCtx:
+        """x: fp32 [B,1,R,R]; xmul: optional fp32 multiplier applied on load (the local discriminator's mask)."""
+        dev = x.device
+        B, R = x.shape[0], x.shape[-1]
+        n = int(round(self.hl.in_features ** 0.5))
+        if x.shape[-2] != R or R & (R - 1) or R // 16 - 3 != n:
+            raise _lib.B200Error(f"discriminator head Linear({self.hl.in_features},1) expects {16 * (n + 3)}x{16 * (n + 3)} inputs, got {tuple(x.shape)}")
+        self.refresh_weights()
+        sc = Scratch.get(dev)
+        c = DiscCtx()
+        c.B, c.R, c.x, c.xmul, c.train, c.sigmoid = B, R, x, xmul, train, sigmoid
+        c.a, c.y, c.st = {}, {}, {}
+        c.a[0] = _empty((B, R // 2, R // 2, 64), bf16, dev)
+        call("b200_conv_c1_fwd", ptr(x), ptr(xmul), B, R, R, ptr(self.convs[0].weight.data), 64, ACT_LEAKY, ptr(c.a[0]), None, 0, 0, stream())
+        for i in range(1, 4):
+            C = 64 << i
+            c.y[i] = conv_s2(c.a[i - 1], self.packed[i].gather, C)
+            bn = self.norms[i]
+            if train:
+                c.st[i] = bn_stats(c.y[i], C, bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, bn.num_batches_tracked, bn.momentum, bn.eps, sc)
+            else:
+                c.st[i] = bn_eval(C, bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, bn.eps, dev)
+            c.a[i] = _empty(c.y[i].shape, bf16, dev)
+            bn_act(c.y[i], C, c.st[i], ACT_LEAKY, c.a[i], C, 0)
+        S = R // 16
+        c.lin = _empty((B,), f32, dev)
+        c.pred = _empty((B, 1), f32, dev)
+        hs = _empty((B * 8,), f32, dev)
+        call("b200_head_fwd", ptr(c.a[3]), ptr(self.E), B, S * S * 512, ptr(self.hl.bias.data), int(sigmoid), ptr(hs), ptr(c.lin), ptr(c.pred), stream())
+        self.calls += 1
+        return c
+
+    def backward(self, c: DiscCtx, dlin: torch.Tensor, grads: Optional[Dict[object, torch.Tensor]], accumulate: bool = False, input_grad: bool = False,
+                 on_ready=None):
+        """dlin: fp32 [B] gradient w.r.t. the pre-sigmoid head output.  ``grads`` None == parameters frozen
+        (util.set_requires_grad(D, False), wgan_l1.py:169): only the data gradient is computed."""
+        if not c.train:
+            raise _lib.B200Error("discriminator backward needs a training-mode forward")
+        dev = dlin.device
+        sc = Scratch.get(dev)
+        B, R = c.B, c.R
+        S = R // 16
+        acc = int(accumulate)
+        G = (lambda p: grads[id(p)]) if grads is not None else None
+        done = on_ready if on_ready is not None else (lambda p: None)
+        if G is not None:
+            dE = _empty((S * S * 512,), f32, dev)
+            call("b200_head_bwd_params", ptr(dlin), ptr(c.a[3]), B, S, 512, ptr(self.hc.weight.data), ptr(self.hl.weight.data), ptr(dE), ptr(G(self.hc.weight)),
+                 ptr(G(self.hl.weight)), ptr(G(self.hl.bias)), acc, stream())
+            done(self.hc.weight)
+        da = _empty(c.a[3].shape, bf16, dev)
+        call("b200_head_bwd_input", ptr(dlin), ptr(self.E), B, S * S * 512, ptr(da), stream())
+        for i in range(3, 0, -1):
+            C = 64 << i
+            bn = self.norms[i]
+            dy = bn_act_bwd(c.y[i], C, c.st[i], bn.weight.data, ACT_LEAKY, da, C, 0, None, 0, 0, False, 0, G(bn.weight) if G else None, G(bn.bias) if G else None,
+                            accumulate, sc)
+            if G is not None:
+                wgrad(dy, C, C, c.a[i - 1], G(self.convs[i].weight), accumulate, sc)
+                done(self.convs[i].weight)
+            da = convt_s2(dy, C, C, self.packed[i].phase, C // 2)
+        dz = bn_act_bwd(c.a[0], 64, None, None, ACT_LEAKY, da, 64, 0, None, 0, 0, False, 0, None, None, False, sc)
+        if G is not None:
+            call("b200_wgrad_c1", ptr(dz), B, R // 2, R // 2, 64, 64, ptr(c.x), ptr(c.xmul), ptr(sc.c1_partial), ptr(G(self.convs[0].weight)), acc, stream())
+            done(self.convs[0].weight)
+        dx = None
+        if input_grad:
+            dx = _empty((B, 1, R, R), f32, dev)
+            call("b200_convt_c1_fwd", ptr(dz), B, R // 2, R // 2, 64, 64, ptr(self.convs[0].weight.data), None, ACT_NONE, None, ptr(c.xmul), ptr(dx), None, stream())
+        return dx

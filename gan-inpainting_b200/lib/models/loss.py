@@ -1,0 +1,101 @@
+"""Drop-in ``lib.models.loss`` (reference lib/models/loss.py:11-47): ``RMSELoss`` and ``LocalLoss`` as fused CUDA
+reductions with hand-written backward kernels (csrc/losses.cu).
+
+The perceptual / style / TV losses of loss.py:49-151 need downloaded VGG19 weights and contribute no gradient
+(they run under ``no_grad`` on detached tensors); they are outside the hot path.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from ... import _lib
+from ...engine import Scratch
+from ..._lib import call, ptr, stream
+
+RECON_L1, RECON_RMSE, RECON_LOCAL_L1, RECON_LOCAL_MSE, RECON_MASKED_RMSE = 0, 1, 2, 3, 4
+
+
+def _check(*ts):
+    n = ts[0].numel()
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise _lib.B200Error("loss kernels run on CUDA tensors only; there is no CPU fallback")
+        if t.numel() != n:
+            raise _lib.B200Error(f"shape mismatch in loss inputs: {[tuple(x.shape) for x in ts if x is not None]}")
+    if n % 4:
+        raise _lib.B200Error("loss inputs must hold a multiple of 4 elements")
+
+
+class _ReconFunction(torch.autograd.Function):
+    """loss(first, second[, mask]) for the symmetric kinds of csrc/losses.cu; d/d(first) and d/d(second) by one
+    elementwise kernel each (roles swapped)."""
+
+    @staticmethod
+    def forward(ctx, kind, first, second, mask, eps):
+        a = first.detach().contiguous().float()
+        b = second.detach().contiguous().float()
+        m = None if mask is None else mask.detach().contiguous().float()
+        _check(a, b, m)
+        out = torch.empty(4, dtype=torch.float32, device=a.device)
+        call("b200_recon_loss", kind, ptr(a), ptr(b), ptr(m), a.numel(), float(eps), ptr(Scratch.get(a.device).recon), ptr(out), stream())
+        ctx.kind, ctx.a, ctx.b, ctx.m, ctx.out = kind, a, b, m, out
+        ctx.shapes = (first.shape, second.shape)
+        return out[0].clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        gout = gout.contiguous().float()
+        res = [None, None, None, None, None]
+        for slot, (y, yh) in ((1, (ctx.b, ctx.a)), (2, (ctx.a, ctx.b))):
+            if not ctx.needs_input_grad[slot]:
+                continue
+            d = torch.empty_like(yh)
+            call("b200_gstep_seed", ptr(y), ptr(yh), None, ptr(ctx.m), None, None, ctx.kind, 1.0, ptr(ctx.out), -1, 0.0, None, ptr(gout), 0, yh.numel(),
+                 ptr(d), None, None, None, 0, stream())
+            res[slot] = d.view(ctx.shapes[slot - 1])
+        return tuple(res)
+
+
+class RMSELoss(nn.Module):
+    """loss.py:11-19: ``sqrt(mean((yhat - y)**2) + eps)``; eps avoids the infinite derivative of sqrt at 0."""
+
+    def __init__(self, eps=1e-16):
+        super().__init__()
+        self.eps = eps
+
+    def forward(self, yhat, y):
+        return _ReconFunction.apply(RECON_RMSE, yhat, y, None, self.eps)
+
+
+class LocalLoss(nn.Module):
+    """loss.py:24-47: ``sum(base(y*mask, yhat*mask)) / count(mask != 0)`` — the loss over the pixels a mask touches,
+    micro-averaged.  ``baseloss`` is a loss *class* accepting ``reduction='none'`` (``nn.L1Loss`` or ``nn.MSELoss``);
+    like in the reference, ``LocalLoss(RMSELoss)`` raises ``TypeError`` because ``RMSELoss.__init__`` takes no
+    ``reduction`` argument."""
+
+    def __init__(self, baseloss, eps=1e-16):
+        super().__init__()
+        self.loss = baseloss(reduction="none")
+        if isinstance(self.loss, nn.L1Loss):
+            self._kind = RECON_LOCAL_L1
+        elif isinstance(self.loss, nn.MSELoss):
+            self._kind = RECON_LOCAL_MSE
+        else:
+            raise NotImplementedError("LocalLoss supports nn.L1Loss and nn.MSELoss bases")
+        self.eps = eps
+
+    def forward(self, yhat, y, mask):
+        return _ReconFunction.apply(self._kind, y, yhat, mask, self.eps)
+
+    @staticmethod
+    def affected_pixels(yhat, y, mask) -> int:
+        """Exact ``(mask != 0)`` pixel count as computed by the kernel (bit-exact parity check)."""
+        a, b, m = y.detach().contiguous().float(), yhat.detach().contiguous().float(), mask.detach().contiguous().float()
+        _check(a, b, m)
+        out = torch.empty(4, dtype=torch.float32, device=a.device)
+        call("b200_recon_loss", RECON_LOCAL_L1, ptr(a), ptr(b), ptr(m), a.numel(), 0.0, ptr(Scratch.get(a.device).recon), ptr(out), stream())
+        words = out.view(torch.int32)[2:4].tolist()
+        return int(words[0]) + (int(words[1]) << 31)

@@ -1,0 +1,322 @@
+"""The per-batch train step of the reference's experiment scripts, as one stream of CUDA kernels.
+
+Three recipes:
+
+* ``wgan``         experiment_list/wgan_l1.py:110-186 (recon 'l1') / wgan_rmse.py (recon 'rmse'):
+                   ceil(mask) -> mask out -> G -> composite -> D step (mean heads, seeds +1/-1, RMSprop, clip
+                   to [-0.01, 0.01]) -> every K-th batch the G step (frozen D, adv + recon, RMSprop).
+* ``minimax``      experiment_list/minimaxgan_rmse.py:110-173 (recon 'rmse') / minimaxgan_l1.py (recon 'l1'):
+                   same prologue, BCE heads on sigmoid outputs, Adam(2e-4, (0.5, 0.999)), G step every batch.
+* ``global_local`` experiment_list/experiment1_global_local_D.py:139-200: G step first (no composite, mask not
+                   ceil'ed, LSGAN heads of a global and a local discriminator, 300*RMSE + 300*masked RMSE), then one
+                   D step over both discriminators with a single Adam.
+
+Unlike the module API (``lib.models.networks`` + autograd) this path uses no autograd at all: the engines' forward
+and backward are called directly, gradients land in the flat gradient buffers of ``optim.flatten_parameters``, the
+optimizers are single fused launches, and the logged scalars are written by the kernels into ONE device vector that
+is read back with one copy per step (instead of the reference's ~8 + 34 ``.item()`` syncs).
+
+Data parallelism (``world_size > 1``, one process per GPU): gradients are summed with NCCL all-reduces over
+slices ("buckets") of the flat gradient buffer, issued on a side stream as soon as the backward pass has moved
+past a bucket, so the transfer overlaps the remaining backward kernels.  BatchNorm statistics stay per replica
+(stock DistributedDataParallel semantics).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib, optim
+from ._lib import call, ptr, stream
+from .engine import Scratch
+
+ADV_WGAN, ADV_BCE, ADV_LSGAN = 0, 1, 2
+RECON_L1, RECON_RMSE, RECON_LOCAL_L1, RECON_LOCAL_MSE, RECON_MASKED_RMSE = 0, 1, 2, 3, 4
+
+# slots of the per-step scalar vector
+SLOTS = ["d_loss_real", "d_loss_fake", "g_adv", "g_adv_local", "d_loss_real_local", "d_loss_fake_local"]
+RECON_SLOT = 8      # 4 floats: loss, denom, exact count (2 words)
+RECON2_SLOT = 12    # second reconstruction term (global_local)
+NSCALARS = 16
+
+
+class GradBucketer:
+    """Bucketed, overlapped gradient all-reduce over a flat gradient buffer whose tensors complete in descending
+    address order during backward (decoder outermost..innermost, then encoder innermost..outermost)."""
+
+    def __init__(self, group: optim.FlatGroup, bucket_mb: float = 25.0, process_group=None):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group)
+        self.group = group
+        self.bucket_elems = max(1, int(bucket_mb * (1 << 20) / 4))
+        self.comm = torch.cuda.Stream()
+        self.off_of = {id(p): o for p, o in zip(group.members, group.offsets)}
+        self.reset()
+
+    def reset(self):
+        self.hi = self.group.numel      # everything in [hi, numel) has been handed to NCCL
+        self.lo = self.group.numel      # everything in [lo, numel) is complete on the compute stream
+        self.launched = 0
+
+    def ready(self, p):
+        """Called right after the kernels producing ``p.grad`` were enqueued."""
+        self.lo = min(self.lo, self.off_of[id(p)])
+        if self.hi - self.lo >= self.bucket_elems:
+            self._launch(self.lo)
+
+    def _launch(self, lo):
+        if lo >= self.hi:
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(ev)
+            self.dist.all_reduce(self.group.grads[lo : self.hi], op=self.dist.ReduceOp.AVG, group=self.pg)
+        self.hi = lo
+        self.launched += 1
+
+    def finish(self):
+        """Flush the remaining range and make the compute stream wait for all reductions; grads hold the MEAN over ranks."""
+        self._launch(0)
+        torch.cuda.current_stream().wait_stream(self.comm)
+        n = self.launched
+        self.reset()
+        return n
+
+
+class InpaintingTrainer:
+    def __init__(self, recipe: str, net_G, net_D, net_D_local=None, recon: str = "l1", lambdas=(300.0, 300.0), clip: float = 0.01,
+                 distributed: bool = False, bucket_mb: float = 25.0, log_grad_means: bool = False):
+        if recipe not in ("wgan", "minimax", "global_local"):
+            raise ValueError(recipe)
+        if recipe == "global_local" and net_D_local is None:
+            raise ValueError("global_local needs a local discriminator")
+        self.recipe, self.recon = recipe, {"l1": RECON_L1, "rmse": RECON_RMSE}[recon]
+        self.G, self.D, self.Dl = net_G, net_D, net_D_local
+        self.lambdas, self.clip = lambdas, clip
+        self.eG, self.eD = net_G._get_engine(), net_D._get_engine()
+        self.eDl = net_D_local._get_engine() if net_D_local is not None else None
+        self.fG = optim.flatten_parameters(net_G)
+        self.fD = optim.flatten_parameters(net_D)
+        self.fDl = optim.flatten_parameters(net_D_local) if net_D_local is not None else None
+        dev = self.fG.params.device
+        self.device = dev
+        if recipe == "wgan":  # wgan_l1.py:64-65 + :152-153
+            self.optG = optim.RMSprop(net_G.parameters(), lr=0.00005)
+            self.optD = optim.RMSprop(net_D.parameters(), lr=0.00005, clip=(-clip, clip))
+            self.sigmoid, self.adv = False, ADV_WGAN
+        elif recipe == "minimax":  # minimaxgan_rmse.py:64-65
+            self.optG = optim.Adam(net_G.parameters(), lr=0.0002, betas=(0.5, 0.999))
+            self.optD = optim.Adam(net_D.parameters(), lr=0.0002, betas=(0.5, 0.999))
+            self.sigmoid, self.adv = True, ADV_BCE
+        else:  # experiment1_global_local_D.py:122-123
+            self.optG = optim.Adam(net_G.parameters(), lr=0.0002, betas=(0.5, 0.999))
+            self.optD = optim.Adam(list(net_D_local.parameters()) + list(net_D.parameters()), lr=0.0002, betas=(0.5, 0.999))
+            self.sigmoid, self.adv = True, ADV_LSGAN
+        self.scalars = torch.zeros(NSCALARS, dtype=torch.float32, device=dev)
+        self.step_count = 0
+        self.world = 1
+        self.buckets: Dict[int, GradBucketer] = {}
+        if distributed:
+            import torch.distributed as dist
+
+            self.world = dist.get_world_size()
+            for fg in (self.fG, self.fD, self.fDl):
+                if fg is not None:
+                    dist.broadcast(fg.params, src=0)
+                    self.buckets[id(fg)] = GradBucketer(fg, bucket_mb)
+            for net in (net_G, net_D, net_D_local):
+                if net is not None:
+                    for b in net.buffers():
+                        dist.broadcast(b, src=0)
+            _lib.WEIGHT_EPOCH += 1
+        self.log_grad_means = log_grad_means
+        self.grad_means: Dict[str, torch.Tensor] = {}
+        self._abs = {}
+        self.kernel_launches_hint = 0
+
+    # ------------------------------------------------------------------------------------------ helpers
+    def _slot(self, name_or_index):
+        i = SLOTS.index(name_or_index) if isinstance(name_or_index, str) else name_or_index
+        return ctypes_ptr(self.scalars, i)
+
+    def _adv(self, ctx, target, scale, slot):
+        """Adversarial head on a discriminator context -> gradient w.r.t. the pre-sigmoid output."""
+        dpred = torch.empty((ctx.B,), dtype=torch.float32, device=self.device)
+        call("b200_adv_loss", ptr(ctx.pred), ctx.B, self.adv, float(target), float(scale), self._slot(slot), ptr(dpred), stream())
+        if not self.sigmoid:
+            return dpred
+        dlin = torch.empty_like(dpred)
+        call("b200_head_dlin", ptr(dpred), ptr(ctx.pred), 1, ctx.B, ptr(dlin), stream())
+        return dlin
+
+    def _reduce(self, fg, hooked: bool):
+        if self.world == 1:
+            return
+        b = self.buckets[id(fg)]
+        if not hooked:
+            b.lo = 0
+        b.finish()
+
+    def _grad_log(self, tag, fg):
+        if not self.log_grad_means:
+            return
+        if tag not in self._abs:
+            names, spans = fg.logging_offsets()
+            # one block per tensor over [start, end): encode as consecutive (start, end) pairs with zero-length gaps
+            flat = []
+            for a, b in spans:
+                flat += [a, b]
+            self._abs[tag] = (names, torch.tensor(flat, dtype=torch.int64, device=self.device), torch.zeros(2 * len(spans), dtype=torch.float32, device=self.device))
+        names, offs, out = self._abs[tag]
+        call("b200_absmean", ptr(fg.grads), ptr(offs), 2 * len(names) - 1, ptr(out), stream())
+        self.grad_means[tag] = (names, out)
+
+    def grad_means_host(self, tag):
+        names, out = self.grad_means[tag]
+        vals = out.tolist()
+        return {n: vals[2 * i] for i, n in enumerate(names)}
+
+    # ------------------------------------------------------------------------------------------ the step
+    @torch.no_grad()
+    def step(self, ground: torch.Tensor, mask: torch.Tensor, update_g: bool = True, seed: Optional[int] = None):
+        """One batch.  ``ground`` / ``mask``: fp32 CUDA [B,1,R,R].  Returns the device scalar vector (see ``read_scalars``)."""
+        if not (ground.is_cuda and mask.is_cuda):
+            raise _lib.B200Error("the train step runs on CUDA tensors only")
+        self.step_count += 1
+        seed = self.step_count if seed is None else seed
+        if self.recipe == "global_local":
+            return self._step_global_local(ground.contiguous().float(), mask.contiguous().float(), seed)
+        return self._step_gan(ground.contiguous().float(), mask.contiguous().float(), update_g, seed)
+
+    def _step_gan(self, ground, mask, update_g, seed):
+        G, D, eG, eD, dev = self.G, self.D, self.eG, self.eD, self.device
+        n = ground.numel()
+        B = ground.shape[0]
+        sc = Scratch.get(dev)
+        # ---- prologue: wgan_l1.py:113-122
+        mask_c = torch.empty_like(mask)
+        masked = torch.empty_like(ground)
+        call("b200_mask_prepare", ptr(ground), ptr(mask), n, 1, ptr(mask_c), ptr(masked), stream())
+        cG = eG.forward(masked, True, comp_base=masked, comp_mul=mask_c, seed=seed)
+        inpainted = cG.comp
+        # ---- D step: :128-153
+        gD = self.fD.grad_map()
+        hook = self.buckets.get(id(self.fD))
+        cR = eD.forward(ground, True, self.sigmoid)
+        if self.recipe == "wgan":
+            cF = eD.forward(inpainted, True, self.sigmoid)
+            eD.backward(cR, self._adv(cR, 1.0, 1.0, "d_loss_real"), gD, accumulate=False)
+            eD.backward(cF, self._adv(cF, 0.0, -1.0, "d_loss_fake"), gD, accumulate=True, on_ready=hook.ready if hook else None)
+        else:  # minimaxgan_rmse.py:129-148: forward/backward real, then forward/backward fake
+            eD.backward(cR, self._adv(cR, 1.0, 1.0, "d_loss_real"), gD, accumulate=False)
+            cF = eD.forward(inpainted, True, self.sigmoid)
+            eD.backward(cF, self._adv(cF, 0.0, 1.0, "d_loss_fake"), gD, accumulate=True, on_ready=hook.ready if hook else None)
+        self._reduce(self.fD, hooked=True)
+        self._grad_log("d", self.fD)
+        self.optD.step()
+        eD.refresh_weights(force=True)
+        # ---- G step: :169-186
+        if update_g:
+            cA = eD.forward(inpainted, True, self.sigmoid)
+            dadv = eD.backward(cA, self._adv(cA, 1.0, 1.0, "g_adv"), None, input_grad=True)
+            call("b200_recon_loss", self.recon, ptr(ground), ptr(inpainted), None, n, 1e-16, ptr(sc.recon), self._slot(RECON_SLOT), stream())
+            dpre = torch.empty_like(ground)
+            gG = self.fG.grad_map()
+            bias = eG.uc[0].bias
+            call("b200_gstep_seed", ptr(ground), ptr(inpainted), ptr(cG.g_out), ptr(mask_c), ptr(dadv), None, self.recon, 1.0, self._slot(RECON_SLOT), -1, 0.0,
+                 None, None, 1, n, ptr(dpre), None, ptr(sc.recon), ptr(gG[id(bias)]), 0, stream())
+            hook = self.buckets.get(id(self.fG))
+            if hook:
+                hook.ready(bias)
+            eG.backward(cG, dpre, gG, accumulate=False, on_ready=hook.ready if hook else None)
+            self._reduce(self.fG, hooked=True)
+            self._grad_log("g", self.fG)
+            self.optG.step()
+            eG.refresh_weights(force=True)
+        self.last = dict(inpainted=inpainted, g_out=cG.g_out, mask=mask_c)
+        return self.scalars
+
+    def _step_global_local(self, ground, mask, seed):
+        eG, eD, eDl, dev = self.eG, self.eD, self.eDl, self.device
+        n = ground.numel()
+        sc = Scratch.get(dev)
+        l1, l2 = self.lambdas
+        masked = torch.empty_like(ground)
+        call("b200_mask_prepare", ptr(ground), ptr(mask), n, 0, None, ptr(masked), stream())  # mask is NOT ceil'ed (:142)
+        # ---- G step (:150-172), discriminators frozen
+        cG = eG.forward(masked, True, seed=seed)
+        inp = cG.g_out
+        cg = eD.forward(inp, True, True)
+        cl = eDl.forward(inp, True, True, xmul=mask)
+        dg = eD.backward(cg, self._adv(cg, 1.0, 1.0, "g_adv"), None, input_grad=True)
+        dl = eDl.backward(cl, self._adv(cl, 1.0, 1.0, "g_adv_local"), None, input_grad=True)
+        call("b200_recon_loss", RECON_RMSE, ptr(ground), ptr(inp), None, n, 1e-16, ptr(sc.recon), self._slot(RECON_SLOT), stream())
+        call("b200_recon_loss", RECON_MASKED_RMSE, ptr(ground), ptr(inp), ptr(mask), n, 1e-16, ptr(sc.recon), self._slot(RECON2_SLOT), stream())
+        dpre = torch.empty_like(ground)
+        gG = self.fG.grad_map()
+        bias = eG.uc[0].bias
+        call("b200_gstep_seed", ptr(ground), ptr(inp), ptr(cG.g_out), ptr(mask), ptr(dg), ptr(dl), RECON_RMSE, float(l1), self._slot(RECON_SLOT), RECON_MASKED_RMSE,
+             float(l2), self._slot(RECON2_SLOT), None, 0, n, ptr(dpre), None, ptr(sc.recon), ptr(gG[id(bias)]), 0, stream())
+        hook = self.buckets.get(id(self.fG))
+        if hook:
+            hook.ready(bias)
+        eG.backward(cG, dpre, gG, accumulate=False, on_ready=hook.ready if hook else None)
+        self._reduce(self.fG, hooked=True)
+        self._grad_log("g", self.fG)
+        self.optG.step()
+        eG.refresh_weights(force=True)
+        # ---- D step (:178-200): four forwards, one summed loss, one Adam over chain(Dl, Dg)
+        gD, gDl = self.fD.grad_map(), self.fDl.grad_map()
+        c1 = eD.forward(ground, True, True)
+        c2 = eD.forward(inp, True, True)
+        c3 = eDl.forward(ground, True, True, xmul=mask)
+        c4 = eDl.forward(inp, True, True, xmul=mask)
+        hg, hl = self.buckets.get(id(self.fD)), self.buckets.get(id(self.fDl))
+        eDl.backward(c3, self._adv(c3, 1.0, 1.0, "d_loss_real_local"), gDl, accumulate=False)
+        eDl.backward(c4, self._adv(c4, 0.0, 1.0, "d_loss_fake_local"), gDl, accumulate=True, on_ready=hl.ready if hl else None)
+        eD.backward(c1, self._adv(c1, 1.0, 1.0, "d_loss_real"), gD, accumulate=False)
+        eD.backward(c2, self._adv(c2, 0.0, 1.0, "d_loss_fake"), gD, accumulate=True, on_ready=hg.ready if hg else None)
+        self._reduce(self.fDl, hooked=True)
+        self._reduce(self.fD, hooked=True)
+        self._grad_log("d", self.fD)
+        self._grad_log("d_local", self.fDl)
+        self.optD.step()
+        eD.refresh_weights(force=True)
+        eDl.refresh_weights(force=True)
+        self.last = dict(inpainted=inp, g_out=cG.g_out, mask=mask)
+        return self.scalars
+
+    # ------------------------------------------------------------------------------------------ reporting
+    def read_scalars(self) -> Dict[str, float]:
+        """ONE device->host copy of everything the reference logs per batch."""
+        v = self.scalars.tolist()
+        out = {k: v[i] for i, k in enumerate(SLOTS)}
+        out["recon"] = v[RECON_SLOT]
+        out["recon_local"] = v[RECON2_SLOT]
+        if self.recipe == "global_local":
+            out["g_loss"] = out["g_adv"] + out["g_adv_local"] + self.lambdas[0] * out["recon"] + self.lambdas[1] * out["recon_local"]
+            out["d_loss"] = out["d_loss_real"] + out["d_loss_fake"] + out["d_loss_real_local"] + out["d_loss_fake_local"]
+        else:
+            out["g_loss"] = out["g_adv"] + out["recon"]
+            out["d_loss"] = out["d_loss_real"] - out["d_loss_fake"] if self.recipe == "wgan" else out["d_loss_real"] + out["d_loss_fake"]
+        return out
+
+    @torch.no_grad()
+    def inpaint(self, ground: torch.Tensor, mask: torch.Tensor, train_mode: bool = False):
+        """Inference (config 5; visualize.py:69-76, evaluate.py:127-136): ceil -> mask out -> G -> composite."""
+        ground, mask = ground.contiguous().float(), mask.contiguous().float()
+        mask_c, masked = torch.empty_like(mask), torch.empty_like(ground)
+        call("b200_mask_prepare", ptr(ground), ptr(mask), ground.numel(), 1, ptr(mask_c), ptr(masked), stream())
+        c = self.eG.forward(masked, train_mode, comp_base=masked, comp_mul=mask_c, keep=False)
+        return c.comp
+
+
+def ctypes_ptr(t: torch.Tensor, index: int):
+    import ctypes
+
+    return ctypes.c_void_p(t.data_ptr() + index * t.element_size())
