@@ -127,6 +127,8 @@ class _UnetFunction(torch.autograd.Function):
         eng = net._get_engine()
         c = eng.forward(x.detach().contiguous().float(), net.training, seed=net._next_seed())
         ctx.net, ctx.c = net, c
+        if net.keep_last_context:
+            object.__setattr__(net, "_last_ctx", c)
         return c.g_out.view(x.shape[0], 1, x.shape[-2], x.shape[-1])
 
     @staticmethod
@@ -170,6 +172,7 @@ class UnetGenerator(nn.Module):
         object.__setattr__(self, "_engine", None)
         object.__setattr__(self, "_calls", 0)
         self.dropout_seed = 0x5EED
+        self.keep_last_context = False  # debugging / parity tests: keep the activations of the last forward in _last_ctx
 
     # ---- engine plumbing
     def _levels(self):
@@ -225,6 +228,8 @@ class _PatchGANFunction(torch.autograd.Function):
         eng = net._get_engine()
         c = eng.forward(x.detach().contiguous().float(), net.training, net._sigmoid)
         ctx.net, ctx.c = net, c
+        if net.keep_last_context:
+            object.__setattr__(net, "_last_ctx", c)
         return c.pred
 
     @staticmethod
@@ -262,6 +267,7 @@ class PatchGANDiscriminator(nn.Module):
             layers.append(nn.Sigmoid())
         self.model = nn.Sequential(*layers)
         object.__setattr__(self, "_sigmoid", bool(sigmoid))
+        self.keep_last_context = False
         object.__setattr__(self, "_c", c)
         object.__setattr__(self, "_engine", None)
 

@@ -53,12 +53,15 @@ class GradBucketer:
         self.world = dist.get_world_size(process_group)
         self.group = group
         self.bucket_elems = max(1, int(bucket_mb * (1 << 20) / 4))
-        self.comm = torch.cuda.Stream()
+        self.cuda = group.grads.is_cuda
+        self.comm = torch.cuda.Stream() if self.cuda else None
+        # NCCL averages inside the collective; other backends (the gloo CPU tests) sum and scale afterwards
+        self.avg = dist.get_backend(process_group) == "nccl"
         self.off_of = {id(p): o for p, o in zip(group.members, group.offsets)}
         self.reset()
 
     def reset(self):
-        self.hi = self.group.numel      # everything in [hi, numel) has been handed to NCCL
+        self.hi = self.group.numel      # everything in [hi, numel) has been handed to the collective
         self.lo = self.group.numel      # everything in [lo, numel) is complete on the compute stream
         self.launched = 0
 
@@ -68,21 +71,33 @@ class GradBucketer:
         if self.hi - self.lo >= self.bucket_elems:
             self._launch(self.lo)
 
+    def _reduce(self, t):
+        if self.avg:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.AVG, group=self.pg)
+        else:
+            self.dist.all_reduce(t, group=self.pg)
+            t.mul_(1.0 / self.world)
+
     def _launch(self, lo):
         if lo >= self.hi:
             return
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream())
-        with torch.cuda.stream(self.comm):
-            self.comm.wait_event(ev)
-            self.dist.all_reduce(self.group.grads[lo : self.hi], op=self.dist.ReduceOp.AVG, group=self.pg)
+        bucket = self.group.grads[lo : self.hi]
+        if self.cuda:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm):
+                self.comm.wait_event(ev)
+                self._reduce(bucket)
+        else:
+            self._reduce(bucket)
         self.hi = lo
         self.launched += 1
 
     def finish(self):
         """Flush the remaining range and make the compute stream wait for all reductions; grads hold the MEAN over ranks."""
         self._launch(0)
-        torch.cuda.current_stream().wait_stream(self.comm)
+        if self.cuda:
+            torch.cuda.current_stream().wait_stream(self.comm)
         n = self.launched
         self.reset()
         return n
@@ -238,7 +253,7 @@ class InpaintingTrainer:
             self._grad_log("g", self.fG)
             self.optG.step()
             eG.refresh_weights(force=True)
-        self.last = dict(inpainted=inpainted, g_out=cG.g_out, mask=mask_c)
+        self.last = dict(inpainted=inpainted, g_out=cG.g_out, mask=mask_c, ctx=dict(G=cG, Dreal=cR, Dfake=cF, Dgen=cA if update_g else None))
         return self.scalars
 
     def _step_global_local(self, ground, mask, seed):
@@ -288,7 +303,7 @@ class InpaintingTrainer:
         self.optD.step()
         eD.refresh_weights(force=True)
         eDl.refresh_weights(force=True)
-        self.last = dict(inpainted=inp, g_out=cG.g_out, mask=mask)
+        self.last = dict(inpainted=inp, g_out=cG.g_out, mask=mask, ctx=dict(G=cG, DgGen=cg, DlGen=cl, DgReal=c1, DgFake=c2, DlReal=c3, DlFake=c4))
         return self.scalars
 
     # ------------------------------------------------------------------------------------------ reporting

@@ -1,0 +1,173 @@
+/*
+ * b200_inpaint.h — C ABI of libb200inpaint.so: the sm_100a kernels behind the GAN-inpainting train step.
+ *
+ * The reference (abeytheo/gan-inpainting) has no FFI: its hot path sits behind the Python nn.Module protocol
+ * (lib/models/networks.py, lib/models/loss.py) and calls ATen ops (cuDNN / MKL-DNN).  Each entry point below
+ * replaces the ATen work of the reference call sites it cites (file:line into the reference tree) and is bound
+ * from Python with ctypes (gan-inpainting_b200/_lib.py); INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated; `stream` is a cudaStream_t.
+ *   - activations are NHWC bf16 ("bf16*" = const void* / void* here), the 1-channel images and all weights,
+ *     gradients of weights, statistics and scalars are fp32.
+ *   - every function returning int returns 0 on success, otherwise B200_ERR_* and b200_last_error() describes it.
+ *   - nothing allocates device memory; scratch buffers are caller-provided (sizes stated per function).
+ */
+#ifndef B200_INPAINT_H
+#define B200_INPAINT_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* b200_stream_t; /* == cudaStream_t */
+
+#define B200_OK 0
+#define B200_ERR_ARG 1
+#define B200_ERR_CUDA 2
+#define B200_ERR_DRIVER 3
+
+/* activation codes */
+#define B200_ACT_NONE 0
+#define B200_ACT_LEAKY 1 /* LeakyReLU(0.2)  networks.py:287, 338 */
+#define B200_ACT_RELU 2  /* ReLU            networks.py:289 */
+#define B200_ACT_TANH 3  /* Tanh            networks.py:297 */
+
+/* reconstruction-loss kinds */
+#define B200_RECON_L1 0          /* nn.L1Loss()                       wgan_l1.py:62,180 */
+#define B200_RECON_RMSE 1        /* RMSELoss                          loss.py:11-19 */
+#define B200_RECON_LOCAL_L1 2    /* LocalLoss(nn.L1Loss)              loss.py:24-47 */
+#define B200_RECON_LOCAL_MSE 3   /* LocalLoss(nn.MSELoss)             loss.py:24-47 */
+#define B200_RECON_MASKED_RMSE 4 /* RMSELoss(mask*y, mask*yhat)       experiment1_global_local_D.py:167 */
+
+/* adversarial heads */
+#define B200_ADV_WGAN 0  /* torch.mean(pred)                  wgan_l1.py:137-143,177 */
+#define B200_ADV_BCE 1   /* nn.BCELoss vs constant target     minimaxgan_rmse.py:61,135,141,162 */
+#define B200_ADV_LSGAN 2 /* nn.MSELoss vs constant target     experiment1_global_local_D.py:119,162-163 */
+
+int b200_abi_version(void);
+const char* b200_last_error(void); /* thread-local, host string */
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * tcgen05 implicit-GEMM convolutions (csrc/conv_gemm.cu).  4x4 kernel, stride 2, padding 1; TMA-staged NHWC bf16
+ * tiles, fp32 accumulation in TMEM.  H, W powers of two; Cin % 64 == 0; Cout % 16 == 0; bn_hint / stages 0 = auto.
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* nn.Conv2d(Cin, Cout, 4, 2, 1, bias=False) forward — networks.py:285-286 (generator d2..d7), :340-348 (PatchGAN c2..c4);
+ * also the data gradient of nn.ConvTranspose2d.  x [B,H,W,Cin]; wpk [Cout][16*Cin] from b200_pack_gather;
+ * y [B,H/2,W/2,*] with pixel stride ldy. */
+int b200_conv_s2_gemm(const void* x, int B, int H, int W, int Cin, const void* wpk, int Cout, void* y, int ldy, int bn_hint, int stages,
+                      b200_stream_t stream);
+
+/* nn.ConvTranspose2d(Cin, Cout, 4, 2, 1, bias=False) forward as 4 sub-pixel phases — networks.py:300-309 (u7..u2);
+ * also the data gradient of nn.Conv2d.  z [B,Hi,Wi,*] with pixel stride ldz; wpk [4][Cout][4*Cin] from b200_pack_phase;
+ * y [B,2Hi,2Wi,*] with pixel stride ldy. */
+int b200_convt_s2_gemm(const void* z, int B, int Hi, int Wi, int Cin, int ldz, const void* wpk, int Cout, void* y, int ldy, int bn_hint, int stages,
+                       b200_stream_t stream);
+
+/* Weight gradient of both layer kinds (autograd of the call sites above; wgan_l1.py:138,141,183):
+ *   partial[s][cs][(kh*4+kw)*Cl + cl] = sum over the pixels of split s of S[b,i,j,cs] * L[b,2i+kh-1,2j+kw-1,cl]
+ * S [B,Hs,Ws,*] (pixel stride lds, Cs % 128 == 0) is the low-resolution tensor (Conv2d: dy; ConvTranspose2d: input),
+ * L [B,2Hs,2Ws,Cl] dense the high-resolution one.  *splits_io: requested split count in, used count out.
+ * partial: (*splits_io) * Cs * 16 * Cl floats.  Reduce with b200_wgrad_reduce. */
+int b200_wgrad_gemm(const void* S, int B, int Hs, int Ws, int Cs, int lds, const void* L, int Cl, void* partial, int* splits_io, int bn_hint, int stages,
+                    b200_stream_t stream);
+
+/* bring-up aid: raw shared-memory image of one TMA box */
+int b200_debug_tma_probe(const void* x, int B, int H, int W, int C, int kind, int tw, int th, int nb, int c0, int c1, int c2, int c3, int c4, void* out,
+                         b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * weight layouts (csrc/pack.cu).  w is the fp32 checkpoint tensor [D0][D1][4][4]
+ * (Conv2d: D0 = Cout, D1 = Cin; ConvTranspose2d: D0 = Cin, D1 = Cout — SURVEY.md §2.1 state_dict contract).
+ * ------------------------------------------------------------------------------------------------------------------ */
+int b200_pack_gather(const float* w, int D0, int D1, void* out /* bf16 [D0][16*D1] */, b200_stream_t stream);
+int b200_pack_phase(const float* w, int D0, int D1, void* out /* bf16 [4][D1][4*D0] */, b200_stream_t stream);
+/* grad[cs][cl][kh][kw] (+)= sum_s partial[s][cs][(kh*4+kw)*Cl + cl]   (deterministic split reduction) */
+int b200_wgrad_reduce(const float* partial, int splits, int Cs, int Cl, float* grad, int accumulate, b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * BatchNorm2d (training / eval) + activation (csrc/norm_act.cu) — nn.BatchNorm2d networks.py:38, 341-349;
+ * LeakyReLU / ReLU prologues and the post-LeakyReLU skip tensor networks.py:287-289, 320-324;
+ * Dropout(0.5) networks.py:313-314.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int b200_bn_stat_blocks(long long P, int C); /* partial buffer holds b200_bn_stat_blocks(P, C) * 2 * C floats */
+
+/* batch statistics of y [P][C] bf16 -> stats_out[4][C] = mean, rstd, scale = gamma*rstd, shift = beta - mean*scale;
+ * running_mean / running_var / num_batches_tracked (int64) updated in place when non-null (momentum, unbiased var). */
+int b200_bn_stats(const void* y, long long P, int C, void* partial, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                  long long* num_batches_tracked, float momentum, float eps, float* stats_out, b200_stream_t stream);
+int b200_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps, float* stats_out,
+                        b200_stream_t stream);
+/* out1[pix*ld1 + off1 + c] = act(dropout(y*scale + shift)); out2 = relu(out1) (the concat half).  scale null = identity. */
+int b200_bn_act(const void* y, long long P, int C, const float* scale, const float* shift, int act, void* out1, int ld1, int off1, void* out2, int ld2,
+                int off2, int dropout, unsigned seed, b200_stream_t stream);
+/* backward of (BN ->) [dropout ->] act with up to two incoming gradients (g2 = skip gradient through ReLU);
+ * stats non-null = training-mode BN (dgamma / dbeta written or accumulated); coef: 3*C floats scratch. */
+int b200_bn_act_bwd(const void* y, long long P, int C, const float* stats, const float* gamma, int act, const void* g1, int ldg1, int offg1, const void* g2,
+                    int ldg2, int offg2, int dropout, unsigned seed, void* partial, float* coef, float* dgamma, float* dbeta, int accumulate, void* dy,
+                    b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * layers with one channel on one side + the discriminator head (csrc/conv_direct.cu)
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* nn.Conv2d(1, C, 4, 2, 1) forward — networks.py:296 (d1), :337 (c1) — x [B,H,W] fp32 (times xmul if non-null: the
+ * local discriminator's mask, experiment1_global_local_D.py:157); y [B,H/2,W/2,C] bf16; y2 = relu copy (concat half).
+ * Also the data gradient of the last ConvTranspose2d(128, 1). */
+int b200_conv_c1_fwd(const float* x, const float* xmul, int B, int H, int W, const float* w, int C, int act, void* y, void* y2, int ld2, int off2,
+                     b200_stream_t stream);
+/* nn.ConvTranspose2d(C, 1, 4, 2, 1) (+bias, Tanh) forward — networks.py:293-297 (u1) — z [B,H,W,*] bf16 -> y [B,2H,2W] fp32;
+ * comp non-null: comp = base + y*mul, the composite `masked + G(masked)*mask` of wgan_l1.py:122.
+ * Also the data gradient of c1 (then y *= mul if mul non-null). */
+int b200_convt_c1_fwd(const void* z, int B, int H, int W, int C, int ldz, const float* w, const float* bias, int act, const float* base, const float* mul,
+                      float* y, float* comp, b200_stream_t stream);
+int b200_wgrad_c1_blocks(void); /* partial: b200_wgrad_c1_blocks() * C * 16 floats */
+/* dw[c][kh*4+kw] (+)= sum z[b,i,j,c] * g[b,2i+kh-1,2j+kw-1] (* gmul) — weight gradient of both kinds above */
+int b200_wgrad_c1(const void* z, int B, int H, int W, int C, int ldz, const float* g, const float* gmul, float* partial, float* dw, int accumulate,
+                  b200_stream_t stream);
+/* Conv2d(512,1,4,1,0) -> Flatten -> Linear(n*n,1) [-> Sigmoid] — networks.py:352-357 — as one dot product per image with
+ * E[h][w][c] = sum_{kh,kw} w5[c][kh][kw] * wl[(h-kh)*n + (w-kw)], n = S-3. */
+int b200_head_weight(const float* w5, const float* wl, int S, int C, float* E, b200_stream_t stream);
+int b200_head_fwd(const void* a, const float* E, int B, int n, const float* bias, int sigmoid, float* scratch /* 8*B */, float* lin, float* pred,
+                  b200_stream_t stream);
+int b200_head_dlin(const float* dpred, const float* pred, int sigmoid, int B, float* dlin, b200_stream_t stream);
+int b200_head_bwd_input(const float* dlin, const float* E, int B, int n, void* da, b200_stream_t stream);
+int b200_head_bwd_params(const float* dlin, const void* a, int B, int S, int C, const float* w5, const float* wl, float* dE /* S*S*C */, float* dw5,
+                         float* dwl, float* dbias, int accumulate, b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * masks, compositing, losses (csrc/losses.cu)
+ * ------------------------------------------------------------------------------------------------------------------ */
+int b200_recon_scratch_floats(void);
+/* mask_out = do_ceil ? ceil(mask) : mask; masked = ground * (1 - mask_out) — wgan_l1.py:114,117 */
+int b200_mask_prepare(const float* ground, const float* mask, long long n, int do_ceil, float* mask_out, float* masked, b200_stream_t stream);
+/* out = base + g * mask — wgan_l1.py:122 */
+int b200_composite(const float* base, const float* g, const float* mask, long long n, float* out, b200_stream_t stream);
+int b200_mul(const float* a, const float* b, long long n, float* out, b200_stream_t stream);
+/* out[0] = loss, out[1] = denominator (float), out[2..3] = exact denominator as two 31-bit int words */
+int b200_recon_loss(int kind, const float* y, const float* yhat, const float* mask, long long n, float eps, float* scratch, float* out,
+                    b200_stream_t stream);
+/* seed of the generator backward: d_inp = dadv1 + dadv2 + gscale*(lambda1*recon1' + lambda2*recon2');
+ * dpre = (composite ? d_inp*mask : d_inp) * (1 - g^2); dbias (+)= sum dpre.  kind < 0 disables a term. */
+int b200_gstep_seed(const float* ground, const float* inp, const float* g, const float* mask, const float* dadv1, const float* dadv2, int kind1, float lambda1,
+                    const float* loss1, int kind2, float lambda2, const float* loss2, const float* gscale, int composite, long long n, float* dpre, float* dinp,
+                    float* scratch, float* dbias, int accumulate, b200_stream_t stream);
+/* loss_out[0] = head(pred[B]); dpred[b] = scale * d loss / d pred[b] */
+int b200_adv_loss(const float* pred, int B, int mode, float target, float scale, float* loss_out, float* dpred, b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * optimizers (csrc/optim.cu) — optim.RMSprop wgan_l1.py:64-65 (+ clamp :152-153), optim.Adam minimaxgan_rmse.py:64-65,
+ * p.grad.abs().mean() logging wgan_l1.py:195-197
+ * ------------------------------------------------------------------------------------------------------------------ */
+int b200_rmsprop_step(float* p, const float* g, float* sq, long long n, float lr, float alpha, float eps, int clamp, float lo, float hi, b200_stream_t stream);
+int b200_step_inc(int* step_count, b200_stream_t stream);
+int b200_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, const int* step_count,
+                   b200_stream_t stream);
+int b200_clamp(float* p, long long n, float lo, float hi, b200_stream_t stream);
+/* out[t] = mean |g[offsets[t] .. offsets[t+1])|, t < ntensors (offsets: int64[ntensors+1]) */
+int b200_absmean(const float* g, const long long* offsets, int ntensors, float* out, b200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_INPAINT_H */

@@ -24,6 +24,97 @@ import torch.nn.functional as F
 
 Params = Dict[str, torch.Tensor]
 
+
+# ----------------------------------------------------------------------------
+# precision policy (None == the reference's pure fp32 arithmetic)
+# ----------------------------------------------------------------------------
+class _RoundSTE(torch.autograd.Function):
+    """Forward: round to bf16 (the tensor is *stored* in bf16); backward: identity."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class _RoundGrad(torch.autograd.Function):
+    """Forward: identity; backward: round to bf16 (the gradient w.r.t. this tensor is stored in bf16)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(torch.float32)
+
+
+class Fp32Policy:
+    """The reference: nothing is rounded.  ``tag`` names the storage point (see ``TeacherForcedPolicy``)."""
+
+    scope = ""
+
+    def act(self, x, tag=None):
+        return x
+
+    def w(self, x):
+        return x
+
+    def grad(self, x):
+        return x
+
+
+class Bf16Policy(Fp32Policy):
+    """Where the B200 path stores bf16 (DESIGN.md "precision policy"): activations and activation gradients in HBM,
+    and the tensor-core operand copies of the 4x4/s2 GEMM-layer weights.  Accumulation, BatchNorm statistics, the
+    1-channel layers' weights (d1, u1, c1, the discriminator head), losses, weight gradients and optimizer state
+    stay fp32.  Free-running: the same algorithm as the reference evaluated at the CUDA path's precision."""
+
+    def act(self, x, tag=None):
+        return _RoundSTE.apply(x)
+
+    def w(self, x):
+        return _RoundSTE.apply(x)
+
+    def grad(self, x):
+        return _RoundGrad.apply(x)
+
+
+class TeacherForcedPolicy(Fp32Policy):
+    """Checks a device implementation *layer by layer* and its backward pass *at the implementation's own forward
+    state*.  ``stored`` maps storage-point tags ("<scope>/a3", "<scope>/y4", ...) to the tensors the implementation
+    produced (NCHW fp32 copies of its bf16 buffers).  At every storage point the oracle
+
+      1. records rel-L2(implementation tensor, oracle value computed from the implementation's *previous* tensor)
+         in ``self.errors[tag]`` — a one-layer error, no accumulation;
+      2. continues from the implementation's tensor (straight-through substitution), so every ReLU / LeakyReLU /
+         dropout mask and every BatchNorm statistic of the oracle's autograd graph is the implementation's.
+
+    Gradients of that graph are then the exact fp32 vector-Jacobian product of the implementation's forward pass —
+    what its backward kernels must reproduce up to bf16 storage of activation gradients.  This removes the
+    mask-flip noise that makes free-running bf16-vs-fp32 gradient comparisons ill-conditioned."""
+
+    def __init__(self, stored, round_weights=True):
+        self.stored = stored
+        self.errors = {}
+        self.round_weights = round_weights
+        self.scope = ""
+
+    def act(self, x, tag=None):
+        key = f"{self.scope}/{tag}" if self.scope else tag
+        if tag is None or key not in self.stored:
+            return x
+        mine = self.stored[key].to(x.dtype)
+        self.errors[key] = float((mine - x.detach()).norm() / x.detach().norm().clamp_min(1e-30))
+        return x + (mine - x).detach()
+
+    def w(self, x):
+        return _RoundSTE.apply(x) if self.round_weights else x
+
+
 # ----------------------------------------------------------------------------
 # layer specs
 # ----------------------------------------------------------------------------
@@ -187,6 +278,7 @@ def unet_forward(
     num_downs: int = 7,
     dropout_masks: Optional[Dict[int, torch.Tensor]] = None,
     taps: Optional[dict] = None,
+    policy=None,
 ) -> torch.Tensor:
     """UnetGenerator.forward, networks.py:246-253 + 320-324.
 
@@ -194,25 +286,33 @@ def unet_forward(
     kept values are scaled by 2 (Dropout(0.5)).  ``None`` == dropout disabled
     (``use_dropout=False``) — parity runs use that, SURVEY.md D8.
     ``taps``: optional dict filled with named intermediate activations.
+    ``policy``: precision policy (default ``Fp32Policy`` == the reference).
     """
+    P = policy or Fp32Policy()
     skips = []  # post-LeakyReLU encoder activations (what the in-place op leaves in the cat, D9)
     h = x
     for lvl in range(1, num_downs + 1):
         k = unet_keys(lvl, num_downs)
         if lvl > 1:
-            h = F.leaky_relu(h, 0.2)
+            h = P.act(F.leaky_relu(h, 0.2), f"a{lvl - 1}")
             skips.append(h)
-        h = F.conv2d(h, p[k["down"] + ".weight"], None, stride=2, padding=1)
+            h = P.grad(h)
+        w = p[k["down"] + ".weight"]
+        h = F.conv2d(h, P.w(w) if lvl > 1 else w, None, stride=2, padding=1)
+        h = P.grad(P.act(h, f"y{lvl}") if lvl > 1 else h)
         if taps is not None:
             taps[f"d{lvl}.conv"] = h
         if k["dnorm"]:
             h = _bn(p, k["dnorm"], h, train, taps)
     for lvl in range(num_downs, 0, -1):
         k = unet_keys(lvl, num_downs)
-        h = F.relu(h)  # uprelu (in place on the child's cat in the reference)
+        h = P.grad(F.relu(h))  # uprelu (in place on the child's cat in the reference)
         if taps is not None:
             taps[f"u{lvl}.in"] = h
-        h = F.conv_transpose2d(h, p[k["up"] + ".weight"], p.get(k["up"] + ".bias"), stride=2, padding=1)
+        w = p[k["up"] + ".weight"]
+        h = F.conv_transpose2d(h, P.w(w) if lvl > 1 else w, p.get(k["up"] + ".bias"), stride=2, padding=1)
+        if lvl > 1:
+            h = P.grad(P.act(h, f"yu{lvl}"))
         if taps is not None:
             taps[f"u{lvl}.conv"] = h
         if lvl == 1:
@@ -220,20 +320,25 @@ def unet_forward(
         h = _bn(p, k["unorm"], h, train, taps)
         if dropout_masks is not None and lvl in dropout_masks:
             h = h * dropout_masks[lvl] * 2.0
-        h = torch.cat([skips[lvl - 2], h], 1)  # skip first, decoder second
+        # relu(round(x)) == round(relu(x)): the decoder half is stored post-ReLU by the CUDA path; the parent's uprelu
+        # (top of this loop) is idempotent on it
+        h = torch.cat([skips[lvl - 2], P.act(F.relu(h), f"s{lvl}")], 1)  # skip first, decoder second
     raise AssertionError("unreachable")
 
 
-def patchgan_forward(p: Params, x: torch.Tensor, train: bool = True, sigmoid: bool = True, taps: Optional[dict] = None):
+def patchgan_forward(p: Params, x: torch.Tensor, train: bool = True, sigmoid: bool = True, taps: Optional[dict] = None, policy=None):
     """PatchGANDiscriminator.forward, networks.py:337-363 -> [B, 1]."""
+    P = policy or Fp32Policy()
     h = x
     for i, (ck, bk) in enumerate(PATCHGAN_CONVS):
-        h = F.conv2d(h, p[ck + ".weight"], None, stride=2, padding=1)
+        w = p[ck + ".weight"]
+        h = F.conv2d(h, P.w(w) if i > 0 else w, None, stride=2, padding=1)
+        h = P.grad(P.act(h, f"y{i}") if i > 0 else h)
         if taps is not None:
             taps[f"c{i + 1}.conv"] = h
         if bk:
             h = _bn(p, bk, h, train, taps)
-        h = F.leaky_relu(h, 0.2)
+        h = P.grad(P.act(F.leaky_relu(h, 0.2), f"a{i}"))
     h = F.conv2d(h, p["model.11.weight"], None, stride=1, padding=0)
     if taps is not None:
         taps["c5.conv"] = h

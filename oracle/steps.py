@@ -55,6 +55,12 @@ def make_optimizer(kind: str, *param_dicts: Params):
     raise ValueError(kind)
 
 
+def _scope(policy, name):
+    """Name the forward pass about to run (TeacherForcedPolicy keys its stored tensors by '<scope>/<tag>')."""
+    if policy is not None:
+        policy.scope = name
+
+
 def grads_of(p: Params) -> Params:
     return {k: (v.grad.detach().clone() if v.grad is not None else None) for k, v in nets.trainable(p).items()}
 
@@ -97,21 +103,25 @@ def wgan_step(
     update_g: bool = True,
     dropout_masks: Optional[dict] = None,
     clip: float = 0.01,
+    policy=None,
 ):
     """wgan_l1.py:110-186 (recon='l1') / wgan_rmse.py (recon='rmse').
 
     ``update_g`` stands for the schedule test at wgan_l1.py:157-163."""
     out = {}
     mask, masked = prepare(ground, mask)
-    g_out = nets.unet_forward(G, masked, train=True, dropout_masks=dropout_masks)
+    _scope(policy, "G")
+    g_out = nets.unet_forward(G, masked, train=True, dropout_masks=dropout_masks, policy=policy)
     inpainted = composite(masked, g_out, mask)
     out["g_out"], out["inpainted"] = g_out.detach(), inpainted.detach()
 
     # ---- D step (:128-153)
     set_requires_grad([D], True)
     d_opt.zero_grad()
-    d_real = nets.patchgan_forward(D, ground, train=True, sigmoid=False)
-    d_fake = nets.patchgan_forward(D, inpainted.detach(), train=True, sigmoid=False)
+    _scope(policy, "Dreal")
+    d_real = nets.patchgan_forward(D, ground, train=True, sigmoid=False, policy=policy)
+    _scope(policy, "Dfake")
+    d_fake = nets.patchgan_forward(D, inpainted.detach(), train=True, sigmoid=False, policy=policy)
     d_loss_real = d_real.mean().view(1)
     d_loss_real.backward(torch.ones(1))  # `one`  (D10)
     d_loss_fake = d_fake.mean().view(1)
@@ -127,7 +137,8 @@ def wgan_step(
     if update_g:
         set_requires_grad([D], False)
         g_opt.zero_grad()
-        d_gen = nets.patchgan_forward(D, inpainted, train=True, sigmoid=False).view(-1)
+        _scope(policy, "Dgen")
+        d_gen = nets.patchgan_forward(D, inpainted, train=True, sigmoid=False, policy=policy).view(-1)
         g_adv = d_gen.mean().view(1)
         rec = _recon(recon, ground, inpainted)
         g_loss = g_adv + rec
@@ -138,20 +149,23 @@ def wgan_step(
     return out
 
 
-def minimax_step(G: Params, D: Params, g_opt, d_opt, ground, mask, recon: str = "rmse", dropout_masks: Optional[dict] = None):
+def minimax_step(G: Params, D: Params, g_opt, d_opt, ground, mask, recon: str = "rmse", dropout_masks: Optional[dict] = None, policy=None):
     """minimaxgan_rmse.py:110-173 (recon='rmse') / minimaxgan_l1.py (recon='l1')."""
     out = {}
     mask, masked = prepare(ground, mask)
-    g_out = nets.unet_forward(G, masked, train=True, dropout_masks=dropout_masks)
+    _scope(policy, "G")
+    g_out = nets.unet_forward(G, masked, train=True, dropout_masks=dropout_masks, policy=policy)
     inpainted = composite(masked, g_out, mask)
     out["g_out"], out["inpainted"] = g_out.detach(), inpainted.detach()
 
     set_requires_grad([D], True)
     d_opt.zero_grad()
-    d_real = nets.patchgan_forward(D, ground, train=True, sigmoid=True).view(-1)
+    _scope(policy, "Dreal")
+    d_real = nets.patchgan_forward(D, ground, train=True, sigmoid=True, policy=policy).view(-1)
     d_loss_real = losses.bce(d_real, 1.0)
     d_loss_real.backward()
-    d_fake = nets.patchgan_forward(D, inpainted.detach(), train=True, sigmoid=True).view(-1)
+    _scope(policy, "Dfake")
+    d_fake = nets.patchgan_forward(D, inpainted.detach(), train=True, sigmoid=True, policy=policy).view(-1)
     d_loss_fake = losses.bce(d_fake, 0.0)
     d_loss_fake.backward()
     out["d_loss_real"], out["d_loss_fake"] = d_loss_real.item(), d_loss_fake.item()
@@ -160,7 +174,8 @@ def minimax_step(G: Params, D: Params, g_opt, d_opt, ground, mask, recon: str = 
 
     set_requires_grad([D], False)
     g_opt.zero_grad()
-    d_gen = nets.patchgan_forward(D, inpainted, train=True, sigmoid=True).view(-1)
+    _scope(policy, "Dgen")
+    d_gen = nets.patchgan_forward(D, inpainted, train=True, sigmoid=True, policy=policy).view(-1)
     g_adv = losses.bce(d_gen, 1.0)
     rec = _recon(recon, ground, inpainted)
     g_loss = g_adv + rec
@@ -182,6 +197,7 @@ def global_local_step(
     lambda1: float = 300.0,
     lambda2: float = 300.0,
     dropout_masks: Optional[dict] = None,
+    policy=None,
 ):
     """experiment1_global_local_D.py:139-200.  G step first, no composite, mask not ceil'ed,
     LSGAN heads on sigmoid outputs, ``d_opt`` is ONE Adam over chain(Dl, Dg) (:123)."""
@@ -190,10 +206,13 @@ def global_local_step(
 
     set_requires_grad([Dg, Dl], False)
     g_opt.zero_grad()
-    inpainted = nets.unet_forward(G, masked, train=True, dropout_masks=dropout_masks)
+    _scope(policy, "G")
+    inpainted = nets.unet_forward(G, masked, train=True, dropout_masks=dropout_masks, policy=policy)
     out["inpainted"] = inpainted.detach()
-    pg = nets.patchgan_forward(Dg, inpainted, train=True, sigmoid=True).view(-1)
-    pl = nets.patchgan_forward(Dl, mask * inpainted, train=True, sigmoid=True).view(-1)
+    _scope(policy, "DgGen")
+    pg = nets.patchgan_forward(Dg, inpainted, train=True, sigmoid=True, policy=policy).view(-1)
+    _scope(policy, "DlGen")
+    pl = nets.patchgan_forward(Dl, mask * inpainted, train=True, sigmoid=True, policy=policy).view(-1)
     g_adv_g, g_adv_l = losses.lsgan(pg, 1.0), losses.lsgan(pl, 1.0)
     rec_g = losses.rmse(ground, inpainted)
     rec_l = losses.rmse(mask * ground, mask * inpainted)  # averages over ALL pixels (not LocalLoss)
@@ -206,10 +225,14 @@ def global_local_step(
     set_requires_grad([Dg, Dl], True)
     d_opt.zero_grad()
     fake = inpainted.detach()
-    l_rg = losses.lsgan(nets.patchgan_forward(Dg, ground, train=True, sigmoid=True).view(-1), 1.0)
-    l_fg = losses.lsgan(nets.patchgan_forward(Dg, fake, train=True, sigmoid=True).view(-1), 0.0)
-    l_rl = losses.lsgan(nets.patchgan_forward(Dl, ground * mask, train=True, sigmoid=True).view(-1), 1.0)
-    l_fl = losses.lsgan(nets.patchgan_forward(Dl, fake * mask, train=True, sigmoid=True).view(-1), 0.0)
+    _scope(policy, "DgReal")
+    l_rg = losses.lsgan(nets.patchgan_forward(Dg, ground, train=True, sigmoid=True, policy=policy).view(-1), 1.0)
+    _scope(policy, "DgFake")
+    l_fg = losses.lsgan(nets.patchgan_forward(Dg, fake, train=True, sigmoid=True, policy=policy).view(-1), 0.0)
+    _scope(policy, "DlReal")
+    l_rl = losses.lsgan(nets.patchgan_forward(Dl, ground * mask, train=True, sigmoid=True, policy=policy).view(-1), 1.0)
+    _scope(policy, "DlFake")
+    l_fl = losses.lsgan(nets.patchgan_forward(Dl, fake * mask, train=True, sigmoid=True, policy=policy).view(-1), 0.0)
     d_loss = l_rl + l_fl + l_rg + l_fg
     d_loss.backward()
     out["d_loss"] = d_loss.item()

@@ -1,0 +1,124 @@
+"""CPU: the oracle (oracle/) against the committed golden vectors that oracle/pin_against_reference.py recorded from the
+REFERENCE modules (/root/reference is not available at test time), plus the properties the precision policies rely on."""
+import torch
+
+from oracle import losses, nets, steps, synth
+from tests.util import rel, summary_close
+
+
+def clone(p):
+    return {k: v.clone() for k, v in p.items()}
+
+
+def test_synthetic_inputs_are_deterministic(golden):
+    g, m = synth.make_batch(golden["batch"], golden["res"], seed=golden["seed_inputs"], soft_edge=True)
+    assert torch.equal(g, golden["ground"]) and torch.equal(m, golden["mask"])
+    mc, _ = steps.prepare(g, m)
+    assert float(mc.sum()) == golden["mask_ceil_sum"]
+    assert losses.masked_pixel_count(m) == golden["masked_pixel_count"]
+    assert set(mc.unique().tolist()) <= {0.0, 1.0} and not set(m.unique().tolist()) <= {0.0, 1.0}  # soft edge got ceil'ed
+
+
+def test_unet_matches_reference_outputs(golden):
+    ground, mask = golden["ground"], golden["mask"]
+    _, masked = steps.prepare(ground, mask)
+    p = steps.enable_grad(nets.init_unet(golden["seed_g"]))
+    taps = {}
+    out = nets.unet_forward(p, masked, train=True, taps=taps)
+    assert rel(out, golden["unet_train_out"]) < 1e-5
+    for name, s in golden["unet_taps"].items():
+        ne, se = summary_close(taps[name], s, 0)
+        assert ne < 1e-5 and se < 1e-4, name
+    (out * torch.linspace(-1, 1, out.numel()).view_as(out)).sum().backward()
+    for k, s in golden["unet_grads"].items():
+        ne, se = summary_close(p[k].grad, s, 0)
+        assert ne < 1e-4 and se < 1e-3, k
+    for k, v in golden["unet_running"].items():
+        assert rel(p[k], v) < 1e-5
+    with torch.no_grad():
+        assert rel(nets.unet_forward(p, masked, train=False), golden["unet_eval_out"]) < 1e-5
+
+
+def test_patchgan_matches_reference_outputs(golden):
+    for sig, tag in ((True, "sig"), (False, "lin")):
+        p = steps.enable_grad(nets.init_patchgan(golden["seed_d"], res=128))
+        x = golden["ground"].clone().requires_grad_(True)
+        r = nets.patchgan_forward(p, x, train=True, sigmoid=sig)
+        assert rel(r, golden[f"patchgan_{tag}_out"]) < 1e-5
+        (r * torch.tensor([[1.0], [-2.0]])).sum().backward()
+        ne, se = summary_close(x.grad, golden[f"patchgan_{tag}_dx"], 0)
+        assert ne < 1e-4 and se < 1e-3
+        for k, s in golden[f"patchgan_{tag}_grads"].items():
+            ne, se = summary_close(p[k].grad, s, 0)
+            assert ne < 1e-4 and se < 1e-3, k
+
+
+def test_losses_match_reference_classes(golden):
+    yhat, ground, mask = golden["loss_yhat"], golden["ground"], golden["mask"]
+    assert abs(float(losses.rmse(yhat, ground)) - golden["rmse"]) < 1e-7
+    assert abs(float(losses.local_loss(yhat, ground, mask, "l1")) - golden["local_l1"]) < 1e-6
+    assert abs(float(losses.local_loss(yhat, ground, mask, "mse")) - golden["local_mse"]) < 1e-6
+
+
+def test_wgan_step_matches_reference_modules(golden):
+    ground, mask = golden["ground"], golden["mask"]
+    for recon in ("l1", "rmse"):
+        G, D = steps.enable_grad(nets.init_unet(golden["seed_g"])), steps.enable_grad(nets.init_patchgan(golden["seed_d"], res=128))
+        o = steps.wgan_step(G, D, steps.make_optimizer("rmsprop", G), steps.make_optimizer("rmsprop", D), ground, mask, recon=recon)
+        g = golden[f"wgan_{recon}"]
+        assert rel(o["inpainted"], g["inpainted"]) < 1e-5
+        for k in ("d_loss_real", "d_loss_fake", "g_adv", "recon"):
+            assert abs(o[k] - g[k]) < 1e-5, (recon, k)
+        for k, s in g["g_grads"].items():
+            ne, _ = summary_close(o["g_grads"][k], s, 0)
+            assert ne < 1e-3, k
+        for k, s in g["d_post"].items():
+            ne, _ = summary_close(D[k], s, 0)
+            assert ne < 1e-5, k
+
+
+def test_minimax_and_global_local_steps_match_reference_modules(golden):
+    ground, mask = golden["ground"], golden["mask"]
+    G, D = steps.enable_grad(nets.init_unet(golden["seed_g"])), steps.enable_grad(nets.init_patchgan(golden["seed_d"], res=128))
+    o = steps.minimax_step(G, D, steps.make_optimizer("adam", G), steps.make_optimizer("adam", D), ground, mask, recon="rmse")
+    g = golden["minimax_rmse"]
+    for k in ("d_loss_real", "d_loss_fake", "g_adv", "recon"):
+        assert abs(o[k] - g[k]) < 1e-5, k
+    G, Dg, Dl = (steps.enable_grad(nets.init_unet(golden["seed_g"])), steps.enable_grad(nets.init_patchgan(golden["seed_d"], res=128)),
+                 steps.enable_grad(nets.init_patchgan(golden["global_local"]["seed_dl"], res=128)))
+    o = steps.global_local_step(G, Dg, Dl, steps.make_optimizer("adam", G), steps.make_optimizer("adam", Dl, Dg), ground, mask)
+    g = golden["global_local"]
+    assert abs(o["g_loss"] - g["g_loss"]) < 1e-3 * abs(g["g_loss"]) and abs(o["d_loss"] - g["d_loss"]) < 1e-5
+    for k, s in g["dl_grads"].items():
+        ne, _ = summary_close(o["dl_grads"][k], s, 0)
+        assert ne < 1e-3, k
+
+
+def test_policies_share_one_algorithm():
+    """Fp32Policy is the identity; Bf16Policy only rounds; TeacherForcedPolicy fed with the oracle's own tensors is a no-op."""
+    ground, mask = synth.make_batch(2, 128, seed=1)
+    _, masked = steps.prepare(ground, mask)
+    p = nets.init_unet(5)
+    a = nets.unet_forward(clone(p), masked, train=True)
+    b = nets.unet_forward(clone(p), masked, train=True, policy=nets.Fp32Policy())
+    assert torch.equal(a, b)
+    c = nets.unet_forward(clone(p), masked, train=True, policy=nets.Bf16Policy())
+    assert 1e-4 < rel(c, a) < 3e-2  # bf16 storage moves the result by ~1 %
+    # teacher forcing with the free-running bf16 tensors reproduces the bf16 run (up to the weights' rounding, also applied)
+    d = steps.enable_grad(nets.init_patchgan(6, res=128))
+    taps = {}
+    r = nets.patchgan_forward(d, ground, train=True, sigmoid=False, taps=taps, policy=nets.Bf16Policy())
+    import torch.nn.functional as F
+
+    stored = {f"y{i}": taps[f"c{i + 1}.conv"].detach() for i in range(1, 4)}
+    pol = nets.TeacherForcedPolicy(stored)
+    r2 = nets.patchgan_forward(clone({k: v.detach() for k, v in d.items()}), ground, train=True, sigmoid=False, policy=pol)
+    assert len(pol.errors) == 3 and max(pol.errors.values()) < 5e-3
+    assert rel(r2, r) < 5e-3
+
+
+def test_flop_counts_match_survey():
+    assert abs(nets.conv_flops_unet(256) / 1e9 - 11.845) < 0.01
+    assert abs(nets.conv_flops_unet(128) / 1e9 - 2.961) < 0.01
+    assert abs(nets.conv_flops_patchgan(256) / 1e9 - 3.258) < 0.01
+    assert abs(nets.conv_flops_patchgan(128) / 1e9 - 0.814) < 0.01

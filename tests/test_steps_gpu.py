@@ -1,0 +1,297 @@
+"""Step-level parity (GPU): one full train step of every recipe through
+``gan_inpainting_b200.trainer.InpaintingTrainer`` against ``oracle.steps`` on the same seeded inputs and weights:
+losses, the composited image, every parameter gradient as the optimizer consumed it, and the post-step weights.
+Also checks the committed golden scalars produced by the REFERENCE modules (batch 2).
+
+Two tiers, as in tests/test_networks_gpu.py (DESIGN.md "Numerical parity"):
+A. teacher-forced oracle step (the oracle continues from the CUDA path's stored activations, so masks and batch
+   statistics coincide): losses, every gradient and the post-step weights to rel-L2 <= 1e-2 (north_star);
+B. free-running fp32 oracle step: images and losses to 1e-2 / 2e-2, gradient cosine >= 0.9, post-step weights 1e-2.
+"""
+import pytest
+import torch
+
+from tests.test_networks_gpu import make_D, make_G
+from tests.util import cos, rel, stored_from_disc_ctx, stored_from_gen_ctx, summary_close
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-2
+
+
+def _imports():
+    from gan_inpainting_b200 import trainer
+    from oracle import nets, steps, synth
+
+    return trainer, nets, steps, synth
+
+
+def close(a, b, tol=TOL, floor=1e-3):
+    """|a - b| <= tol * max(|b|, floor); ``floor`` is the natural scale of a quantity that may cancel to ~0 (a WGAN critic mean)."""
+    return abs(a - b) <= tol * max(abs(b), floor)
+
+
+def check_grads(flat_group, ref_grads, tol=TOL, what=""):
+    bad = []
+    for name, p, g in zip(flat_group.names, flat_group.members, flat_group.grad_views):
+        e = rel(g, ref_grads[name])
+        if not e < tol:
+            bad.append((name, e))
+    assert not bad, (what, bad)
+
+
+def check_cos(flat_group, ref_grads, lo=0.9, what=""):
+    bad = []
+    for name, g in zip(flat_group.names, flat_group.grad_views):
+        if float(ref_grads[name].norm()) < 1e-12:  # e.g. the WGAN head bias: d(mean real - mean fake)/d bias == 0 exactly
+            assert float(g.norm()) < 1e-6, name
+            continue
+        c = cos(g, ref_grads[name])
+        if not c > lo:
+            bad.append((name, c))
+    assert not bad, (what, bad)
+
+
+def forced_policy(tr, nets):
+    """TeacherForcedPolicy over every forward pass of the last trainer step."""
+    stored = {}
+    for scope, c in tr.last["ctx"].items():
+        if c is None:
+            continue
+        if scope == "G":
+            stored.update(stored_from_gen_ctx(c, tr.G._cfg["widths"], scope))
+        else:
+            stored.update(stored_from_disc_ctx(c, scope))
+    return nets.TeacherForcedPolicy(stored)
+
+
+def check_forced_layers(pol, n_expected):
+    assert len(pol.errors) == n_expected, (len(pol.errors), n_expected)
+    worst = max(pol.errors.items(), key=lambda kv: kv[1])
+    assert worst[1] < 5e-3, worst
+
+
+RMSPROP_STEP = 5e-4  # first RMSprop step: lr * g / (sqrt(0.01 g^2) + eps) = 10 * lr * sign(g), lr = 5e-5
+ADAM_STEP = 2e-4     # first Adam step: lr * sign(g), lr = 2e-4
+
+
+def check_params(net, ref_params, step, tol=TOL, what="", flips=0.02):
+    """Post-step weights.  The first RMSprop / Adam step is sign descent (|update| == ``step`` for every element), which
+    is discontinuous where a gradient element is ~0: the bound is tol * ||w_ref|| plus the norm of a fraction ``flips``
+    of sign disagreements (each 2 * step) — 2 % teacher-forced, 15 % free-running (where gradient cosine is ~0.95).
+    The optimizer kernels themselves are checked exactly against torch.optim in tests/test_kernels_gpu.py."""
+    bad = []
+    for k, v in net.state_dict().items():
+        if v.dtype.is_floating_point:
+            r = ref_params[k].detach().float()
+            err = float((v.detach().float().cpu() - r).norm())
+            bound = tol * float(r.norm()) + 2 * step * (flips * r.numel()) ** 0.5
+            if not err <= bound:
+                bad.append((k, err, bound))
+    assert not bad, (what, bad)
+
+
+@pytest.mark.parametrize("recon", ["l1", "rmse"])
+def test_wgan_step(dev, recon):
+    trainer, nets, steps, synth = _imports()
+    R, B = 128, 8
+    ground, mask = synth.make_batch(B, R, seed=21, soft_edge=True)
+    gp, dp = nets.init_unet(0), nets.init_patchgan(1, res=R)
+    G, D = make_G(dev, gp).train(), make_D(dev, dp, R, False).train()
+    tr = trainer.InpaintingTrainer("wgan", G, D, recon=recon)
+    tr.step(ground.to(dev), mask.to(dev), update_g=True)
+    s = tr.read_scalars()
+    cl = lambda p: steps.enable_grad({k: v.clone() for k, v in p.items()})
+    assert torch.equal(tr.last["mask"].cpu(), torch.ceil(mask))  # bit-exact binarisation
+    # ---- tier A: teacher-forced
+    pol = forced_policy(tr, nets)
+    G_, D_ = cl(gp), cl(dp)
+    o = steps.wgan_step(G_, D_, steps.make_optimizer("rmsprop", G_), steps.make_optimizer("rmsprop", D_), ground, mask, recon=recon, policy=pol)
+    check_forced_layers(pol, 24 + 3 * 7)
+    assert rel(tr.last["inpainted"], o["inpainted"]) < 1e-4
+    for k in ("d_loss_real", "d_loss_fake", "g_adv", "recon", "g_loss"):
+        assert close(s[k], o[k], 2e-3), (k, s[k], o[k])
+    check_grads(tr.fD, o["d_grads"], what="D grads (teacher-forced)")
+    check_grads(tr.fG, o["g_grads"], what="G grads (teacher-forced)")
+    check_params(D, D_, RMSPROP_STEP, what="D after RMSprop + clip")
+    check_params(G, G_, RMSPROP_STEP, what="G after RMSprop")
+    # ---- tier B: free-running fp32 reference
+    G_, D_ = cl(gp), cl(dp)
+    o = steps.wgan_step(G_, D_, steps.make_optimizer("rmsprop", G_), steps.make_optimizer("rmsprop", D_), ground, mask, recon=recon)
+    assert rel(tr.last["inpainted"], o["inpainted"]) < TOL
+    for k in ("d_loss_real", "d_loss_fake", "g_adv", "recon", "g_loss"):
+        assert close(s[k], o[k], 2e-2, floor=0.1), (k, s[k], o[k])  # critic outputs are O(0.1-1); their batch mean cancels
+    check_cos(tr.fD, o["d_grads"], what="D grads (free-running)")
+    check_cos(tr.fG, o["g_grads"], what="G grads (free-running)")
+    check_params(D, D_, RMSPROP_STEP, what="D after RMSprop + clip (free-running)", flips=0.15)
+    check_params(G, G_, RMSPROP_STEP, what="G after RMSprop (free-running)", flips=0.15)
+    # the clip touches every D parameter, BN gamma included (gamma = 1 -> 0.01)
+    assert float(max(p.abs().max() for p in D.parameters())) <= 0.01 + 1e-7
+    assert abs(float(D.state_dict()["model.3.weight"].mean()) - 0.01) < 1e-6
+
+
+def test_wgan_d_only_step(dev):
+    """4 of 5 steady-state batches skip the G update (wgan_l1.py:157-163)."""
+    trainer, nets, steps, synth = _imports()
+    R, B = 128, 4
+    ground, mask = synth.make_batch(B, R, seed=22)
+    gp, dp = nets.init_unet(0), nets.init_patchgan(1, res=R)
+    G, D = make_G(dev, gp).train(), make_D(dev, dp, R, False).train()
+    tr = trainer.InpaintingTrainer("wgan", G, D)
+    tr.step(ground.to(dev), mask.to(dev), update_g=False)
+    G_, D_ = steps.enable_grad({k: v.clone() for k, v in gp.items()}), steps.enable_grad({k: v.clone() for k, v in dp.items()})
+    steps.wgan_step(G_, D_, steps.make_optimizer("rmsprop", G_), steps.make_optimizer("rmsprop", D_), ground, mask, update_g=False)
+    check_params(D, D_, RMSPROP_STEP, what="D after D-only step", flips=0.15)
+    for k, v in G.state_dict().items():  # conv / norm weights untouched; BN running stats did move (train-mode forward)
+        if "running" not in k and v.dtype.is_floating_point:
+            assert torch.equal(v.cpu(), gp[k]), k
+    check_params(G, G_, RMSPROP_STEP, what="G buffers after D-only step", tol=1.5e-2)
+
+
+@pytest.mark.parametrize("recon", ["rmse", "l1"])
+def test_minimax_step(dev, recon):
+    trainer, nets, steps, synth = _imports()
+    R, B = 128, 8
+    ground, mask = synth.make_batch(B, R, seed=23, soft_edge=True)
+    gp, dp = nets.init_unet(0), nets.init_patchgan(1, res=R)
+    G, D = make_G(dev, gp).train(), make_D(dev, dp, R, True).train()
+    tr = trainer.InpaintingTrainer("minimax", G, D, recon=recon)
+    tr.step(ground.to(dev), mask.to(dev))
+    s = tr.read_scalars()
+    cl = lambda p: steps.enable_grad({k: v.clone() for k, v in p.items()})
+    # ---- tier A: teacher-forced
+    pol = forced_policy(tr, nets)
+    G_, D_ = cl(gp), cl(dp)
+    o = steps.minimax_step(G_, D_, steps.make_optimizer("adam", G_), steps.make_optimizer("adam", D_), ground, mask, recon=recon, policy=pol)
+    check_forced_layers(pol, 24 + 3 * 7)
+    assert rel(tr.last["inpainted"], o["inpainted"]) < 1e-4
+    for k in ("d_loss_real", "d_loss_fake", "g_adv", "recon", "g_loss"):
+        assert close(s[k], o[k], 2e-3), (k, s[k], o[k])
+    check_grads(tr.fD, o["d_grads"], what="D grads (teacher-forced)")
+    check_grads(tr.fG, o["g_grads"], what="G grads (teacher-forced)")
+    check_params(D, D_, ADAM_STEP, what="D after Adam")
+    check_params(G, G_, ADAM_STEP, what="G after Adam")
+    # ---- tier B: free-running fp32 reference
+    G_, D_ = cl(gp), cl(dp)
+    o = steps.minimax_step(G_, D_, steps.make_optimizer("adam", G_), steps.make_optimizer("adam", D_), ground, mask, recon=recon)
+    assert rel(tr.last["inpainted"], o["inpainted"]) < TOL
+    for k in ("d_loss_real", "d_loss_fake", "g_adv", "recon", "g_loss"):
+        assert close(s[k], o[k], 2e-2), (k, s[k], o[k])
+    check_cos(tr.fD, o["d_grads"], what="D grads (free-running)")
+    check_cos(tr.fG, o["g_grads"], what="G grads (free-running)")
+    check_params(D, D_, ADAM_STEP, what="D after Adam (free-running)", flips=0.15)
+    check_params(G, G_, ADAM_STEP, what="G after Adam (free-running)", flips=0.15)
+
+
+def test_global_local_step(dev):
+    """config 1 (experiment1_global_local_D): 128x128, batch 8."""
+    trainer, nets, steps, synth = _imports()
+    R, B = 128, 8
+    ground, mask = synth.make_batch(B, R, seed=24, soft_edge=True)
+    gp, dp, dlp = nets.init_unet(0), nets.init_patchgan(1, res=R), nets.init_patchgan(2, res=R)
+    G, Dg, Dl = make_G(dev, gp).train(), make_D(dev, dp, R, True).train(), make_D(dev, dlp, R, True).train()
+    tr = trainer.InpaintingTrainer("global_local", G, Dg, Dl)
+    tr.step(ground.to(dev), mask.to(dev))
+    s = tr.read_scalars()
+    cl = lambda p: steps.enable_grad({k: v.clone() for k, v in p.items()})
+    run = lambda G_, Dg_, Dl_, pol: steps.global_local_step(G_, Dg_, Dl_, steps.make_optimizer("adam", G_), steps.make_optimizer("adam", Dl_, Dg_), ground,
+                                                           mask, policy=pol)
+    # ---- tier A: teacher-forced
+    pol = forced_policy(tr, nets)
+    G_, Dg_, Dl_ = cl(gp), cl(dp), cl(dlp)
+    o = run(G_, Dg_, Dl_, pol)
+    check_forced_layers(pol, 24 + 6 * 7)
+    assert rel(tr.last["inpainted"], o["inpainted"]) < 1e-4
+    assert close(s["g_adv"], o["g_adv_global"], 2e-3) and close(s["g_adv_local"], o["g_adv_local"], 2e-3)
+    assert close(s["recon"], o["recon_global"], 2e-3) and close(s["recon_local"], o["recon_local"], 2e-3)
+    assert close(s["g_loss"], o["g_loss"], 2e-3) and close(s["d_loss"], o["d_loss"], 2e-3)
+    check_grads(tr.fG, o["g_grads"], what="G grads (teacher-forced)")
+    check_grads(tr.fD, o["dg_grads"], what="Dg grads (teacher-forced)")
+    check_grads(tr.fDl, o["dl_grads"], what="Dl grads (teacher-forced)")
+    check_params(G, G_, ADAM_STEP, what="G after Adam")
+    check_params(Dg, Dg_, ADAM_STEP, what="Dg after Adam")
+    check_params(Dl, Dl_, ADAM_STEP, what="Dl after Adam")
+    # ---- tier B: free-running fp32 reference
+    G_, Dg_, Dl_ = cl(gp), cl(dp), cl(dlp)
+    o = run(G_, Dg_, Dl_, None)
+    assert rel(tr.last["inpainted"], o["inpainted"]) < 1.5e-2
+    assert close(s["g_adv"], o["g_adv_global"], 2e-2) and close(s["g_adv_local"], o["g_adv_local"], 2e-2)
+    assert close(s["recon"], o["recon_global"], 2e-2) and close(s["recon_local"], o["recon_local"], 2e-2)
+    assert close(s["g_loss"], o["g_loss"], 2e-2) and close(s["d_loss"], o["d_loss"], 2e-2)
+    check_cos(tr.fG, o["g_grads"], what="G grads (free-running)")
+    check_cos(tr.fD, o["dg_grads"], what="Dg grads (free-running)")
+    check_cos(tr.fDl, o["dl_grads"], what="Dl grads (free-running)")
+    check_params(G, G_, ADAM_STEP, what="G after Adam (free-running)", flips=0.15)
+
+
+def test_steps_vs_reference_golden_scalars(dev, golden):
+    """Batch-2 scalars recorded from the REFERENCE modules (oracle/pin_against_reference.py)."""
+    trainer, nets, _, _ = _imports()
+    ground, mask = golden["ground"].to(dev), golden["mask"].to(dev)
+    for key, recipe, recon, sig in (("wgan_l1", "wgan", "l1", False), ("wgan_rmse", "wgan", "rmse", False), ("minimax_rmse", "minimax", "rmse", True),
+                                    ("minimax_l1", "minimax", "l1", True)):
+        G = make_G(dev, nets.init_unet(golden["seed_g"])).train()
+        D = make_D(dev, nets.init_patchgan(golden["seed_d"], res=128), 128, sig).train()
+        tr = trainer.InpaintingTrainer(recipe, G, D, recon=recon)
+        tr.step(ground, mask)
+        s, g = tr.read_scalars(), golden[key]
+        assert rel(tr.last["inpainted"], g["inpainted"]) < TOL, key
+        for k in ("d_loss_real", "d_loss_fake", "g_adv", "recon"):
+            assert close(s[k], g[k], 3e-2, floor=0.1), (key, k, s[k], g[k])
+
+
+def test_module_api_step_equals_fused_step(dev):
+    """The reference-style loop (nn.Module calls + autograd + optimizer.step(), wgan_l1.py:110-186) and the fused
+    trainer run the same kernels: identical losses and weights."""
+    from gan_inpainting_b200 import optim as bo
+    from gan_inpainting_b200.lib.models import util
+    trainer, nets, steps, synth = _imports()
+    R, B = 128, 4
+    ground, mask = synth.make_batch(B, R, seed=25)
+    ground, mask = ground.to(dev), mask.to(dev)
+    gp, dp = nets.init_unet(0), nets.init_patchgan(1, res=R)
+    G, D = make_G(dev, gp).train(), make_D(dev, dp, R, False).train()
+    g_opt, d_opt = bo.RMSprop(G.parameters(), lr=0.00005), bo.RMSprop(D.parameters(), lr=0.00005)
+    one = torch.ones(1, device=dev)
+    mask_c = torch.ceil(mask)
+    masked = ground * (1 - mask_c)
+    inpainted = masked + G(masked) * mask_c
+    util.set_requires_grad([D], True)
+    d_opt.zero_grad()
+    pr, pf = D(ground), D(inpainted.detach())
+    pr.mean().view(1).backward(one)
+    pf.mean().view(1).backward(-one)
+    d_opt.step()
+    bo.clamp_(D.parameters(), -0.01, 0.01)
+    util.set_requires_grad([D], False)
+    g_opt.zero_grad()
+    g_loss = D(inpainted).view(-1).mean().view(1) + torch.nn.L1Loss()(ground, inpainted)
+    g_loss.backward()
+    g_opt.step()
+
+    G2, D2 = make_G(dev, gp).train(), make_D(dev, dp, R, False).train()
+    tr = trainer.InpaintingTrainer("wgan", G2, D2, recon="l1")
+    tr.step(ground, mask)
+    s = tr.read_scalars()
+    assert close(float(g_loss), s["g_loss"], 1e-4)
+    for (k, a), b in zip(D.state_dict().items(), D2.state_dict().values()):
+        if a.dtype.is_floating_point:
+            assert rel(a, b) < 1e-4, k
+    for (k, a), b in zip(G.state_dict().items(), G2.state_dict().values()):
+        if a.dtype.is_floating_point:
+            assert rel(a, b) < 1e-3, k
+
+
+def test_inference_composite(dev):
+    """config 5: ceil -> mask out -> G (eval) -> composite (visualize.py:69-76)."""
+    trainer, nets, steps, synth = _imports()
+    ground, mask = synth.make_batch(2, 256, seed=26, soft_edge=True)
+    gp = nets.init_unet(0)
+    G = make_G(dev, gp).eval()
+    D = make_D(dev, nets.init_patchgan(1, res=256), 256, False)
+    tr = trainer.InpaintingTrainer("wgan", G, D)
+    out = tr.inpaint(ground.to(dev), mask.to(dev))
+    ref = steps.inference({k: v.clone() for k, v in gp.items()}, ground, mask)
+    assert rel(out, ref) < TOL
+    keep = torch.ceil(mask) == 0
+    assert torch.equal(out.cpu()[keep], ground[keep])  # pixels outside the mask pass through bit-exactly
