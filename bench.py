@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""Benchmark of the GAN-inpainting train step (BASELINE.json metric: train-step images/sec at 256x256).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--recipe wgan_l1|minimaxgan_rmse|inference]
+
+Workload at N=1 (BASELINE.json configs[1]): ``wgan_l1`` — U-Net generator + PatchGAN global discriminator, 256x256,
+batch 64 per GPU, bf16 operands / fp32 accumulation.  One "step" is the full step of experiment_list/wgan_l1.py:110-186
+on one synthetic batch: ceil(mask) -> mask-out -> G forward -> composite -> D update (2 forward, 2 backward, RMSprop,
+clip) -> G update (D forward, D data-gradient, G backward, RMSprop).  Nothing is skipped inside the timed region.
+
+One JSON line on stdout (rank 0):
+  value      images/s with the batch already resident in HBM (CUDA events, max over ranks)
+  e2e        the same step through the public API with HOST inputs: per step a pinned-host -> device copy of
+             (ground, mask) and a device -> host read of the loss vector, inside the timed region
+  roofline   tensor-pipe roofline of the dominant kernel (the tcgen05 implicit-GEMM body that runs every 4x4/s2
+             convolution, its data gradient and its weight gradient): algorithmic FLOPs / measured kernel time
+  cpu_baseline  the oracle port of the reference step on this box's host cores (bounded sample, rank 0, N=1)
+
+`--impl reference` times the reference algorithm's CPU implementation (oracle/, fp32 PyTorch on all host cores) on a
+bounded sample of the same workload and prints the same line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RECIPES = {
+    # name: (trainer recipe, recon, sigmoid D, update_g)
+    "wgan_l1": ("wgan", "l1"),
+    "wgan_rmse": ("wgan", "rmse"),
+    "minimaxgan_rmse": ("minimax", "rmse"),
+    "minimaxgan_l1": ("minimax", "l1"),
+}
+METRIC = "train-step images/sec at 256x256"
+
+
+def flops_per_image(res: int, recipe: str) -> dict:
+    """Algorithmic conv FLOPs (2*MAC) per image, SURVEY.md §8(d): full step = 3*G + 8*D."""
+    from oracle import nets
+
+    g, d = nets.conv_flops_unet(res), nets.conv_flops_patchgan(res)
+    # tensor-core part: everything but the 1-channel-side layers (d1, u1, c1) and the D head
+    g1 = 2.0 * (res // 2) ** 2 * 64 * 16            # d1
+    gu1 = 2.0 * (res // 2) ** 2 * 128 * 16          # u1
+    dc1 = 2.0 * (res // 2) ** 2 * 64 * 16           # c1
+    dhead = d - sum(2.0 * (res >> (i + 1)) ** 2 * (64 << i) * (1 if i == 0 else (64 << (i - 1))) * 16 for i in range(4))
+    g_tc, d_tc = g - g1 - gu1, d - dc1 - dhead
+    if recipe == "inference":
+        return dict(total=g, tensor=g_tc)
+    # G: fwd + dgrad + wgrad (d2's dgrad to a1 IS needed; d1 has none).  D: 2 fwd + 2*(dgrad+wgrad) in the D step
+    # (c2's dgrad is needed for c1's wgrad) + 1 fwd + 1 dgrad in the G step.
+    return dict(total=3 * g + 8 * d, tensor=3 * g_tc + 8 * d_tc)
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons, power = [], [], set(), []
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                power.append(float(r[3]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.strip().lower() == "active":
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        load = sorted(sm[len(sm) // 4:]) or sorted(sm)
+        return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": max(mx), "power_w_max": max(power), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port of the reference step on the host cores
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_step_runner(recipe: str, res: int, batch: int):
+    import torch
+
+    from oracle import nets, steps, synth
+
+    torch.set_num_threads(os.cpu_count())
+    kind, recon = RECIPES[recipe]
+    G, D = steps.enable_grad(nets.init_unet(0)), steps.enable_grad(nets.init_patchgan(1, res=res))
+    if kind == "wgan":
+        go, do = steps.make_optimizer("rmsprop", G), steps.make_optimizer("rmsprop", D)
+        fn = lambda g, m: steps.wgan_step(G, D, go, do, g, m, recon=recon)
+    else:
+        go, do = steps.make_optimizer("adam", G), steps.make_optimizer("adam", D)
+        fn = lambda g, m: steps.minimax_step(G, D, go, do, g, m, recon=recon)
+    ground, mask = synth.make_batch(batch, res, seed=1234)
+    return lambda: fn(ground, mask)
+
+
+def time_cpu(recipe: str, res: int, batch: int, steps_n: int, warmup: int):
+    run = cpu_step_runner(recipe, res, batch)
+    for _ in range(warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(steps_n):
+        run()
+    dt = time.perf_counter() - t0
+    return batch * steps_n / dt, dt / steps_n
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = args.ref_batch
+    ips, spt = time_cpu(args.recipe, args.res, batch, args.steps, args.warmup)
+    sample = f"{args.steps} steps x {batch} images of the {args.recipe} step at {args.res}x{args.res} (fp32, torch CPU, {os.cpu_count()} threads)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": spt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.recipe}: G + global D full train step, {args.res}x{args.res}, batch {batch} per step (bounded CPU sample)",
+                   "recipe": args.recipe, "res": args.res, "batch_per_step": batch},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    from gan_inpainting_b200 import _lib, build
+    from gan_inpainting_b200.lib.models import networks
+    from gan_inpainting_b200.trainer import InpaintingTrainer
+    from oracle import synth  # synthetic input generator only
+
+    if rank == 0:
+        build.build(verbose=False)
+    if dist:
+        dist.barrier()
+    B, R = args.batch, args.res
+    kind, recon = RECIPES[args.recipe]
+    torch.manual_seed(0)
+    G = networks.get_network("generator", "unet").to(dev).train()  # reference default: dropout ON
+    D = networks.PatchGANDiscriminator(sigmoid=(kind != "wgan"), imagedim=R).to(dev).train()
+    tr = InpaintingTrainer(kind, G, D, recon=recon, distributed=world > 1, bucket_mb=args.bucket_mb)
+    ground_h, mask_h = synth.make_batch(B, R, seed=1234, rank=rank)
+    ground_h, mask_h = ground_h.pin_memory(), mask_h.pin_memory()
+    ground, mask = ground_h.to(dev), mask_h.to(dev)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, n):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        sync_all()
+        ms = e0.elapsed_time(e1)
+        if dist:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    step_dev = lambda: tr.step(ground, mask, update_g=True)
+    out_h = torch.empty(16, dtype=torch.float32).pin_memory()
+    g_d, m_d = torch.empty_like(ground), torch.empty_like(mask)
+
+    def step_e2e():
+        g_d.copy_(ground_h, non_blocking=True)
+        m_d.copy_(mask_h, non_blocking=True)
+        tr.step(g_d, m_d, update_g=True)
+        out_h.copy_(tr.scalars, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller reads the losses every step (wgan_l1.py:199-201)
+
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    sampler = ClockSampler(local)
+    l0 = _lib.value("b200_launch_count")
+    if rank == 0:
+        sampler.start()
+    ms = timed(step_dev, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = _lib.value("b200_launch_count") - l0
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    ips = B * world * args.steps / (ms * 1e-3)
+    ips_e2e = B * world * args.steps / (ms_e2e * 1e-3)
+
+    # ---- per-kernel time of one instrumented step (CUDA events around every C-ABI call, on the launching stream)
+    prof = {}
+
+    def hook(name):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+
+        def after():
+            e1.record()
+            prof.setdefault(name, []).append((e0, e1))
+
+        return after
+
+    kernel_ms = {}
+    if rank == 0:
+        _lib.PROFILE = hook
+        step_dev()
+        torch.cuda.synchronize()
+        _lib.PROFILE = None
+        kernel_ms = {k: sum(a.elapsed_time(b) for a, b in v) for k, v in prof.items()}
+    if dist:
+        dist.barrier()
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+    peaks = measured_peaks()
+    fl = flops_per_image(R, args.recipe)
+    gemm_names = ("b200_conv_s2_gemm", "b200_convt_s2_gemm", "b200_wgrad_gemm")
+    gemm_ms = sum(kernel_ms.get(k, 0.0) for k in gemm_names)
+    gemm_calls = sum(len(prof.get(k, [])) for k in gemm_names)
+    achieved = fl["tensor"] * B / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+    step_ms_instr = sum(kernel_ms.values())
+    roofline = {
+        "bound": "tensor", "kernel": "igemm_kernel (tcgen05 implicit GEMM: conv / convT phases / wgrad)", "achieved": achieved,
+        "peak": peaks["tf_sustained"], "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)", "unit": "TFLOP/s",
+        "frac": (achieved / peaks["tf_sustained"]) if achieved else None, "traffic": None,
+        "launches_per_step": gemm_calls, "avg_launch_ms": gemm_ms / max(gemm_calls, 1), "algorithmic_gflop_per_step": fl["tensor"] * B / 1e9,
+        "share_of_step": gemm_ms / step_ms_instr if step_ms_instr else None,
+        "step_breakdown_ms": {k: round(v, 4) for k, v in sorted(kernel_ms.items(), key=lambda kv: -kv[1])},
+        "whole_step_tflops": fl["total"] * B * world * args.steps / (ms * 1e-3) / 1e12,
+    }
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cb = args.ref_batch
+        c_ips, c_spt = time_cpu(args.recipe, R, cb, 2, 1)
+        cpu = {"value": c_ips, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"2 steps x {cb} images of the same {args.recipe} step at {R}x{R} (oracle port of the reference, fp32 torch CPU, all host threads)"}
+    nbytes = ground_h.numel() * 4
+    line = {
+        "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"{args.recipe}: U-Net generator + PatchGAN global D, full train step (D update + G update), {R}x{R}, batch {B} per GPU",
+                   "recipe": args.recipe, "res": R, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                   "dropout": True, "l2": "no flush: one step streams ~6 GB of activations/gradients, far larger than the 126 MB L2",
+                   "bn": "per-replica batch statistics", "bucket_mb": args.bucket_mb},
+        "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": out_h.numel() * 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--recipe", default="wgan_l1", choices=list(RECIPES))
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--res", type=int, default=256)
+    ap.add_argument("--ref-batch", type=int, default=4, help="images per step of the bounded CPU sample")
+    ap.add_argument("--bucket-mb", type=float, default=25.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "b200" and args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            # plain `python bench.py --gpus N`: relaunch under torchrun, one rank per GPU
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+                   "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+            raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -66,6 +66,7 @@ SIGNATURES = {
 VALUE_FUNCS = {
     "b200_abi_version": (c_int, []),
     "b200_last_error": (c_char_p, []),
+    "b200_launch_count": (c_longlong, []),
     "b200_bn_stat_blocks": (c_int, [L, I]),
     "b200_wgrad_c1_blocks": (c_int, []),
     "b200_recon_scratch_floats": (c_int, []),
@@ -103,9 +104,16 @@ def exported_symbols():
     return list(VALUE_FUNCS) + list(SIGNATURES)
 
 
+# optional per-call hook: PROFILE(name) -> callable run after the call (bench.py times kernels with CUDA events this way)
+PROFILE = None
+
+
 def call(name: str, *args):
     lib = load()
+    after = PROFILE(name) if PROFILE is not None else None
     rc = getattr(lib, name)(*args)
+    if after is not None:
+        after()
     if rc != 0:
         raise B200Error(f"{name} failed (status {rc}): {lib.b200_last_error().decode()}")
 

@@ -10,7 +10,12 @@ void b200_set_error(const char* msg) {
   g_err[sizeof(g_err) - 1] = 0;
 }
 
+static long long g_launches = 0;
+void b200_count_launch(void) { ++g_launches; }
+
 extern "C" {
 const char* b200_last_error(void) { return g_err; }
+// number of kernels this library has launched since load (bench.py's gpu_launches evidence)
+long long b200_launch_count(void) { return g_launches; }
 int b200_abi_version(void) { return 1; }
 }

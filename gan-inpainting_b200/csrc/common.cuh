@@ -13,6 +13,7 @@
 
 #define B200_CHECK_LAUNCH()                              \
   do {                                                   \
+    b200_count_launch();                                 \
     cudaError_t e__ = cudaGetLastError();                \
     if (e__ != cudaSuccess) {                            \
       b200_set_error(cudaGetErrorString(e__));           \
@@ -21,6 +22,7 @@
   } while (0)
 
 void b200_set_error(const char* msg);
+void b200_count_launch(void);
 
 namespace b200 {
 

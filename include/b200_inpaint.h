@@ -47,6 +47,7 @@ typedef struct CUstream_st* b200_stream_t; /* == cudaStream_t */
 
 int b200_abi_version(void);
 const char* b200_last_error(void); /* thread-local, host string */
+long long b200_launch_count(void);  /* kernels launched by this library since load */
 
 /* ------------------------------------------------------------------------------------------------------------------
  * tcgen05 implicit-GEMM convolutions (csrc/conv_gemm.cu).  4x4 kernel, stride 2, padding 1; TMA-staged NHWC bf16
