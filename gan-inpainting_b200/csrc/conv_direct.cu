@@ -18,50 +18,70 @@ namespace b200 {
 enum { ACT_NONE = 0, ACT_LEAKY = 1, ACT_RELU = 2, ACT_TANH = 3 };
 
 // ------------------------------------------------------------------------------------------------
-// conv_c1_fwd: thread = (pixel lane, 4 output channels); 64 weights in registers.
+// conv_c1_fwd: block = 256 output pixels (TOH x TOW); the (2*TOH+2) x (2*TOW+2) input window is staged in shared
+// memory (zero halo, mask multiply applied once), thread = 4 output channels with the 64 weights in registers.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) conv_c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ xmul, int B, int H, int W,
+constexpr int kXsFloats = 34 * 68;  // covers 18 x 68 (8 x 32 tile) and 34 x 36 (16 x 16 tile)
+
+__global__ void __launch_bounds__(256) conv_c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ xmul, int H, int W, int tow_shift,
                                                           const float* __restrict__ w, int C, int act, __nv_bfloat16* __restrict__ y,
                                                           __nv_bfloat16* __restrict__ y2, int ld2, int off2) {
-  const int lanes = C >> 2;          // threads per output pixel
-  const int ppb = 256 / lanes;       // pixels per pass
+  __shared__ __align__(16) float xs[kXsFloats];
+  const int TOW = 1 << tow_shift, TOH = 256 >> tow_shift;
+  const int Ho = H >> 1, Wo = W >> 1;
+  const int tiles_w = Wo >> tow_shift, tiles_h = Ho / TOH;
+  const int tw_i = blockIdx.x % tiles_w;
+  const int th_i = (blockIdx.x / tiles_w) % tiles_h;
+  const int b = blockIdx.x / (tiles_w * tiles_h);
+  const int oh0 = th_i * TOH, ow0 = tw_i << tow_shift;
+  const int rows = 2 * TOH + 2, cols = 2 * TOW + 2, xstride = 2 * TOW + 4;
+  const int ih0 = 2 * oh0 - 1, iw0 = 2 * ow0 - 1;
+  const float* xb = x + (size_t)b * H * W;
+  const float* mb = xmul ? xmul + (size_t)b * H * W : nullptr;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int r = warp; r < rows; r += 8) {
+    const int ih = ih0 + r;
+    const bool rok = ih >= 0 && ih < H;
+    for (int cI = lane; cI < cols; cI += 32) {
+      const int iw = iw0 + cI;
+      float v = 0.f;
+      if (rok && iw >= 0 && iw < W) {
+        v = __ldg(xb + (size_t)ih * W + iw);
+        if (mb) v *= __ldg(mb + (size_t)ih * W + iw);
+      }
+      xs[r * xstride + cI] = v;
+    }
+  }
+  const int lanes = C >> 2;     // threads per output pixel
+  const int ppp = 256 / lanes;  // pixels per pass
   const int cg = threadIdx.x % lanes;
   const int pl = threadIdx.x / lanes;
-  const int Ho = H >> 1, Wo = W >> 1;
-  const long long total = (long long)B * Ho * Wo;
   float wr[16][4];
 #pragma unroll
   for (int t = 0; t < 16; ++t)
 #pragma unroll
     for (int i = 0; i < 4; ++i) wr[t][i] = __ldg(w + (size_t)(cg * 4 + i) * 16 + t);
+  __syncthreads();
 
-  for (long long pix = (long long)blockIdx.x * ppb + pl; pix < total; pix += (long long)gridDim.x * ppb) {
-    const int ow = (int)(pix % Wo);
-    const int oh = (int)((pix / Wo) % Ho);
-    const int b = (int)(pix / ((long long)Wo * Ho));
-    const float* xb = x + (size_t)b * H * W;
-    const float* mb = xmul ? xmul + (size_t)b * H * W : nullptr;
+  for (int pp = pl; pp < 256; pp += ppp) {
+    const int ol_h = pp >> tow_shift, ol_w = pp & (TOW - 1);
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int kh = 0; kh < 4; ++kh) {
-      const int ih = 2 * oh + kh - 1;
-      const bool rok = (ih >= 0) && (ih < H);
+      const float* row = xs + (2 * ol_h + kh) * xstride + 2 * ol_w;
+      const float2 a = *reinterpret_cast<const float2*>(row);
+      const float2 c2 = *reinterpret_cast<const float2*>(row + 2);
+      const float v[4] = {a.x, a.y, c2.x, c2.y};
 #pragma unroll
-      for (int kw = 0; kw < 4; ++kw) {
-        const int iw = 2 * ow + kw - 1;
-        float v = 0.f;
-        if (rok && iw >= 0 && iw < W) {
-          v = __ldg(xb + (size_t)ih * W + iw);
-          if (mb) v *= __ldg(mb + (size_t)ih * W + iw);
-        }
+      for (int kw = 0; kw < 4; ++kw)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc[i] = fmaf(v, wr[kh * 4 + kw][i], acc[i]);
-      }
+        for (int i = 0; i < 4; ++i) acc[i] = fmaf(v[kw], wr[kh * 4 + kw][i], acc[i]);
     }
     if (act == ACT_LEAKY) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[i] = acc[i] > 0.f ? acc[i] : 0.2f * acc[i];
     }
+    const size_t pix = ((size_t)b * Ho + (oh0 + ol_h)) * Wo + (ow0 + ol_w);
     uint2 o = make_uint2(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]));
     *reinterpret_cast<uint2*>(y + pix * C + cg * 4) = o;
     if (y2) {  // relu copy into the decoder's concat buffer (skip connection)
@@ -104,52 +124,66 @@ __global__ void __launch_bounds__(256) convt_c1_fwd_kernel(const __nv_bfloat16* 
     for (int c = 0; c < 8; ++c) wr[t][c] = __ldg(w + (size_t)(chunk * 8 + c) * 16 + half * 8 + t);
 
   const int npix = kTH * kTH;
-  for (int base_p = warp * PPW; base_p < npix; base_p += 8 * PPW) {
-    const int pp = base_p + pslot;
-    const int li = pp / kTH, lj = pp - li * kTH;
-    const int i = i0 + li, j = j0 + lj;
-    const bool ok = (pp < npix) && i >= 0 && i < H && j >= 0 && j < W;
-    float v[8];
+  constexpr int U = 4;  // pixels in flight per lane (hides the HBM latency of the z loads)
+  for (int base0 = warp * PPW; base0 < npix; base0 += U * 8 * PPW) {
+    uint4 q[U];
+    bool ok[U];
+    int pps[U];
 #pragma unroll
-    for (int t = 0; t < 8; ++t) v[t] = 0.f;
-    if (ok) {
-      const uint4 q = __ldg(reinterpret_cast<const uint4*>(z + (((size_t)b * H + i) * W + j) * ldz + chunk * 8));
-      const uint32_t u[4] = {q.x, q.y, q.z, q.w};
-      float f[8];
+    for (int u = 0; u < U; ++u) {
+      const int pp = base0 + u * 8 * PPW + pslot;
+      const int li = pp / kTH, lj = pp - li * kTH;
+      const int i = i0 + li, j = j0 + lj;
+      pps[u] = pp;
+      ok[u] = (pp < npix) && i >= 0 && i < H && j >= 0 && j < W;
+      q[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (ok[u]) q[u] = __ldg(reinterpret_cast<const uint4*>(z + (((size_t)b * H + i) * W + j) * ldz + chunk * 8));
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (base0 + u * 8 * PPW >= npix) break;  // warp-uniform
+      const int pp = pps[u];
+      float v[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v[t] = 0.f;
+      if (ok[u]) {
+        const uint32_t uu[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 t2 = unpack_bf16x2(uu[k]);
+          f[2 * k] = t2.x;
+          f[2 * k + 1] = t2.y;
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) v[t] = fmaf(f[c], wr[t][c], v[t]);
+      }
+      // transposing reduction over the 8 chunk lanes (bits 0..2): lane keeps tap (lane & 7)
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float2 t2 = unpack_bf16x2(u[k]);
-        f[2 * k] = t2.x;
-        f[2 * k + 1] = t2.y;
+        const bool up = lane & 4;
+        const float send = up ? v[k] : v[k + 4];
+        const float keep = up ? v[k + 4] : v[k];
+        v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
       }
 #pragma unroll
-      for (int t = 0; t < 8; ++t)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) v[t] = fmaf(f[c], wr[t][c], v[t]);
+      for (int k = 0; k < 2; ++k) {
+        const bool up = lane & 2;
+        const float send = up ? v[k] : v[k + 2];
+        const float keep = up ? v[k + 2] : v[k];
+        v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+      }
+      {
+        const bool up = lane & 1;
+        const float send = up ? v[0] : v[1];
+        const float keep = up ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+      }
+      if (LPP == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 8);
+      if (pp < npix && (chunk < 8)) T[pp][half * 8 + (lane & 7)] = v[0];
     }
-    // transposing reduction over the 8 chunk lanes (bits 0..2): lane keeps tap (lane & 7)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const bool up = lane & 4;
-      const float send = up ? v[k] : v[k + 4];
-      const float keep = up ? v[k + 4] : v[k];
-      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const bool up = lane & 2;
-      const float send = up ? v[k] : v[k + 2];
-      const float keep = up ? v[k + 2] : v[k];
-      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-    {
-      const bool up = lane & 1;
-      const float send = up ? v[0] : v[1];
-      const float keep = up ? v[1] : v[0];
-      v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-    }
-    if (LPP == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 8);
-    if (pp < npix && (chunk < 8)) T[pp][half * 8 + (lane & 7)] = v[0];
   }
   __syncthreads();
 
@@ -180,64 +214,88 @@ __global__ void __launch_bounds__(256) convt_c1_fwd_kernel(const __nv_bfloat16* 
 
 // ------------------------------------------------------------------------------------------------
 // wgrad_c1: dW[c][kh*4+kw] = sum_{b,i,j} z[b,i,j,c] * g[b,2i+kh-1,2j+kw-1]
-// lane = 8 channels x 8 taps accumulators; deterministic per-block partials.
+// Persistent blocks walk 8 x 32 pixel tiles: the 18 x 66 window of g is staged in shared memory (zero halo, mask
+// multiply applied once); lane = 8 channels x 8 taps accumulators, the next pixel's z is prefetched.
+// Deterministic per-block partials.
 // ------------------------------------------------------------------------------------------------
+constexpr int kWgTH = 8, kWgTW = 32, kWgStride = 2 * kWgTW + 4;
+
 template <int LPP>
 __global__ void __launch_bounds__(256) wgrad_c1_kernel(const __nv_bfloat16* __restrict__ z, int B, int H, int W, int ldz, const float* __restrict__ g,
                                                        const float* __restrict__ gmul, float* __restrict__ partial) {
-  constexpr int LP = 2 * LPP;
-  constexpr int PPW = 32 / LP;
+  constexpr int LP = 2 * LPP;       // lanes per pixel
+  constexpr int PPP = 256 / LP;     // pixels per pass (whole block)
   constexpr int C = 8 * LPP;
+  __shared__ __align__(16) float gs[(2 * kWgTH + 2) * kWgStride];
   __shared__ float sum[C * 16];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int chunk = lane & (LPP - 1);
-  const int half = (lane / LPP) & 1;
-  const int pslot = lane / LP;
-  const int slot = warp * PPW + pslot;  // pixel slot inside the block
-  constexpr int SLOTS = 8 * PPW;
-  const long long total = (long long)B * H * W;
+  const int chunk = threadIdx.x & (LPP - 1);
+  const int half = (threadIdx.x / LPP) & 1;
+  const int slot = threadIdx.x / LP;  // pixel slot inside the block
   const int Hg = 2 * H, Wg = 2 * W;
+  const int tiles_w = W / kWgTW, tiles_h = H / kWgTH;
+  const int ntiles = B * tiles_w * tiles_h;
   float acc[8][8];
 #pragma unroll
   for (int t = 0; t < 8; ++t)
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[t][c] = 0.f;
 
-  for (long long pix = (long long)blockIdx.x * SLOTS + slot; pix < total; pix += (long long)gridDim.x * SLOTS) {
-    const int j = (int)(pix % W);
-    const int i = (int)((pix / W) % H);
-    const int b = (int)(pix / ((long long)W * H));
-    const uint4 q = __ldg(reinterpret_cast<const uint4*>(z + (size_t)pix * ldz + chunk * 8));
-    const uint32_t u[4] = {q.x, q.y, q.z, q.w};
-    float f[8];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 t2 = unpack_bf16x2(u[k]);
-      f[2 * k] = t2.x;
-      f[2 * k + 1] = t2.y;
-    }
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int tw_i = tile % tiles_w;
+    const int th_i = (tile / tiles_w) % tiles_h;
+    const int b = tile / (tiles_w * tiles_h);
+    const int i0 = th_i * kWgTH, j0 = tw_i * kWgTW;
     const float* gb = g + (size_t)b * Hg * Wg;
     const float* mb = gmul ? gmul + (size_t)b * Hg * Wg : nullptr;
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int ih = 2 * i + (half * 2 + r) - 1;
+    __syncthreads();  // previous tile's readers are done
+    for (int r = warp; r < 2 * kWgTH + 2; r += 8) {
+      const int ih = 2 * i0 - 1 + r;
       const bool rok = ih >= 0 && ih < Hg;
-#pragma unroll
-      for (int kw = 0; kw < 4; ++kw) {
-        const int iw = 2 * j + kw - 1;
-        float gv = 0.f;
+      for (int cI = lane; cI < 2 * kWgTW + 2; cI += 32) {
+        const int iw = 2 * j0 - 1 + cI;
+        float v = 0.f;
         if (rok && iw >= 0 && iw < Wg) {
-          gv = __ldg(gb + (size_t)ih * Wg + iw);
-          if (mb) gv *= __ldg(mb + (size_t)ih * Wg + iw);
+          v = __ldg(gb + (size_t)ih * Wg + iw);
+          if (mb) v *= __ldg(mb + (size_t)ih * Wg + iw);
         }
+        gs[r * kWgStride + cI] = v;
+      }
+    }
+    __syncthreads();
+    const __nv_bfloat16* zt = z + ((size_t)b * H * W) * ldz + chunk * 8;
+    auto zaddr = [&](int pp) { return zt + ((size_t)(i0 + (pp >> 5)) * W + (j0 + (pp & 31))) * ldz; };
+    uint4 q = __ldg(reinterpret_cast<const uint4*>(zaddr(slot)));
+#pragma unroll 2
+    for (int pp = slot; pp < kWgTH * kWgTW; pp += PPP) {
+      const uint4 cur = q;
+      if (pp + PPP < kWgTH * kWgTW) q = __ldg(reinterpret_cast<const uint4*>(zaddr(pp + PPP)));
+      const uint32_t u[4] = {cur.x, cur.y, cur.z, cur.w};
+      float f[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[r * 4 + kw][c] = fmaf(f[c], gv, acc[r * 4 + kw][c]);
+      for (int k = 0; k < 4; ++k) {
+        const float2 t2 = unpack_bf16x2(u[k]);
+        f[2 * k] = t2.x;
+        f[2 * k + 1] = t2.y;
+      }
+      const int li = pp >> 5, lj = pp & 31;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const float* row = gs + (2 * li + half * 2 + r) * kWgStride + 2 * lj;
+        const float2 a = *reinterpret_cast<const float2*>(row);
+        const float2 c2 = *reinterpret_cast<const float2*>(row + 2);
+        const float gv[4] = {a.x, a.y, c2.x, c2.y};
+#pragma unroll
+        for (int kw = 0; kw < 4; ++kw)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[r * 4 + kw][c] = fmaf(f[c], gv[kw], acc[r * 4 + kw][c]);
       }
     }
   }
+  __syncthreads();
   for (int k = threadIdx.x; k < C * 16; k += 256) sum[k] = 0.f;
   __syncthreads();
-  for (int s = 0; s < SLOTS; ++s) {
+  for (int s = 0; s < PPP; ++s) {
     if (slot == s) {
 #pragma unroll
       for (int t = 0; t < 8; ++t)
@@ -410,14 +468,16 @@ extern "C" {
 
 int b200_conv_c1_fwd(const float* x, const float* xmul, int B, int H, int W, const float* w, int C, int act, void* y, void* y2, int ld2, int off2,
                      cudaStream_t stream) {
-  if ((C != 64 && C != 128 && C != 32 && C != 256) || (H & 1) || (W & 1) || B < 1 || ld2 % 4 || off2 % 4) {
-    b200_set_error("conv_c1_fwd: C must be 32/64/128/256 and H, W even");
+  const int Ho = H / 2, Wo = W / 2;
+  int tow_shift = 5;  // 8 x 32 output tile; 16 x 16 when the image is only 16 pixels wide
+  if (Wo < 32) tow_shift = 4;
+  const int TOW = 1 << tow_shift, TOH = 256 >> tow_shift;
+  if ((C != 64 && C != 128 && C != 32 && C != 256) || (H & 1) || (W & 1) || B < 1 || ld2 % 4 || off2 % 4 || Wo % TOW || Ho % TOH) {
+    b200_set_error("conv_c1_fwd: C must be 32/64/128/256; output must tile by 8x32 (or 16x16)");
     return B200_ERR_ARG;
   }
-  const int ppb = 256 / (C >> 2);
-  long long blocks = ((long long)B * (H / 2) * (W / 2) + ppb - 1) / ppb;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  conv_c1_fwd_kernel<<<(int)blocks, 256, 0, stream>>>(x, xmul, B, H, W, w, C, act, (__nv_bfloat16*)y, (__nv_bfloat16*)y2, ld2, off2);
+  const int grid = B * (Ho / TOH) * (Wo / TOW);
+  conv_c1_fwd_kernel<<<grid, 256, 0, stream>>>(x, xmul, H, W, tow_shift, w, C, act, (__nv_bfloat16*)y, (__nv_bfloat16*)y2, ld2, off2);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -442,8 +502,8 @@ int b200_wgrad_c1_blocks(void) { return 148 * 2; }
 // partial: scratch of b200_wgrad_c1_blocks() * C * 16 floats
 int b200_wgrad_c1(const void* z, int B, int H, int W, int C, int ldz, const float* g, const float* gmul, float* partial, float* dw, int accumulate,
                   cudaStream_t stream) {
-  if ((C != 64 && C != 128) || ldz % 8 || B < 1) {
-    b200_set_error("wgrad_c1: C must be 64/128");
+  if ((C != 64 && C != 128) || ldz % 8 || B < 1 || H % kWgTH || W % kWgTW) {
+    b200_set_error("wgrad_c1: C must be 64/128, H % 8 == 0, W % 32 == 0");
     return B200_ERR_ARG;
   }
   const int nblk = b200_wgrad_c1_blocks();

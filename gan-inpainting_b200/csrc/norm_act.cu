@@ -16,18 +16,35 @@ enum { ACT_NONE = 0, ACT_LEAKY = 1, ACT_RELU = 2 };
 constexpr int kStatThreads = 256;
 
 // ---------------------------------------------------------------- statistics: sum, sum of squares per channel
-// partial[blk][2][C]
-__global__ void __launch_bounds__(kStatThreads) bn_stats_kernel(const __nv_bfloat16* __restrict__ y, long long P, int C, float* __restrict__ partial) {
-  const int chunks = C >> 3;               // 8-channel chunks per pixel
-  const int lanes = kStatThreads / chunks;  // pixel lanes per block (C <= 2048)
-  const int chunk = threadIdx.x % chunks;
-  const int pl = threadIdx.x / chunks;
+// partial[blk][2][C].  C is a power of two (chunk index by mask / shift, no integer division in the loop).
+__global__ void __launch_bounds__(kStatThreads) bn_stats_kernel(const __nv_bfloat16* __restrict__ y, int P, int C, int cshift, float* __restrict__ partial) {
+  const int chunks = C >> 3;                // 8-channel chunks per pixel
+  const int lanes = kStatThreads >> cshift;  // pixel lanes per block
+  const int chunk = threadIdx.x & (chunks - 1);
+  const int pl = threadIdx.x >> cshift;
   float s[8], q[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
   if (pl < lanes) {
-    for (long long pix = (long long)blockIdx.x * lanes + pl; pix < P; pix += (long long)gridDim.x * lanes) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(y + pix * C + chunk * 8));
+    const int stride = gridDim.x * lanes;
+    const __nv_bfloat16* base = y + chunk * 8;
+    int pix = blockIdx.x * lanes + pl;
+    // two independent loads in flight per thread
+    for (; pix + stride < P; pix += 2 * stride) {
+      const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(base + (size_t)pix * C));
+      const uint4 v1 = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(pix + stride) * C));
+      const uint32_t u[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 f = unpack_bf16x2(u[i]);
+        s[2 * (i & 3)] += f.x;
+        q[2 * (i & 3)] += f.x * f.x;
+        s[2 * (i & 3) + 1] += f.y;
+        q[2 * (i & 3) + 1] += f.y * f.y;
+      }
+    }
+    if (pix < P) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + (size_t)pix * C));
       const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -46,9 +63,8 @@ __global__ void __launch_bounds__(kStatThreads) bn_stats_kernel(const __nv_bfloa
     red[threadIdx.x][8 + i] = q[i];
   }
   __syncthreads();
-  // thread t < 2*C... : channel c, stat k
   for (int o = threadIdx.x; o < 2 * C; o += kStatThreads) {
-    const int k = o / C, c = o - k * C;
+    const int k = o >= C, c = o - k * C;
     const int ch = c >> 3, ci = c & 7;
     float acc = 0.f;
     for (int l = 0; l < lanes; ++l) acc += red[l * chunks + ch][k * 8 + ci];
@@ -56,19 +72,44 @@ __global__ void __launch_bounds__(kStatThreads) bn_stats_kernel(const __nv_bfloa
   }
 }
 
-// mean / rstd / scale / shift (+ running-stat update) from the partials.  One thread per channel.
-// stats_out[4][C] = mean, rstd, scale = gamma*rstd, shift = beta - mean*scale
-__global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblk, int C, double count, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* __restrict__ running_mean, float* __restrict__ running_var,
-                                   long long* __restrict__ num_batches_tracked, float momentum, float eps, float* __restrict__ stats_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
-  if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int b = 0; b < nblk; ++b) {
-    s += (double)partial[((size_t)b * 2 + 0) * C + c];
-    q += (double)partial[((size_t)b * 2 + 1) * C + c];
+// Sum the per-block partials of 32 consecutive channels: thread (w, l) walks blocks w, w+32, ... of channel c0+l
+// (coalesced 128-byte rows), fp64 accumulate, fixed-order tree over the 32 walkers -> deterministic.
+constexpr int kFinThreads = 1024;
+__device__ __forceinline__ void reduce_partials(const float* __restrict__ partial, int nblk, int C, int c, double& s, double& q) {
+  __shared__ double sh[2][32][33];
+  const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double a = 0.0, b = 0.0;
+  if (c < C) {
+    for (int blk = w; blk < nblk; blk += 32) {
+      a += (double)partial[((size_t)blk * 2 + 0) * C + c];
+      b += (double)partial[((size_t)blk * 2 + 1) * C + c];
+    }
   }
+  sh[0][w][l] = a;
+  sh[1][w][l] = b;
+  __syncthreads();
+  s = 0.0;
+  q = 0.0;
+  if (w == 0) {
+    for (int k = 0; k < 32; ++k) {
+      s += sh[0][k][l];
+      q += sh[1][k][l];
+    }
+  }
+}
+
+// mean / rstd / scale / shift (+ running-stat update) from the partials.  Block = 32 channels x 32 block walkers.
+// stats_out[4][C] = mean, rstd, scale = gamma*rstd, shift = beta - mean*scale
+__global__ void __launch_bounds__(kFinThreads) bn_finalize_kernel(const float* __restrict__ partial, int nblk, int C, double count,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                  float* __restrict__ running_mean, float* __restrict__ running_var,
+                                                                  long long* __restrict__ num_batches_tracked, float momentum, float eps,
+                                                                  float* __restrict__ stats_out) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  double s, q;
+  reduce_partials(partial, nblk, C, c, s, q);
+  if (threadIdx.x >= 32 || c >= C) return;
+  if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
   const double mean = s / count;
   double var = q / count - mean * mean;
   if (var < 0.0) var = 0.0;
@@ -102,8 +143,9 @@ __global__ void bn_eval_coeffs_kernel(int C, const float* __restrict__ gamma, co
 // ---------------------------------------------------------------- apply: out = act(y*scale + shift) [dropout], optional second store relu(out)
 struct ApplyParams {
   const __nv_bfloat16* y;
-  long long P;
+  int P;
   int C;
+  int cshift;  // log2(C / 8)
   const float* scale;  // may be null (identity)
   const float* shift;
   int act;
@@ -116,11 +158,11 @@ struct ApplyParams {
 };
 
 __global__ void __launch_bounds__(256) bn_act_kernel(const ApplyParams p) {
-  const int chunks = p.C >> 3;
-  const long long total = p.P * chunks;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const long long pix = idx / chunks;
-    const int c0 = (int)(idx - pix * chunks) * 8;
+  const unsigned total = (unsigned)p.P << p.cshift;
+  const unsigned cmask = (1u << p.cshift) - 1u;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const size_t pix = idx >> p.cshift;
+    const int c0 = (int)(idx & cmask) * 8;
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.y + pix * p.C + c0));
     const uint32_t u[4] = {v.x, v.y, v.z, v.w};
     float f[8];
@@ -169,8 +211,9 @@ __global__ void __launch_bounds__(256) bn_act_kernel(const ApplyParams p) {
 //   ACT_NONE : dz = g1
 struct BwdParams {
   const __nv_bfloat16* y;  // raw conv output
-  long long P;
+  int P;
   int C;
+  int cshift;  // log2(C / 8)
   const float* scale;  // forward scale/shift (null: identity)
   const float* shift;
   int act;
@@ -198,7 +241,7 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
   }
 }
 
-__device__ __forceinline__ void compute_dz(const BwdParams& p, long long pix, int c0, float (&yv)[8], float (&dz)[8]) {
+__device__ __forceinline__ void compute_dz(const BwdParams& p, size_t pix, int c0, float (&yv)[8], float (&dz)[8]) {
   load8(p.y + pix * p.C + c0, yv);
   float g1[8];
   load8(p.g1 + pix * p.ldg1 + p.offg1 + c0, g1);
@@ -239,16 +282,17 @@ __device__ __forceinline__ void compute_dz(const BwdParams& p, long long pix, in
 
 __global__ void __launch_bounds__(kStatThreads) bn_bwd_reduce_kernel(const BwdParams p) {
   const int chunks = p.C >> 3;
-  const int lanes = kStatThreads / chunks;
-  const int chunk = threadIdx.x % chunks;
-  const int pl = threadIdx.x / chunks;
+  const int lanes = kStatThreads >> p.cshift;
+  const int chunk = threadIdx.x & (chunks - 1);
+  const int pl = threadIdx.x >> p.cshift;
   float s[8], q[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
   if (pl < lanes) {
-    for (long long pix = (long long)blockIdx.x * lanes + pl; pix < p.P; pix += (long long)gridDim.x * lanes) {
+    const int stride = gridDim.x * lanes;
+    for (int pix = blockIdx.x * lanes + pl; pix < p.P; pix += stride) {
       float yv[8], dz[8];
-      compute_dz(p, pix, chunk * 8, yv, dz);
+      compute_dz(p, (size_t)pix, chunk * 8, yv, dz);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         s[i] += dz[i];
@@ -264,7 +308,7 @@ __global__ void __launch_bounds__(kStatThreads) bn_bwd_reduce_kernel(const BwdPa
   }
   __syncthreads();
   for (int o = threadIdx.x; o < 2 * p.C; o += kStatThreads) {
-    const int k = o / p.C, c = o - k * p.C;
+    const int k = o >= p.C, c = o - k * p.C;
     const int ch = c >> 3, ci = c & 7;
     float acc = 0.f;
     for (int l = 0; l < lanes; ++l) acc += red[l * chunks + ch][k * 8 + ci];
@@ -273,16 +317,14 @@ __global__ void __launch_bounds__(kStatThreads) bn_bwd_reduce_kernel(const BwdPa
 }
 
 // dgamma / dbeta (+= if accumulate) and the apply coefficients.  stats[4][C] from the forward.
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, double count, const float* __restrict__ stats,
-                                       const float* __restrict__ gamma, float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate,
-                                       float* __restrict__ coef) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double sdz = 0.0, sdzy = 0.0;
-  for (int b = 0; b < nblk; ++b) {
-    sdz += (double)partial[((size_t)b * 2 + 0) * C + c];
-    sdzy += (double)partial[((size_t)b * 2 + 1) * C + c];
-  }
+__global__ void __launch_bounds__(kFinThreads) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, double count,
+                                                                      const float* __restrict__ stats, const float* __restrict__ gamma,
+                                                                      float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate,
+                                                                      float* __restrict__ coef) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  double sdz, sdzy;
+  reduce_partials(partial, nblk, C, c, sdz, sdzy);
+  if (threadIdx.x >= 32 || c >= C) return;
   const double mean = stats[0 * C + c], rstd = stats[1 * C + c];
   const double dg = rstd * (sdzy - mean * sdz);  // sum dz * xhat
   const double db = sdz;
@@ -302,11 +344,11 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nb
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdParams p) {
-  const int chunks = p.C >> 3;
-  const long long total = p.P * chunks;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const long long pix = idx / chunks;
-    const int c0 = (int)(idx - pix * chunks) * 8;
+  const unsigned total = (unsigned)p.P << p.cshift;
+  const unsigned cmask = (1u << p.cshift) - 1u;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const size_t pix = idx >> p.cshift;
+    const int c0 = (int)(idx & cmask) * 8;
     float yv[8], dz[8];
     compute_dz(p, pix, c0, yv, dz);
     if (p.coef) {
@@ -333,10 +375,16 @@ using namespace b200;
 
 extern "C" {
 
+static int chunk_shift(int C) {  // log2(C / 8) for power-of-two C in [8, 2048], else -1
+  for (int s = 0; s <= 8; ++s)
+    if ((8 << s) == C) return s;
+  return -1;
+}
+
 int b200_bn_stat_blocks(long long P, int C) {
   const int lanes = kStatThreads / (C >> 3);
-  long long g = (P + lanes - 1) / lanes;
-  // enough pixels per block to amortise the smem reduction; at most 4 waves of 148 SMs
+  long long g = (P + 2 * lanes - 1) / (2 * lanes);
+  // two pixels in flight per thread; at most 4 resident blocks on each of the 148 SMs
   long long cap = 148 * 4;
   if (g > cap) g = cap;
   if (g < 1) g = 1;
@@ -346,15 +394,16 @@ int b200_bn_stat_blocks(long long P, int C) {
 // y[P][C] bf16 -> partial[nblk][2][C]; then finalize -> stats[4][C] (+ running stats).  training mode.
 int b200_bn_stats(const void* y, long long P, int C, void* partial, const float* gamma, const float* beta, float* running_mean, float* running_var,
                   long long* num_batches_tracked, float momentum, float eps, float* stats_out, cudaStream_t stream) {
-  if (C % 8 || C > 2048 || C < 8) {
-    b200_set_error("bn_stats: C must be a multiple of 8 in [8, 2048]");
+  const int cs = chunk_shift(C);
+  if (cs < 0 || P < 1 || P * (C >> 3) >= (1LL << 31)) {
+    b200_set_error("bn_stats: C must be a power of two in [8, 2048] and P*C/8 < 2^31");
     return B200_ERR_ARG;
   }
   const int nblk = b200_bn_stat_blocks(P, C);
-  bn_stats_kernel<<<nblk, kStatThreads, 0, stream>>>((const __nv_bfloat16*)y, P, C, (float*)partial);
+  bn_stats_kernel<<<nblk, kStatThreads, 0, stream>>>((const __nv_bfloat16*)y, (int)P, C, cs, (float*)partial);
   B200_CHECK_LAUNCH();
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>((const float*)partial, nblk, C, (double)P, gamma, beta, running_mean, running_var,
-                                                           num_batches_tracked, momentum, eps, stats_out);
+  bn_finalize_kernel<<<(C + 31) / 32, kFinThreads, 0, stream>>>((const float*)partial, nblk, C, (double)P, gamma, beta, running_mean, running_var,
+                                                                num_batches_tracked, momentum, eps, stats_out);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -368,11 +417,12 @@ int b200_bn_eval_coeffs(int C, const float* gamma, const float* beta, const floa
 
 int b200_bn_act(const void* y, long long P, int C, const float* scale, const float* shift, int act, void* out1, int ld1, int off1, void* out2, int ld2,
                 int off2, int dropout, unsigned seed, cudaStream_t stream) {
-  if (C % 8 || ld1 % 8 || off1 % 8 || ld2 % 8 || off2 % 8) {
-    b200_set_error("bn_act: channel counts / strides must be multiples of 8");
+  const int cs = chunk_shift(C);
+  if (cs < 0 || ld1 % 8 || off1 % 8 || ld2 % 8 || off2 % 8 || P * (C >> 3) >= (1LL << 31)) {
+    b200_set_error("bn_act: C must be a power of two >= 8; strides / offsets multiples of 8");
     return B200_ERR_ARG;
   }
-  ApplyParams p{(const __nv_bfloat16*)y, P, C, scale, shift, act, (__nv_bfloat16*)out1, ld1, off1, (__nv_bfloat16*)out2, ld2, off2, dropout, seed};
+  ApplyParams p{(const __nv_bfloat16*)y, (int)P, C, cs, scale, shift, act, (__nv_bfloat16*)out1, ld1, off1, (__nv_bfloat16*)out2, ld2, off2, dropout, seed};
   bn_act_kernel<<<grid_for(P * (C >> 3), 256), 256, 0, stream>>>(p);
   B200_CHECK_LAUNCH();
   return B200_OK;
@@ -384,14 +434,16 @@ int b200_bn_act(const void* y, long long P, int C, const float* scale, const flo
 int b200_bn_act_bwd(const void* y, long long P, int C, const float* stats /*[4][C] or null*/, const float* gamma, int act, const void* g1, int ldg1,
                     int offg1, const void* g2, int ldg2, int offg2, int dropout, unsigned seed, void* partial, float* coef /*[3][C] scratch*/,
                     float* dgamma, float* dbeta, int accumulate, void* dy, cudaStream_t stream) {
-  if (C % 8 || C > 2048 || ldg1 % 8 || offg1 % 8 || ldg2 % 8 || offg2 % 8) {
-    b200_set_error("bn_act_bwd: channel counts / strides must be multiples of 8");
+  const int cs = chunk_shift(C);
+  if (cs < 0 || ldg1 % 8 || offg1 % 8 || ldg2 % 8 || offg2 % 8 || P * (C >> 3) >= (1LL << 31)) {
+    b200_set_error("bn_act_bwd: C must be a power of two in [8, 2048]; strides / offsets multiples of 8");
     return B200_ERR_ARG;
   }
   BwdParams p{};
   p.y = (const __nv_bfloat16*)y;
-  p.P = P;
+  p.P = (int)P;
   p.C = C;
+  p.cshift = cs;
   p.scale = stats ? stats + 2 * C : nullptr;
   p.shift = stats ? stats + 3 * C : nullptr;
   p.act = act;
@@ -410,7 +462,7 @@ int b200_bn_act_bwd(const void* y, long long P, int C, const float* stats /*[4][
     const int nblk = b200_bn_stat_blocks(P, C);
     bn_bwd_reduce_kernel<<<nblk, kStatThreads, 0, stream>>>(p);
     B200_CHECK_LAUNCH();
-    bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>((const float*)partial, nblk, C, (double)P, stats, gamma, dgamma, dbeta, accumulate, coef);
+    bn_bwd_finalize_kernel<<<(C + 31) / 32, kFinThreads, 0, stream>>>((const float*)partial, nblk, C, (double)P, stats, gamma, dgamma, dbeta, accumulate, coef);
     B200_CHECK_LAUNCH();
     p.coef = coef;
   }

@@ -104,6 +104,7 @@ def wgan_step(
     dropout_masks: Optional[dict] = None,
     clip: float = 0.01,
     policy=None,
+    after_d_step=None,
 ):
     """wgan_l1.py:110-186 (recon='l1') / wgan_rmse.py (recon='rmse').
 
@@ -132,6 +133,8 @@ def wgan_step(
     with torch.no_grad():
         for v in leaves(D):  # every D parameter incl. BN gamma/beta and the Linear head (:152-153)
             v.clamp_(-clip, clip)
+    if after_d_step is not None:  # test hook: e.g. continue the G step from an implementation's post-step D weights
+        after_d_step(D)
 
     # ---- G step (:169-186)
     if update_g:
@@ -149,7 +152,8 @@ def wgan_step(
     return out
 
 
-def minimax_step(G: Params, D: Params, g_opt, d_opt, ground, mask, recon: str = "rmse", dropout_masks: Optional[dict] = None, policy=None):
+def minimax_step(G: Params, D: Params, g_opt, d_opt, ground, mask, recon: str = "rmse", dropout_masks: Optional[dict] = None, policy=None,
+                 after_d_step=None):
     """minimaxgan_rmse.py:110-173 (recon='rmse') / minimaxgan_l1.py (recon='l1')."""
     out = {}
     mask, masked = prepare(ground, mask)
@@ -171,6 +175,8 @@ def minimax_step(G: Params, D: Params, g_opt, d_opt, ground, mask, recon: str = 
     out["d_loss_real"], out["d_loss_fake"] = d_loss_real.item(), d_loss_fake.item()
     out["d_grads"] = grads_of(D)
     d_opt.step()
+    if after_d_step is not None:
+        after_d_step(D)
 
     set_requires_grad([D], False)
     g_opt.zero_grad()

@@ -65,6 +65,22 @@ def forced_policy(tr, nets):
     return nets.TeacherForcedPolicy(stored)
 
 
+def adopt_params(net, checks):
+    """after_d_step hook for the teacher-forced tier: first record the oracle's own post-step weights (compared with the
+    CUDA path's afterwards), then continue the step from the CUDA path's weights, so that the remaining forward passes
+    are compared layer by layer under identical parameters (sign descent flips a few near-zero-gradient elements)."""
+
+    def hook(params):
+        checks.update({k: v.detach().clone() for k, v in params.items()})
+        sd = net.state_dict()
+        with torch.no_grad():
+            for k, v in params.items():
+                if v.dtype.is_floating_point:
+                    v.copy_(sd[k].cpu())
+
+    return hook
+
+
 def check_forced_layers(pol, n_expected):
     assert len(pol.errors) == n_expected, (len(pol.errors), n_expected)
     worst = max(pol.errors.items(), key=lambda kv: kv[1])
@@ -106,14 +122,16 @@ def test_wgan_step(dev, recon):
     # ---- tier A: teacher-forced
     pol = forced_policy(tr, nets)
     G_, D_ = cl(gp), cl(dp)
-    o = steps.wgan_step(G_, D_, steps.make_optimizer("rmsprop", G_), steps.make_optimizer("rmsprop", D_), ground, mask, recon=recon, policy=pol)
+    d_post = {}
+    o = steps.wgan_step(G_, D_, steps.make_optimizer("rmsprop", G_), steps.make_optimizer("rmsprop", D_), ground, mask, recon=recon, policy=pol,
+                        after_d_step=adopt_params(D, d_post))
     check_forced_layers(pol, 24 + 3 * 7)
     assert rel(tr.last["inpainted"], o["inpainted"]) < 1e-4
     for k in ("d_loss_real", "d_loss_fake", "g_adv", "recon", "g_loss"):
         assert close(s[k], o[k], 2e-3), (k, s[k], o[k])
     check_grads(tr.fD, o["d_grads"], what="D grads (teacher-forced)")
     check_grads(tr.fG, o["g_grads"], what="G grads (teacher-forced)")
-    check_params(D, D_, RMSPROP_STEP, what="D after RMSprop + clip")
+    check_params(D, d_post, RMSPROP_STEP, what="D after RMSprop + clip")
     check_params(G, G_, RMSPROP_STEP, what="G after RMSprop")
     # ---- tier B: free-running fp32 reference
     G_, D_ = cl(gp), cl(dp)
@@ -162,14 +180,16 @@ def test_minimax_step(dev, recon):
     # ---- tier A: teacher-forced
     pol = forced_policy(tr, nets)
     G_, D_ = cl(gp), cl(dp)
-    o = steps.minimax_step(G_, D_, steps.make_optimizer("adam", G_), steps.make_optimizer("adam", D_), ground, mask, recon=recon, policy=pol)
+    d_post = {}
+    o = steps.minimax_step(G_, D_, steps.make_optimizer("adam", G_), steps.make_optimizer("adam", D_), ground, mask, recon=recon, policy=pol,
+                           after_d_step=adopt_params(D, d_post))
     check_forced_layers(pol, 24 + 3 * 7)
     assert rel(tr.last["inpainted"], o["inpainted"]) < 1e-4
     for k in ("d_loss_real", "d_loss_fake", "g_adv", "recon", "g_loss"):
         assert close(s[k], o[k], 2e-3), (k, s[k], o[k])
     check_grads(tr.fD, o["d_grads"], what="D grads (teacher-forced)")
     check_grads(tr.fG, o["g_grads"], what="G grads (teacher-forced)")
-    check_params(D, D_, ADAM_STEP, what="D after Adam")
+    check_params(D, d_post, ADAM_STEP, what="D after Adam")
     check_params(G, G_, ADAM_STEP, what="G after Adam")
     # ---- tier B: free-running fp32 reference
     G_, D_ = cl(gp), cl(dp)
@@ -295,3 +315,28 @@ def test_inference_composite(dev):
     assert rel(out, ref) < TOL
     keep = torch.ceil(mask) == 0
     assert torch.equal(out.cpu()[keep], ground[keep])  # pixels outside the mask pass through bit-exactly
+
+
+def test_begin_call_surface(dev, tmp_path):
+    """experiment_list.<recipe>.begin(state, loaders) (train.py:183-186 / wgan_l1.py:15): state keys of train.py:22-36, loaders yield
+    (ground, mask, segment); history dicts, the -7777 sentinel and the epochN_G.pt checkpoint follow the reference."""
+    from gan_inpainting_b200.experiment_list import minimaxgan_rmse, wgan_l1
+    _, nets, _, synth = _imports()
+    batches = []
+    for i in range(3):
+        g, m = synth.make_batch(2, 128, seed=40 + i)
+        batches.append((g, m, torch.zeros(2, dtype=torch.long)))
+    state = dict(experiments=["wgan_l1"], numepoch=1, batchsize=2, generator="unet", discriminator="patchgan", imagedim=128, saveevery=1, updatediscevery=3,
+                 evalevery=1, debug="false", experiment_dir=str(tmp_path / "model"), log_dir=str(tmp_path / "log"))
+    out = wgan_l1.begin(state, {"train": batches, "test": batches, "extra": batches})
+    h = out["history"]
+    assert len(h) == 2 and out["d_iter"] == 6 and out["g_iter"] == 0
+    assert h[0]["g"]["total"] == -7777 and h[0]["d"]["update_count"] == 3  # 3 batches < 140: the WGAN schedule never updates G
+    assert all(v == -7777 for v in h[0]["gradients"]["avg_g"].values()) and all(v > 0 for v in h[0]["gradients"]["avg_d"].values())
+    assert not any("bias" in n for n in h[0]["gradients"]["avg_d"])
+    sd = torch.load(tmp_path / "model" / "epoch1_G.pt")
+    assert set(sd) == set(nets.init_unet(0))
+    out = minimaxgan_rmse.begin(dict(state, numepoch=0), {"train": batches, "test": batches, "extra": batches})
+    h = out["history"]
+    assert out["g_iter"] == 3 and h[0]["g"]["update_count"] == 3 and h[0]["g"]["total"] > 0
+    assert all(v > 0 for v in h[0]["gradients"]["avg_g"].values())
