@@ -26,8 +26,8 @@ U = c_uint32
 # name -> argtypes (all of these return an int status; 0 == OK).  Order == include/b200_inpaint.h.
 SIGNATURES = {
     # ---- tcgen05 implicit-GEMM convolutions (csrc/conv_gemm.cu)
-    "b200_conv_s2_gemm": [P, I, I, I, I, P, I, P, I, I, I, S],
-    "b200_convt_s2_gemm": [P, I, I, I, I, I, P, I, P, I, I, I, S],
+    "b200_conv_s2_gemm": [P, I, I, I, I, P, I, P, I, I, I, P, POINTER(c_int), S],
+    "b200_convt_s2_gemm": [P, I, I, I, I, I, P, I, P, I, I, I, P, POINTER(c_int), S],
     "b200_wgrad_gemm": [P, I, I, I, I, I, P, I, P, POINTER(c_int), I, I, S],
     "b200_debug_tma_probe": [P, I, I, I, I, I, I, I, I, I, I, I, I, I, P, S],
     # ---- weight layouts (csrc/pack.cu)
@@ -36,6 +36,7 @@ SIGNATURES = {
     "b200_wgrad_reduce": [P, I, I, I, P, I, S],
     # ---- BatchNorm + activation (csrc/norm_act.cu)
     "b200_bn_stats": [P, L, I, P, P, P, P, P, P, F, F, P, S],
+    "b200_bn_finalize": [P, I, L, I, P, P, P, P, P, F, F, P, S],
     "b200_bn_eval_coeffs": [I, P, P, P, P, F, P, S],
     "b200_bn_act": [P, L, I, P, P, I, P, I, I, P, I, I, I, U, S],
     "b200_bn_act_bwd": [P, L, I, P, P, I, P, I, I, P, I, I, I, U, P, P, P, P, I, P, S],
@@ -68,6 +69,7 @@ VALUE_FUNCS = {
     "b200_last_error": (c_char_p, []),
     "b200_launch_count": (c_longlong, []),
     "b200_bn_stat_blocks": (c_int, [L, I]),
+    "b200_igemm_stat_rows": (c_int, []),
     "b200_wgrad_c1_blocks": (c_int, []),
     "b200_recon_scratch_floats": (c_int, []),
 }

@@ -162,6 +162,41 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// ---------------------------------------------------------------- warp-level bf16 MMA for the HBM-bound 1-channel-side layers
+// D(16x8, fp32) += A(16x16, bf16, row) * B(16x8, bf16, col).  Fragment layout (g = lane >> 2, q = lane & 3):
+//   a0 = A[g][2q..2q+1], a1 = A[g+8][2q..], a2 = A[g][2q+8..], a3 = A[g+8][2q+8..];  b0 = B[2q..2q+1][g], b1 = B[2q+8..][g];
+//   d0,d1 = D[g][2q..2q+1], d2,d3 = D[g+8][2q..2q+1]
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// four transposed 8x8 b16 matrices from shared memory: lane l supplies the address of row (l & 7) of matrix (l >> 3)
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(smem_row)));
+}
+// 16-byte asynchronous global -> shared copy (LDGSTS), bypassing L1
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+// 4-byte variant with zero fill when !valid (image halos)
+__device__ __forceinline__ void cp_async4_zfill(void* smem_dst, const void* gmem_src, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(valid ? 4 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// fp32 pair -> bf16x2 "hi" plus the bf16x2 residual "lo" (hi + lo carries ~16 mantissa bits: fp32-grade operands on the bf16 pipe)
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16x2(x0, x1);
+  const float2 h = unpack_bf16x2(hi);
+  lo = pack_bf16x2(x0 - h.x, x1 - h.y);
+}
+
 // counter-based keep/drop bit for Dropout(0.5): stateless, so forward and backward regenerate it.
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   x ^= x >> 16;

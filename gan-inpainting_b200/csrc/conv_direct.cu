@@ -13,19 +13,28 @@
 // product per image with the effective weight E = W5 (*) Wl (full correlation of the two).
 #include "common.cuh"
 
+#include <mutex>
+
 namespace b200 {
 
 enum { ACT_NONE = 0, ACT_LEAKY = 1, ACT_RELU = 2, ACT_TANH = 3 };
 
 // ------------------------------------------------------------------------------------------------
-// conv_c1_fwd: block = 256 output pixels (TOH x TOW); the (2*TOH+2) x (2*TOW+2) input window is staged in shared
-// memory (zero halo, mask multiply applied once), thread = 4 output channels with the 64 weights in registers.
+// conv_c1_fwd: y[pix][c] = sum_t patch[pix][t] * w[c][t]  (t = kh*4+kw, K = 16) on the warp-level bf16 MMA
+// (m16n8k16), fp32 operands carried as bf16 hi+lo pairs (3 MMAs: hi*hi + lo*hi + hi*lo), fp32 accumulation.
+// Block = 256 output pixels (TOH x TOW); the (2*TOH+2) x (2*TOW+2) input window is staged in shared memory (zero
+// halo, mask multiply applied once).  Warp = two 16-pixel row segments; the n-columns of the MMA are permuted so that
+// a lane ends up with C/4 CONSECUTIVE channels of a pixel and stores them with 128-bit stores (a quad covers the pixel's
+// whole channel vector).  The kernel is bound by the bf16 output stream (2*C bytes per pixel).
 // ------------------------------------------------------------------------------------------------
 constexpr int kXsFloats = 34 * 68;  // covers 18 x 68 (8 x 32 tile) and 34 x 36 (16 x 16 tile)
 
+template <int C>
 __global__ void __launch_bounds__(256) conv_c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ xmul, int H, int W, int tow_shift,
-                                                          const float* __restrict__ w, int C, int act, __nv_bfloat16* __restrict__ y,
+                                                          const float* __restrict__ w, int act, __nv_bfloat16* __restrict__ y,
                                                           __nv_bfloat16* __restrict__ y2, int ld2, int off2) {
+  constexpr int NT = C / 8;   // n-tiles
+  constexpr int CPL = C / 4;  // consecutive channels per lane
   __shared__ __align__(16) float xs[kXsFloats];
   const int TOW = 1 << tow_shift, TOH = 256 >> tow_shift;
   const int Ho = H >> 1, Wo = W >> 1;
@@ -52,137 +61,162 @@ __global__ void __launch_bounds__(256) conv_c1_fwd_kernel(const float* __restric
       xs[r * xstride + cI] = v;
     }
   }
-  const int lanes = C >> 2;     // threads per output pixel
-  const int ppp = 256 / lanes;  // pixels per pass
-  const int cg = threadIdx.x % lanes;
-  const int pl = threadIdx.x / lanes;
-  float wr[16][4];
+  const int g = lane >> 2, q = lane & 3;
+  // B fragments: MMA column g of n-tile j carries channel (g>>1)*CPL + 2j + (g&1)
+  uint32_t bhi[NT][2], blo[NT][2];
 #pragma unroll
-  for (int t = 0; t < 16; ++t)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) wr[t][i] = __ldg(w + (size_t)(cg * 4 + i) * 16 + t);
+  for (int j = 0; j < NT; ++j) {
+    const float* wc = w + (size_t)((g >> 1) * CPL + 2 * j + (g & 1)) * 16 + 2 * q;
+    const float2 w0 = __ldg(reinterpret_cast<const float2*>(wc));
+    const float2 w1 = __ldg(reinterpret_cast<const float2*>(wc + 8));
+    split_bf16x2(w0.x, w0.y, bhi[j][0], blo[j][0]);
+    split_bf16x2(w1.x, w1.y, bhi[j][1], blo[j][1]);
+  }
   __syncthreads();
 
-  for (int pp = pl; pp < 256; pp += ppp) {
-    const int ol_h = pp >> tow_shift, ol_w = pp & (TOW - 1);
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int kh = q >> 1, kw = (q & 1) * 2;  // taps 2q, 2q+1 (and +8: kh + 2)
+#pragma unroll 1
+  for (int m = 0; m < 2; ++m) {
+    const int mt = warp * 2 + m;  // 16 m-tiles of 16 pixels per block
+    const int ol_h = (mt * 16) >> tow_shift, ol_w0 = (mt * 16) & (TOW - 1);
+    uint32_t ahi[4], alo[4];
 #pragma unroll
-    for (int kh = 0; kh < 4; ++kh) {
-      const float* row = xs + (2 * ol_h + kh) * xstride + 2 * ol_w;
-      const float2 a = *reinterpret_cast<const float2*>(row);
-      const float2 c2 = *reinterpret_cast<const float2*>(row + 2);
-      const float v[4] = {a.x, a.y, c2.x, c2.y};
+    for (int i = 0; i < 4; ++i) {
+      const int pw = ol_w0 + g + (i & 1) * 8, kk = kh + (i >> 1) * 2;
+      const float2 v = *reinterpret_cast<const float2*>(xs + (2 * ol_h + kk) * xstride + 2 * pw + kw);
+      split_bf16x2(v.x, v.y, ahi[i], alo[i]);
+    }
+    float acc[NT][4];
 #pragma unroll
-      for (int kw = 0; kw < 4; ++kw)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acc[i] = fmaf(v[kw], wr[kh * 4 + kw][i], acc[i]);
+    for (int j = 0; j < NT; ++j) {
+      acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+      mma_bf16_16816(acc[j], alo, bhi[j][0], bhi[j][1]);
+      mma_bf16_16816(acc[j], ahi, blo[j][0], blo[j][1]);
+      mma_bf16_16816(acc[j], ahi, bhi[j][0], bhi[j][1]);
     }
     if (act == ACT_LEAKY) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[i] = acc[i] > 0.f ? acc[i] : 0.2f * acc[i];
+      for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[j][i] = acc[j][i] > 0.f ? acc[j][i] : 0.2f * acc[j][i];
     }
-    const size_t pix = ((size_t)b * Ho + (oh0 + ol_h)) * Wo + (ow0 + ol_w);
-    uint2 o = make_uint2(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]));
-    *reinterpret_cast<uint2*>(y + pix * C + cg * 4) = o;
-    if (y2) {  // relu copy into the decoder's concat buffer (skip connection)
-      o = make_uint2(pack_bf16x2(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f)), pack_bf16x2(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f)));
-      *reinterpret_cast<uint2*>(y2 + pix * ld2 + off2 + cg * 4) = o;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {  // pixel g (d0,d1) and pixel g+8 (d2,d3)
+      const size_t pix = ((size_t)b * Ho + (oh0 + ol_h)) * Wo + (ow0 + ol_w0 + g + half * 8);
+      uint32_t o[NT];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) o[j] = pack_bf16x2(acc[j][2 * half], acc[j][2 * half + 1]);
+      uint4* dst = reinterpret_cast<uint4*>(y + pix * C + q * CPL);
+#pragma unroll
+      for (int j = 0; j < NT; j += 4) dst[j >> 2] = make_uint4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+      if (y2) {  // relu copy into the decoder's concat buffer (skip connection)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) o[j] = pack_bf16x2(fmaxf(acc[j][2 * half], 0.f), fmaxf(acc[j][2 * half + 1], 0.f));
+        uint4* dst2 = reinterpret_cast<uint4*>(y2 + pix * ld2 + off2 + q * CPL);
+#pragma unroll
+        for (int j = 0; j < NT; j += 4) dst2[j >> 2] = make_uint4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+      }
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// convt_c1_fwd: block = 16x16 input pixels (+1 halo).  Phase 1: per input pixel the 16 tap dot
-// products over C (lane = 8 channels x 8 taps, transposing shuffle reduction) -> smem T[pix][16].
-// Phase 2: every output pixel sums its 4 contributing (pixel, tap) entries.
-//   y[2i+p, 2j+q] = sum_{a,b} T[i+p+a-1, j+q+b-1][(3-p-2a)*4 + (3-q-2b)]
+// convt_c1_fwd: block = 16x16 input pixels (+1 halo).
+// Phase 1: T[pix][t] = sum_c z[pix][c] * w[c][t] (16 taps) for the 18 x 18 halo window on the warp-level bf16 MMA
+//   (m16n8k16; z is bf16, the fp32 weights are carried as bf16 hi+lo pairs).  The MMA's k index is permuted so that a
+//   lane loads 8 CONSECUTIVE channels of its pixel with one 128-bit load (a quad covers 64 contiguous bytes): for the
+//   32-channel group gi and k-step s, logical k = 2q+e <-> channel gi*32 + q*8 + 4s + e, k = 2q+8+e <-> ... + 2 + e.
+// Phase 2: every output pixel sums its 4 contributing (pixel, tap) entries
+//   y[2i+p, 2j+q] = sum_{a,b} T[i+p+a-1, j+q+b-1][(3-p-2a)*4 + (3-q-2b)]   (+ bias, tanh, composite / mask multiply)
 // ------------------------------------------------------------------------------------------------
 constexpr int kTT = 16;             // tile side (input pixels)
 constexpr int kTH = kTT + 2;        // with halo
 
-template <int LPP>  // lanes per pixel per tap-half = C/8 (8 or 16)
+template <int C>
 __global__ void __launch_bounds__(256) convt_c1_fwd_kernel(const __nv_bfloat16* __restrict__ z, int B, int H, int W, int ldz, const float* __restrict__ w,
                                                            const float* __restrict__ bias, int act, const float* __restrict__ base,
                                                            const float* __restrict__ mul, float* __restrict__ y, float* __restrict__ comp) {
+  constexpr int NG = C / 32;  // 32-channel groups
   __shared__ float T[kTH * kTH][17];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int LP = 2 * LPP;       // lanes per pixel
-  constexpr int PPW = 32 / LP;      // pixels per warp pass
-  const int chunk = lane & (LPP - 1);
-  const int half = (lane / LPP) & 1;
-  const int pslot = lane / LP;
+  const int g = lane >> 2, q = lane & 3;
   const int tiles_w = W / kTT, tiles_h = H / kTT;
   const int tw_i = blockIdx.x % tiles_w;
   const int th_i = (blockIdx.x / tiles_w) % tiles_h;
   const int b = blockIdx.x / (tiles_w * tiles_h);
   const int i0 = th_i * kTT - 1, j0 = tw_i * kTT - 1;  // image coordinates of the halo origin
 
-  float wr[8][8];  // [tap in half][channel]
+  // B fragments [group][k-step][n-tile]: b0 = {w[ch][tap], w[ch+1][tap]}, b1 = {w[ch+2][tap], w[ch+3][tap]}, tap = nt*8 + g
+  uint32_t bhi[NG][2][2][2], blo[NG][2][2][2];
 #pragma unroll
-  for (int t = 0; t < 8; ++t)
+  for (int gi = 0; gi < NG; ++gi)
 #pragma unroll
-    for (int c = 0; c < 8; ++c) wr[t][c] = __ldg(w + (size_t)(chunk * 8 + c) * 16 + half * 8 + t);
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const float* wc = w + (size_t)(gi * 32 + q * 8 + 4 * s) * 16 + nt * 8 + g;
+        split_bf16x2(__ldg(wc), __ldg(wc + 16), bhi[gi][s][nt][0], blo[gi][s][nt][0]);
+        split_bf16x2(__ldg(wc + 32), __ldg(wc + 48), bhi[gi][s][nt][1], blo[gi][s][nt][1]);
+      }
 
-  const int npix = kTH * kTH;
-  constexpr int U = 4;  // pixels in flight per lane (hides the HBM latency of the z loads)
-  for (int base0 = warp * PPW; base0 < npix; base0 += U * 8 * PPW) {
-    uint4 q[U];
-    bool ok[U];
-    int pps[U];
+  constexpr int npix = kTH * kTH;
+  constexpr int nmt = (npix + 15) / 16;
+  auto load_rows = [&](int mt, uint4 (&qa)[NG], uint4 (&qb)[NG]) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int pp = base0 + u * 8 * PPW + pslot;
+    for (int h = 0; h < 2; ++h) {
+      const int pp = mt * 16 + g + h * 8;
       const int li = pp / kTH, lj = pp - li * kTH;
       const int i = i0 + li, j = j0 + lj;
-      pps[u] = pp;
-      ok[u] = (pp < npix) && i >= 0 && i < H && j >= 0 && j < W;
-      q[u] = make_uint4(0u, 0u, 0u, 0u);
-      if (ok[u]) q[u] = __ldg(reinterpret_cast<const uint4*>(z + (((size_t)b * H + i) * W + j) * ldz + chunk * 8));
+      const bool ok = (pp < npix) && i >= 0 && i < H && j >= 0 && j < W;
+      const __nv_bfloat16* src = z + (((size_t)b * H + i) * W + j) * ldz + q * 8;
+#pragma unroll
+      for (int gi = 0; gi < NG; ++gi) {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (ok) v = __ldg(reinterpret_cast<const uint4*>(src + gi * 32));
+        if (h == 0) qa[gi] = v; else qb[gi] = v;
+      }
     }
+  };
+  uint4 qa[NG], qb[NG];
+  if (warp < nmt) load_rows(warp, qa, qb);
+  for (int mt = warp; mt < nmt; mt += 8) {
+    uint4 na[NG], nb[NG];
+    if (mt + 8 < nmt) load_rows(mt + 8, na, nb);  // next tile's rows are in flight while this one is multiplied
+    float acc[2][4];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (base0 + u * 8 * PPW >= npix) break;  // warp-uniform
-      const int pp = pps[u];
-      float v[8];
+    for (int nt = 0; nt < 2; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
 #pragma unroll
-      for (int t = 0; t < 8; ++t) v[t] = 0.f;
-      if (ok[u]) {
-        const uint32_t uu[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
-        float f[8];
+    for (int gi = 0; gi < NG; ++gi) {
+      const uint32_t pa[4] = {qa[gi].x, qa[gi].y, qa[gi].z, qa[gi].w};
+      const uint32_t pb[4] = {qb[gi].x, qb[gi].y, qb[gi].z, qb[gi].w};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float2 t2 = unpack_bf16x2(uu[k]);
-          f[2 * k] = t2.x;
-          f[2 * k + 1] = t2.y;
+      for (int s = 0; s < 2; ++s) {
+        const uint32_t a[4] = {pa[2 * s], pb[2 * s], pa[2 * s + 1], pb[2 * s + 1]};
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          mma_bf16_16816(acc[nt], a, blo[gi][s][nt][0], blo[gi][s][nt][1]);
+          mma_bf16_16816(acc[nt], a, bhi[gi][s][nt][0], bhi[gi][s][nt][1]);
         }
-#pragma unroll
-        for (int t = 0; t < 8; ++t)
-#pragma unroll
-          for (int c = 0; c < 8; ++c) v[t] = fmaf(f[c], wr[t][c], v[t]);
       }
-      // transposing reduction over the 8 chunk lanes (bits 0..2): lane keeps tap (lane & 7)
+    }
+    const int pp0 = mt * 16 + g;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const bool up = lane & 4;
-        const float send = up ? v[k] : v[k + 4];
-        const float keep = up ? v[k + 4] : v[k];
-        v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    for (int nt = 0; nt < 2; ++nt) {
+      if (pp0 < npix) {
+        T[pp0][nt * 8 + 2 * q] = acc[nt][0];
+        T[pp0][nt * 8 + 2 * q + 1] = acc[nt][1];
       }
+      if (pp0 + 8 < npix) {
+        T[pp0 + 8][nt * 8 + 2 * q] = acc[nt][2];
+        T[pp0 + 8][nt * 8 + 2 * q + 1] = acc[nt][3];
+      }
+    }
+    if (mt + 8 < nmt) {
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const bool up = lane & 2;
-        const float send = up ? v[k] : v[k + 2];
-        const float keep = up ? v[k + 2] : v[k];
-        v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+      for (int gi = 0; gi < NG; ++gi) {
+        qa[gi] = na[gi];
+        qb[gi] = nb[gi];
       }
-      {
-        const bool up = lane & 1;
-        const float send = up ? v[0] : v[1];
-        const float keep = up ? v[1] : v[0];
-        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-      }
-      if (LPP == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 8);
-      if (pp < npix && (chunk < 8)) T[pp][half * 8 + (lane & 7)] = v[0];
     }
   }
   __syncthreads();
@@ -191,13 +225,13 @@ __global__ void __launch_bounds__(256) convt_c1_fwd_kernel(const __nv_bfloat16* 
   const int Ho = 2 * H, Wo = 2 * W;
   for (int o = threadIdx.x; o < 4 * kTT * kTT; o += 256) {
     const int lo_h = o / (2 * kTT), lo_w = o - lo_h * (2 * kTT);
-    const int p = lo_h & 1, q = lo_w & 1;
+    const int p = lo_h & 1, qq = lo_w & 1;
     const int li = (lo_h >> 1) + 1, lj = (lo_w >> 1) + 1;  // halo-local input coordinates of (i, j)
     float s = bv;
 #pragma unroll
     for (int a = 0; a < 2; ++a)
 #pragma unroll
-      for (int bb = 0; bb < 2; ++bb) s += T[(li + p + a - 1) * kTH + (lj + q + bb - 1)][(3 - p - 2 * a) * 4 + (3 - q - 2 * bb)];
+      for (int bb = 0; bb < 2; ++bb) s += T[(li + p + a - 1) * kTH + (lj + qq + bb - 1)][(3 - p - 2 * a) * 4 + (3 - qq - 2 * bb)];
     if (act == ACT_TANH) s = tanhf(s);
     const int oh = th_i * 2 * kTT + lo_h, ow = tw_i * 2 * kTT + lo_w;
     const size_t idx = ((size_t)b * Ho + oh) * Wo + ow;
@@ -213,98 +247,122 @@ __global__ void __launch_bounds__(256) convt_c1_fwd_kernel(const __nv_bfloat16* 
 }
 
 // ------------------------------------------------------------------------------------------------
-// wgrad_c1: dW[c][kh*4+kw] = sum_{b,i,j} z[b,i,j,c] * g[b,2i+kh-1,2j+kw-1]
-// Persistent blocks walk 8 x 32 pixel tiles: the 18 x 66 window of g is staged in shared memory (zero halo, mask
-// multiply applied once); lane = 8 channels x 8 taps accumulators, the next pixel's z is prefetched.
-// Deterministic per-block partials.
+// wgrad_c1: dW[c][t] = sum_{b,i,j} z[b,i,j,c] * g[b,2i+kh-1,2j+kw-1],  t = kh*4+kw
+// as D[t][c] = sum_pix P[t][pix] * z[pix][c] on the warp-level bf16 MMA (m16n8k16): A = the im2col'd fp32 image g as
+// bf16 hi+lo pairs (built from a shared-memory window, mask multiply applied once), B = z read with ldmatrix.trans
+// from a cp.async-staged shared-memory tile (so the HBM stream of z is fully asynchronous, double buffered).
+// Persistent blocks walk 4 x 32 pixel tiles, one 16-pixel k-step per warp and tile; accumulators stay in registers
+// across tiles; deterministic per-block partials.
 // ------------------------------------------------------------------------------------------------
-constexpr int kWgTH = 8, kWgTW = 32, kWgStride = 2 * kWgTW + 4;
+constexpr int kWgTH = 4, kWgTW = 32, kWgStride = 2 * kWgTW + 4, kWgRows = 2 * kWgTH + 2;
 
-template <int LPP>
+template <int C>
 __global__ void __launch_bounds__(256) wgrad_c1_kernel(const __nv_bfloat16* __restrict__ z, int B, int H, int W, int ldz, const float* __restrict__ g,
                                                        const float* __restrict__ gmul, float* __restrict__ partial) {
-  constexpr int LP = 2 * LPP;       // lanes per pixel
-  constexpr int PPP = 256 / LP;     // pixels per pass (whole block)
-  constexpr int C = 8 * LPP;
-  __shared__ __align__(16) float gs[(2 * kWgTH + 2) * kWgStride];
-  __shared__ float sum[C * 16];
+  constexpr int NT = C / 8;
+  constexpr int ROWB = (C + 8) * 2;              // padded shared-memory row (bytes): conflict-free ldmatrix
+  constexpr int ZBYTES = kWgTH * kWgTW * ROWB;   // one stage of z
+  constexpr int GFLOATS = kWgRows * kWgStride;
+  extern __shared__ __align__(16) uint8_t wsm[];
+  uint8_t* zs = wsm;                                   // [2][128][ROWB]
+  float* gs = reinterpret_cast<float*>(wsm + 2 * ZBYTES);  // [2][GFLOATS] image window, then [2][GFLOATS] mask window
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int chunk = threadIdx.x & (LPP - 1);
-  const int half = (threadIdx.x / LPP) & 1;
-  const int slot = threadIdx.x / LP;  // pixel slot inside the block
+  const int gq = lane >> 2, q = lane & 3;
   const int Hg = 2 * H, Wg = 2 * W;
   const int tiles_w = W / kWgTW, tiles_h = H / kWgTH;
   const int ntiles = B * tiles_w * tiles_h;
-  float acc[8][8];
-#pragma unroll
-  for (int t = 0; t < 8; ++t)
-#pragma unroll
-    for (int c = 0; c < 8; ++c) acc[t][c] = 0.f;
 
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  auto stage_tile = [&](int tile, int buf) {
     const int tw_i = tile % tiles_w;
     const int th_i = (tile / tiles_w) % tiles_h;
     const int b = tile / (tiles_w * tiles_h);
     const int i0 = th_i * kWgTH, j0 = tw_i * kWgTW;
+    // z: 128 pixels x C channels, 16-byte chunks
+    constexpr int CH = C / 8;
+    uint8_t* zd = zs + buf * ZBYTES;
+    for (int e = threadIdx.x; e < kWgTH * kWgTW * CH; e += 256) {
+      const int pp = e / CH, ch = e - pp * CH;
+      const int li = pp >> 5, lj = pp & 31;
+      cp_async16(zd + pp * ROWB + ch * 16, z + (((size_t)b * H + i0 + li) * W + j0 + lj) * ldz + ch * 8);
+    }
+    // g (and mask) window: rows 2*i0-1 .. 2*i0+2*TH, cols 2*j0-1 .. 2*j0+2*TW, zero-filled halo
     const float* gb = g + (size_t)b * Hg * Wg;
     const float* mb = gmul ? gmul + (size_t)b * Hg * Wg : nullptr;
-    __syncthreads();  // previous tile's readers are done
-    for (int r = warp; r < 2 * kWgTH + 2; r += 8) {
-      const int ih = 2 * i0 - 1 + r;
-      const bool rok = ih >= 0 && ih < Hg;
-      for (int cI = lane; cI < 2 * kWgTW + 2; cI += 32) {
-        const int iw = 2 * j0 - 1 + cI;
-        float v = 0.f;
-        if (rok && iw >= 0 && iw < Wg) {
-          v = __ldg(gb + (size_t)ih * Wg + iw);
-          if (mb) v *= __ldg(mb + (size_t)ih * Wg + iw);
-        }
-        gs[r * kWgStride + cI] = v;
-      }
+    float* gd = gs + buf * GFLOATS;
+    float* md = gs + (2 + buf) * GFLOATS;
+    for (int e = threadIdx.x; e < kWgRows * (2 * kWgTW + 2); e += 256) {
+      const int r = e / (2 * kWgTW + 2), cI = e - r * (2 * kWgTW + 2);
+      const int ih = 2 * i0 - 1 + r, iw = 2 * j0 - 1 + cI;
+      const bool ok = ih >= 0 && ih < Hg && iw >= 0 && iw < Wg;
+      const size_t off = ok ? (size_t)ih * Wg + iw : 0;
+      cp_async4_zfill(gd + r * kWgStride + cI, gb + off, ok);
+      if (mb) cp_async4_zfill(md + r * kWgStride + cI, mb + off, ok);
+    }
+    cp_async_commit();
+  };
+
+  float acc[NT][4];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+
+  int buf = 0;
+  if ((int)blockIdx.x < ntiles) stage_tile(blockIdx.x, 0);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+    const int next = tile + gridDim.x;
+    if (next < ntiles) {
+      stage_tile(next, buf ^ 1);  // the other buffer was released by the barrier that ended the previous iteration
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
-    const __nv_bfloat16* zt = z + ((size_t)b * H * W) * ldz + chunk * 8;
-    auto zaddr = [&](int pp) { return zt + ((size_t)(i0 + (pp >> 5)) * W + (j0 + (pp & 31))) * ldz; };
-    uint4 q = __ldg(reinterpret_cast<const uint4*>(zaddr(slot)));
-#pragma unroll 2
-    for (int pp = slot; pp < kWgTH * kWgTW; pp += PPP) {
-      const uint4 cur = q;
-      if (pp + PPP < kWgTH * kWgTW) q = __ldg(reinterpret_cast<const uint4*>(zaddr(pp + PPP)));
-      const uint32_t u[4] = {cur.x, cur.y, cur.z, cur.w};
-      float f[8];
+    // this warp's k-step: pixels (row = warp / 2, cols (warp & 1) * 16 + 0..15)
+    const int r = warp >> 1, c0 = (warp & 1) * 16;
+    const float* gd = gs + buf * GFLOATS;
+    const int moff = 2 * GFLOATS;  // mask window of the same buffer
+    uint32_t ahi[4], alo[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 t2 = unpack_bf16x2(u[k]);
-        f[2 * k] = t2.x;
-        f[2 * k + 1] = t2.y;
+    for (int i = 0; i < 4; ++i) {
+      const int t = gq + (i & 1) * 8, kp = 2 * q + (i >> 1) * 8;  // tap, first of the two pixels
+      const float* src = gd + (2 * r + (t >> 2)) * kWgStride + 2 * (c0 + kp) + (t & 3);
+      float v0 = src[0], v1 = src[2];
+      if (gmul) {
+        v0 *= src[moff];
+        v1 *= src[moff + 2];
       }
-      const int li = pp >> 5, lj = pp & 31;
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const float* row = gs + (2 * li + half * 2 + r) * kWgStride + 2 * lj;
-        const float2 a = *reinterpret_cast<const float2*>(row);
-        const float2 c2 = *reinterpret_cast<const float2*>(row + 2);
-        const float gv[4] = {a.x, a.y, c2.x, c2.y};
-#pragma unroll
-        for (int kw = 0; kw < 4; ++kw)
-#pragma unroll
-          for (int c = 0; c < 8; ++c) acc[r * 4 + kw][c] = fmaf(f[c], gv[kw], acc[r * 4 + kw][c]);
-      }
+      split_bf16x2(v0, v1, ahi[i], alo[i]);
     }
+    const uint8_t* zrow = zs + buf * ZBYTES + (size_t)((warp * 16) + (lane & 7) + ((lane >> 3) & 1) * 8) * ROWB + ((lane >> 4) * 8) * 2;
+#pragma unroll
+    for (int j = 0; j < NT; j += 2) {
+      uint32_t bf[4];
+      ldmatrix_x4_trans(bf, zrow + j * 16);
+      mma_bf16_16816(acc[j], alo, bf[0], bf[1]);
+      mma_bf16_16816(acc[j], ahi, bf[0], bf[1]);
+      mma_bf16_16816(acc[j + 1], alo, bf[2], bf[3]);
+      mma_bf16_16816(acc[j + 1], ahi, bf[2], bf[3]);
+    }
+    __syncthreads();  // everyone is done with `buf` before the next iteration's prefetch overwrites it
+  }
+
+  // cross-warp reduction in shared memory (reusing the staging buffers): red[warp][t][c]
+  float* red = reinterpret_cast<float*>(wsm);
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    float* rw = red + (size_t)warp * 16 * C;
+    rw[gq * C + j * 8 + 2 * q] = acc[j][0];
+    rw[gq * C + j * 8 + 2 * q + 1] = acc[j][1];
+    rw[(gq + 8) * C + j * 8 + 2 * q] = acc[j][2];
+    rw[(gq + 8) * C + j * 8 + 2 * q + 1] = acc[j][3];
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < C * 16; k += 256) sum[k] = 0.f;
-  __syncthreads();
-  for (int s = 0; s < PPP; ++s) {
-    if (slot == s) {
+  for (int k = threadIdx.x; k < C * 16; k += 256) {
+    const int c = k >> 4, t = k & 15;
+    float s = 0.f;
 #pragma unroll
-      for (int t = 0; t < 8; ++t)
-#pragma unroll
-        for (int c = 0; c < 8; ++c) sum[(chunk * 8 + c) * 16 + half * 8 + t] += acc[t][c];
-    }
-    __syncthreads();
+    for (int wv = 0; wv < 8; ++wv) s += red[((size_t)wv * 16 + t) * C + c];
+    partial[(size_t)blockIdx.x * C * 16 + k] = s;
   }
-  for (int k = threadIdx.x; k < C * 16; k += 256) partial[(size_t)blockIdx.x * C * 16 + k] = sum[k];
 }
 
 __global__ void partial_sum_kernel(const float* __restrict__ partial, int nblk, int n, float* __restrict__ out, int accumulate) {
@@ -472,12 +530,15 @@ int b200_conv_c1_fwd(const float* x, const float* xmul, int B, int H, int W, con
   int tow_shift = 5;  // 8 x 32 output tile; 16 x 16 when the image is only 16 pixels wide
   if (Wo < 32) tow_shift = 4;
   const int TOW = 1 << tow_shift, TOH = 256 >> tow_shift;
-  if ((C != 64 && C != 128 && C != 32 && C != 256) || (H & 1) || (W & 1) || B < 1 || ld2 % 4 || off2 % 4 || Wo % TOW || Ho % TOH) {
-    b200_set_error("conv_c1_fwd: C must be 32/64/128/256; output must tile by 8x32 (or 16x16)");
+  if ((C != 64 && C != 128) || (H & 1) || (W & 1) || B < 1 || ld2 % 8 || off2 % 8 || Wo % TOW || Ho % TOH) {
+    b200_set_error("conv_c1_fwd: C must be 64/128; output must tile by 8x32 (or 16x16); concat stride / offset multiples of 8");
     return B200_ERR_ARG;
   }
   const int grid = B * (Ho / TOH) * (Wo / TOW);
-  conv_c1_fwd_kernel<<<grid, 256, 0, stream>>>(x, xmul, H, W, tow_shift, w, C, act, (__nv_bfloat16*)y, (__nv_bfloat16*)y2, ld2, off2);
+  if (C == 64)
+    conv_c1_fwd_kernel<64><<<grid, 256, 0, stream>>>(x, xmul, H, W, tow_shift, w, act, (__nv_bfloat16*)y, (__nv_bfloat16*)y2, ld2, off2);
+  else
+    conv_c1_fwd_kernel<128><<<grid, 256, 0, stream>>>(x, xmul, H, W, tow_shift, w, act, (__nv_bfloat16*)y, (__nv_bfloat16*)y2, ld2, off2);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -490,9 +551,9 @@ int b200_convt_c1_fwd(const void* z, int B, int H, int W, int C, int ldz, const 
   }
   const int grid = B * (H / kTT) * (W / kTT);
   if (C == 64)
-    convt_c1_fwd_kernel<8><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)z, B, H, W, ldz, w, bias, act, base, mul, y, comp);
+    convt_c1_fwd_kernel<64><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)z, B, H, W, ldz, w, bias, act, base, mul, y, comp);
   else
-    convt_c1_fwd_kernel<16><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)z, B, H, W, ldz, w, bias, act, base, mul, y, comp);
+    convt_c1_fwd_kernel<128><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)z, B, H, W, ldz, w, bias, act, base, mul, y, comp);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -503,14 +564,20 @@ int b200_wgrad_c1_blocks(void) { return 148 * 2; }
 int b200_wgrad_c1(const void* z, int B, int H, int W, int C, int ldz, const float* g, const float* gmul, float* partial, float* dw, int accumulate,
                   cudaStream_t stream) {
   if ((C != 64 && C != 128) || ldz % 8 || B < 1 || H % kWgTH || W % kWgTW) {
-    b200_set_error("wgrad_c1: C must be 64/128, H % 8 == 0, W % 32 == 0");
+    b200_set_error("wgrad_c1: C must be 64/128, H % 4 == 0, W % 32 == 0");
     return B200_ERR_ARG;
   }
   const int nblk = b200_wgrad_c1_blocks();
+  const size_t smem = 2 * (size_t)(kWgTH * kWgTW * (C + 8) * 2) + 4 * (size_t)(kWgRows * kWgStride) * sizeof(float);
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaFuncSetAttribute(wgrad_c1_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(wgrad_c1_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  });
   if (C == 64)
-    wgrad_c1_kernel<8><<<nblk, 256, 0, stream>>>((const __nv_bfloat16*)z, B, H, W, ldz, g, gmul, partial);
+    wgrad_c1_kernel<64><<<nblk, 256, smem, stream>>>((const __nv_bfloat16*)z, B, H, W, ldz, g, gmul, partial);
   else
-    wgrad_c1_kernel<16><<<nblk, 256, 0, stream>>>((const __nv_bfloat16*)z, B, H, W, ldz, g, gmul, partial);
+    wgrad_c1_kernel<128><<<nblk, 256, smem, stream>>>((const __nv_bfloat16*)z, B, H, W, ldz, g, gmul, partial);
   B200_CHECK_LAUNCH();
   partial_sum_kernel<<<(C * 16 + 255) / 256, 256, 0, stream>>>(partial, nblk, C * 16, dw, accumulate);
   B200_CHECK_LAUNCH();

@@ -408,6 +408,19 @@ int b200_bn_stats(const void* y, long long P, int C, void* partial, const float*
   return B200_OK;
 }
 
+// Finalize from per-CTA partial rows written by the convolution epilogue (b200_conv_s2_gemm / b200_convt_s2_gemm `stats`).
+int b200_bn_finalize(const float* partial, int rows, long long P, int C, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                     long long* num_batches_tracked, float momentum, float eps, float* stats_out, cudaStream_t stream) {
+  if (rows < 1 || P < 1 || C < 1) {
+    b200_set_error("bn_finalize: bad sizes");
+    return B200_ERR_ARG;
+  }
+  bn_finalize_kernel<<<(C + 31) / 32, kFinThreads, 0, stream>>>(partial, rows, C, (double)P, gamma, beta, running_mean, running_var, num_batches_tracked, momentum,
+                                                                eps, stats_out);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
 int b200_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps, float* stats_out,
                         cudaStream_t stream) {
   bn_eval_coeffs_kernel<<<(C + 127) / 128, 128, 0, stream>>>(C, gamma, beta, running_mean, running_var, eps, stats_out);

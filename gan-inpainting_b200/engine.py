@@ -87,24 +87,60 @@ def _m_tiles(B: int, hs: int, ws: int, npix: int = 128) -> int:
 # ------------------------------------------------------------------------------------------------
 # thin op wrappers (shapes are NHWC; all tensors contiguous)
 # ------------------------------------------------------------------------------------------------
-def conv_s2(x, wpk, cout, out=None, ldy=None):
+class BnPlan:
+    """Asks the convolution epilogue for the batch statistics of its output (training-mode BatchNorm that follows) and
+    finalizes them: mean / rstd / scale / shift in ``stats`` [4, C], running statistics updated in place."""
+
+    def __init__(self, bn, train: bool, scratch: "Scratch"):
+        track = bn.track_running_stats and train
+        self.bn, self.scratch = bn, scratch
+        self.rm, self.rv, self.nbt = (bn.running_mean, bn.running_var, bn.num_batches_tracked) if track else (None, None, None)
+        self.rows = ctypes.c_int(0)
+
+    def finalize(self, y, C):
+        bn = self.bn
+        stats = _empty((4, C), f32, y.device)
+        call("b200_bn_finalize", ptr(self.scratch.bn_partial), self.rows.value, y.numel() // C, C, ptr(bn.weight.data), ptr(bn.bias.data), ptr(self.rm),
+             ptr(self.rv), ptr(self.nbt), float(bn.momentum), float(bn.eps), ptr(stats), stream())
+        return stats
+
+
+def conv_s2(x, wpk, cout, out=None, ldy=None, plan: Optional[BnPlan] = None):
     """x [B,H,W,Cin] bf16 -> [B,H/2,W/2,cout]; wpk [cout][16*Cin]."""
     B, H, W, Cin = x.shape
     if out is None:
         out = _empty((B, H // 2, W // 2, cout), bf16, x.device)
         ldy = cout
     bn = pick_bn(_m_tiles(B, H // 2, W // 2), cout)
-    call("b200_conv_s2_gemm", ptr(x), B, H, W, Cin, ptr(wpk), cout, ptr(out), ldy, bn, 0, stream())
+    call("b200_conv_s2_gemm", ptr(x), B, H, W, Cin, ptr(wpk), cout, ptr(out), ldy, bn, 0, ptr(plan.scratch.bn_partial) if plan else None,
+         ctypes.byref(plan.rows) if plan else None, stream())
     return out
 
 
-def convt_s2(z, ldz, cin, wpk, cout):
+def convt_s2(z, ldz, cin, wpk, cout, plan: Optional[BnPlan] = None):
     """z [B,Hi,Wi,>=cin] (pixel stride ldz) -> [B,2Hi,2Wi,cout]; wpk [4][cout][4*cin]."""
     B, Hi, Wi = z.shape[:3]
     out = _empty((B, 2 * Hi, 2 * Wi, cout), bf16, z.device)
     bn = pick_bn(_m_tiles(B, Hi, Wi), cout, phases=4)
-    call("b200_convt_s2_gemm", ptr(z), B, Hi, Wi, cin, ldz, ptr(wpk), cout, ptr(out), cout, bn, 0, stream())
+    call("b200_convt_s2_gemm", ptr(z), B, Hi, Wi, cin, ldz, ptr(wpk), cout, ptr(out), cout, bn, 0, ptr(plan.scratch.bn_partial) if plan else None,
+         ctypes.byref(plan.rows) if plan else None, stream())
     return out
+
+
+def pick_splits(ptiles: int, ctas: int) -> int:
+    """Pixel-range splits of a weight-gradient GEMM for the persistent kernel (one CTA per SM, static tile schedule).
+    ``ctas`` output tiles exist per split and ``ptiles`` 64-pixel k-blocks in total.  Cost model in k-block units:
+    rounds of NUM_SMS concurrent tiles x (k-blocks per tile + a fixed per-tile cost) + the partial-sum traffic (one fp32
+    tile written and re-read per split ~ 6 k-blocks of operand traffic)."""
+    best, best_cost = 1, None
+    for s in range(1, min(ptiles, 64) + 1):
+        kb = -(-ptiles // s)
+        s_eff = -(-ptiles // kb)
+        rounds = -(-(ctas * s_eff) // NUM_SMS)
+        cost = rounds * (kb + 6) + 0.05 * s_eff * ctas * 6 / NUM_SMS
+        if best_cost is None or cost < best_cost - 1e-9:
+            best, best_cost = s_eff, cost
+    return best
 
 
 def wgrad(S, lds, cs, Lt, grad, accumulate, scratch: Scratch):
@@ -114,7 +150,7 @@ def wgrad(S, lds, cs, Lt, grad, accumulate, scratch: Scratch):
     ptiles = _m_tiles(B, Hs, Ws, 64)
     bn = 256
     ctas = (cs // 128) * (16 * cl // bn)
-    splits = max(1, min(ptiles, (2 * NUM_SMS + ctas - 1) // ctas, 64))
+    splits = pick_splits(ptiles, ctas)
     part = scratch.wgrad_buf(splits * cs * 16 * cl)
     sp = ctypes.c_int(splits)
     call("b200_wgrad_gemm", ptr(S), B, Hs, Ws, cs, lds, ptr(Lt), cl, ptr(part), ctypes.byref(sp), bn, 0, stream())
@@ -230,9 +266,10 @@ class GeneratorEngine:
         call("b200_conv_c1_fwd", ptr(x), None, B, R, R, ptr(self.dc[0].weight.data), w[1], ACT_LEAKY, ptr(c.a[1]), ptr(c.cat[1]), 2 * w[1], 0, stream())
         # d2 .. dN
         for l in range(2, N + 1):
-            c.y[l] = conv_s2(c.a[l - 1], self.packed_d[l].gather, w[l])
+            plan = self._plan(self.dn[l - 1], train, sc) if l < N else None
+            c.y[l] = conv_s2(c.a[l - 1], self.packed_d[l].gather, w[l], plan=plan)
             if l < N:
-                c.sd[l] = self._stats(self.dn[l - 1], c.y[l], w[l], train, sc)
+                c.sd[l] = self._stats(self.dn[l - 1], c.y[l], w[l], train, plan)
                 c.a[l] = _empty(c.y[l].shape, bf16, dev)
                 bn_act(c.y[l], w[l], c.sd[l], ACT_LEAKY, c.a[l], w[l], 0, c.cat[l], 2 * w[l], 0)
             else:
@@ -241,8 +278,9 @@ class GeneratorEngine:
         # uN .. u2
         for l in range(N, 1, -1):
             zin, cin = (c.r_in, w[N]) if l == N else (c.cat[l], 2 * w[l])
-            c.yu[l] = convt_s2(zin, cin, cin, self.packed_u[l].phase, w[l - 1])
-            c.su[l] = self._stats(self.un[l - 1], c.yu[l], w[l - 1], train, sc)
+            plan = self._plan(self.un[l - 1], train, sc)
+            c.yu[l] = convt_s2(zin, cin, cin, self.packed_u[l].phase, w[l - 1], plan=plan)
+            c.su[l] = self._stats(self.un[l - 1], c.yu[l], w[l - 1], train, plan)
             bn_act(c.yu[l], w[l - 1], c.su[l], ACT_RELU, c.cat[l - 1], 2 * w[l - 1], w[l - 1], dropout=c.dropout and l in self.dropout_levels,
                    seed=seed * 16 + l)
         # u1: direct transposed conv + bias + tanh (+ composite)
@@ -256,13 +294,19 @@ class GeneratorEngine:
             c.a = c.y = c.yu = c.cat = None
         return c
 
-    def _stats(self, bn, y, C, train, sc):
+    @staticmethod
+    def _plan(bn, train, sc):
+        """Batch statistics are needed in training mode (and always when the norm keeps no running statistics)."""
+        if bn is None or not (train or not bn.track_running_stats):
+            return None
+        return BnPlan(bn, train, sc)
+
+    @staticmethod
+    def _stats(bn, y, C, train, plan):
         if bn is None:
             return None
-        if train or not bn.track_running_stats:
-            track = bn.track_running_stats and train
-            return bn_stats(y, C, bn.weight.data, bn.bias.data, bn.running_mean if track else None, bn.running_var if track else None,
-                            bn.num_batches_tracked if track else None, bn.momentum, bn.eps, sc)
+        if plan is not None:
+            return plan.finalize(y, C)
         return bn_eval(C, bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, bn.eps, y.device)
 
     # ---- backward
@@ -361,10 +405,11 @@ class DiscriminatorEngine:
         call("b200_conv_c1_fwd", ptr(x), ptr(xmul), B, R, R, ptr(self.convs[0].weight.data), 64, ACT_LEAKY, ptr(c.a[0]), None, 0, 0, stream())
         for i in range(1, 4):
             C = 64 << i
-            c.y[i] = conv_s2(c.a[i - 1], self.packed[i].gather, C)
             bn = self.norms[i]
+            plan = BnPlan(bn, train, sc) if train else None
+            c.y[i] = conv_s2(c.a[i - 1], self.packed[i].gather, C, plan=plan)
             if train:
-                c.st[i] = bn_stats(c.y[i], C, bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, bn.num_batches_tracked, bn.momentum, bn.eps, sc)
+                c.st[i] = plan.finalize(c.y[i], C)
             else:
                 c.st[i] = bn_eval(C, bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, bn.eps, dev)
             c.a[i] = _empty(c.y[i].shape, bf16, dev)

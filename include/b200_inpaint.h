@@ -51,20 +51,26 @@ long long b200_launch_count(void);  /* kernels launched by this library since lo
 
 /* ------------------------------------------------------------------------------------------------------------------
  * tcgen05 implicit-GEMM convolutions (csrc/conv_gemm.cu).  4x4 kernel, stride 2, padding 1; TMA-staged NHWC bf16
- * tiles, fp32 accumulation in TMEM.  H, W powers of two; Cin % 64 == 0; Cout % 16 == 0; bn_hint / stages 0 = auto.
+ * tiles, fp32 accumulation in TMEM; persistent CTAs (one per SM) walk the output tiles with two TMEM accumulators so
+ * the epilogue of one tile overlaps the main loop of the next.  H, W powers of two; Cin % 64 == 0; Cout % 32 == 0;
+ * bn_hint / stages 0 = auto.
+ * `stats` (optional, fprop entry points): the epilogue also accumulates the per-channel sum / sum of squares of the stored
+ * bf16 outputs for the nn.BatchNorm2d that follows (networks.py:310, 341-349): one row [2][Cout] per CTA, *stat_rows (host int)
+ * receives the number of rows written (<= b200_igemm_stat_rows()); reduce them with b200_bn_finalize.
  * ------------------------------------------------------------------------------------------------------------------ */
 
 /* nn.Conv2d(Cin, Cout, 4, 2, 1, bias=False) forward — networks.py:285-286 (generator d2..d7), :340-348 (PatchGAN c2..c4);
  * also the data gradient of nn.ConvTranspose2d.  x [B,H,W,Cin]; wpk [Cout][16*Cin] from b200_pack_gather;
  * y [B,H/2,W/2,*] with pixel stride ldy. */
-int b200_conv_s2_gemm(const void* x, int B, int H, int W, int Cin, const void* wpk, int Cout, void* y, int ldy, int bn_hint, int stages,
-                      b200_stream_t stream);
+int b200_igemm_stat_rows(void);
+int b200_conv_s2_gemm(const void* x, int B, int H, int W, int Cin, const void* wpk, int Cout, void* y, int ldy, int bn_hint, int stages, float* stats,
+                      int* stat_rows, b200_stream_t stream);
 
 /* nn.ConvTranspose2d(Cin, Cout, 4, 2, 1, bias=False) forward as 4 sub-pixel phases — networks.py:300-309 (u7..u2);
  * also the data gradient of nn.Conv2d.  z [B,Hi,Wi,*] with pixel stride ldz; wpk [4][Cout][4*Cin] from b200_pack_phase;
  * y [B,2Hi,2Wi,*] with pixel stride ldy. */
 int b200_convt_s2_gemm(const void* z, int B, int Hi, int Wi, int Cin, int ldz, const void* wpk, int Cout, void* y, int ldy, int bn_hint, int stages,
-                       b200_stream_t stream);
+                       float* stats, int* stat_rows, b200_stream_t stream);
 
 /* Weight gradient of both layer kinds (autograd of the call sites above; wgan_l1.py:138,141,183):
  *   partial[s][cs][(kh*4+kw)*Cl + cl] = sum over the pixels of split s of S[b,i,j,cs] * L[b,2i+kh-1,2j+kw-1,cl]
@@ -98,6 +104,9 @@ int b200_bn_stat_blocks(long long P, int C); /* partial buffer holds b200_bn_sta
  * running_mean / running_var / num_batches_tracked (int64) updated in place when non-null (momentum, unbiased var). */
 int b200_bn_stats(const void* y, long long P, int C, void* partial, const float* gamma, const float* beta, float* running_mean, float* running_var,
                   long long* num_batches_tracked, float momentum, float eps, float* stats_out, b200_stream_t stream);
+/* same outputs from the partial rows the convolution epilogue wrote (see `stats` above); P = pixels per channel */
+int b200_bn_finalize(const float* partial, int rows, long long P, int C, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                     long long* num_batches_tracked, float momentum, float eps, float* stats_out, b200_stream_t stream);
 int b200_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps, float* stats_out,
                         b200_stream_t stream);
 /* out1[pix*ld1 + off1 + c] = act(dropout(y*scale + shift)); out2 = relu(out1) (the concat half).  scale null = identity. */

@@ -42,7 +42,7 @@ def _packs(w):
     return p
 
 
-@pytest.mark.parametrize("B,H,Cin,Cout", [(2, 16, 64, 128), (3, 8, 256, 512), (8, 2, 512, 512), (2, 64, 64, 128), (5, 4, 512, 512)])
+@pytest.mark.parametrize("B,H,Cin,Cout", [(2, 16, 64, 128), (3, 8, 256, 512), (8, 2, 512, 512), (2, 64, 64, 128), (5, 4, 512, 512), (48, 32, 128, 256)])
 def test_conv_s2_fprop(dev, B, H, Cin, Cout):
     eng = _eng()
     torch.manual_seed(0)
@@ -53,7 +53,7 @@ def test_conv_s2_fprop(dev, B, H, Cin, Cout):
     assert rel(y, ref) < BF16_TOL
 
 
-@pytest.mark.parametrize("B,Hi,Cin,Cout", [(2, 8, 128, 64), (2, 1, 512, 512), (3, 4, 1024, 512), (2, 32, 512, 128), (2, 64, 256, 64)])
+@pytest.mark.parametrize("B,Hi,Cin,Cout", [(2, 8, 128, 64), (2, 1, 512, 512), (3, 4, 1024, 512), (2, 32, 512, 128), (2, 64, 256, 64), (20, 32, 128, 64)])
 def test_convt_s2_fprop(dev, B, Hi, Cin, Cout):
     eng = _eng()
     torch.manual_seed(1)
@@ -62,6 +62,39 @@ def test_convt_s2_fprop(dev, B, Hi, Cin, Cout):
     y = eng.convt_s2(z, Cin, Cin, _packs(w).phase, Cout)
     ref = nhwc(F.conv_transpose2d(nchw(z.float()), bf(w).float(), stride=2, padding=1))
     assert rel(y, ref) < BF16_TOL
+
+
+@pytest.mark.parametrize("kind,B,H,Cin,Cout", [("conv", 3, 16, 64, 128), ("conv", 40, 32, 64, 128), ("conv", 5, 4, 512, 512), ("convt", 2, 8, 128, 64),
+                                               ("convt", 24, 16, 256, 64), ("convt", 3, 2, 512, 512)])
+def test_conv_epilogue_batchnorm_statistics(dev, kind, B, H, Cin, Cout):
+    """The persistent GEMM's epilogue hands the following BatchNorm2d (networks.py:310, 341-349) its batch statistics: per-CTA partial
+    rows + b200_bn_finalize must equal mean / biased variance of the STORED output, and update the running statistics like torch."""
+    eng = _eng()
+    torch.manual_seed(7)
+    bn = torch.nn.BatchNorm2d(Cout).to(dev)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5)
+        bn.bias.uniform_(-0.5, 0.5)
+    plan = eng.BnPlan(bn, True, eng.Scratch.get(dev))
+    x = bf(torch.randn(B, H, H, Cin, device=dev))
+    if kind == "conv":
+        w = torch.randn(Cout, Cin, 4, 4, device=dev) / math.sqrt(Cin * 16)
+        y = eng.conv_s2(x, _packs(w).gather, Cout, plan=plan)
+        ref = nhwc(F.conv2d(nchw(x.float()), bf(w).float(), stride=2, padding=1))
+    else:
+        w = torch.randn(Cin, Cout, 4, 4, device=dev) / math.sqrt(Cin * 4)
+        y = eng.convt_s2(x, Cin, Cin, _packs(w).phase, Cout, plan=plan)
+        ref = nhwc(F.conv_transpose2d(nchw(x.float()), bf(w).float(), stride=2, padding=1))
+    assert rel(y, ref) < BF16_TOL
+    assert 1 <= plan.rows.value <= 148
+    st = plan.finalize(y, Cout)
+    yf = y.float().reshape(-1, Cout)
+    mean, var = yf.mean(0), yf.var(0, unbiased=False)
+    assert rel(st[0], mean) < 1e-4 and rel(st[1], 1.0 / torch.sqrt(var + bn.eps)) < 1e-4
+    assert rel(st[2], bn.weight * st[1]) < 1e-5 and rel(st[3], bn.bias - st[0] * st[2]) < 1e-4
+    n = yf.shape[0]
+    assert rel(bn.running_mean, 0.1 * mean) < 1e-4 and rel(bn.running_var, 0.9 + 0.1 * var * n / (n - 1)) < 1e-4
+    assert int(bn.num_batches_tracked) == 1
 
 
 @pytest.mark.parametrize("B,H,Cin,Cout", [(2, 16, 64, 128), (4, 8, 256, 512)])
@@ -88,7 +121,7 @@ def test_convt_dgrad_is_gather_conv(dev, B, Hi, Cin, Cout):
     assert rel(dz, ref) < BF16_TOL
 
 
-@pytest.mark.parametrize("B,Hs,Cs,Cl,acc", [(2, 8, 128, 64, False), (3, 4, 512, 256, True), (2, 32, 256, 64, False), (4, 1, 512, 512, False)])
+@pytest.mark.parametrize("B,Hs,Cs,Cl,acc", [(2, 8, 128, 64, False), (3, 4, 512, 256, True), (2, 32, 256, 64, False), (4, 1, 512, 512, False), (16, 32, 128, 64, False)])
 def test_wgrad(dev, B, Hs, Cs, Cl, acc):
     eng = _eng()
     torch.manual_seed(4)

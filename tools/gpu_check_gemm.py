@@ -39,7 +39,7 @@ def check_conv(B, H, Cin, Cout, bn=0, stages=0):
     w = (torch.randn(Cout, Cin, 4, 4, device=dev) / (Cin * 16) ** 0.5).bfloat16()
     y = torch.full((B, H // 2, H // 2, Cout), float("nan"), device=dev, dtype=torch.bfloat16)
     wp = pack_conv(w)
-    _lib.call("b200_conv_s2_gemm", _lib.ptr(x), B, H, H, Cin, _lib.ptr(wp), Cout, _lib.ptr(y), Cout, bn, stages, _lib.stream())
+    _lib.call("b200_conv_s2_gemm", _lib.ptr(x), B, H, H, Cin, _lib.ptr(wp), Cout, _lib.ptr(y), Cout, bn, stages, None, None, _lib.stream())
     torch.cuda.synchronize()
     ref = F.conv2d(x.permute(0, 3, 1, 2).float(), w.float(), stride=2, padding=1).permute(0, 2, 3, 1)
     return rel(y, ref)
@@ -50,7 +50,7 @@ def check_convt(B, Hi, Cin, Cout, bn=0, stages=0):
     w = (torch.randn(Cin, Cout, 4, 4, device=dev) / (Cin * 4) ** 0.5).bfloat16()
     y = torch.full((B, 2 * Hi, 2 * Hi, Cout), float("nan"), device=dev, dtype=torch.bfloat16)
     wp = pack_convt(w)
-    _lib.call("b200_convt_s2_gemm", _lib.ptr(z), B, Hi, Hi, Cin, Cin, _lib.ptr(wp), Cout, _lib.ptr(y), Cout, bn, stages, _lib.stream())
+    _lib.call("b200_convt_s2_gemm", _lib.ptr(z), B, Hi, Hi, Cin, Cin, _lib.ptr(wp), Cout, _lib.ptr(y), Cout, bn, stages, None, None, _lib.stream())
     torch.cuda.synchronize()
     ref = F.conv_transpose2d(z.permute(0, 3, 1, 2).float(), w.float(), stride=2, padding=1).permute(0, 2, 3, 1)
     return rel(y, ref)
@@ -61,7 +61,7 @@ def check_wgrad(B, Hs, Cs, Cl, splits=4, bn=0, stages=0):
     L = torch.randn(B, 2 * Hs, 2 * Hs, Cl, device=dev).bfloat16()
     sp = ctypes.c_int(splits)
     part = torch.full((max(splits, 1), Cs, 16 * Cl), float("nan"), device=dev, dtype=torch.float32)
-    _lib.call("b200_wgrad_gemm", _lib.ptr(S), B, Hs, Hs, Cs, Cs, _lib.ptr(L), Cl, _lib.ptr(part), ctypes.byref(sp), bn, stages, _lib.stream())
+    _lib.call("b200_wgrad_gemm", _lib.ptr(S), B, Hs, Hs, Cs, Cs, _lib.ptr(L), Cl, _lib.ptr(part), ctypes.byref(sp), bn, stages, None, None, _lib.stream())
     torch.cuda.synchronize()
     g = part[: sp.value].sum(0).view(Cs, 4, 4, Cl).permute(0, 3, 1, 2)  # [Cs,Cl,kh,kw]
     ref = torch.nn.grad.conv2d_weight(L.permute(0, 3, 1, 2).float(), (Cs, Cl, 4, 4), S.permute(0, 3, 1, 2).float(), stride=2, padding=1)
