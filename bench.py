@@ -241,6 +241,13 @@ def run_b200(args):
     ms = timed(step_dev, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     launches = _lib.value("b200_launch_count") - l0
+    # host-side enqueue cost of one step (Python + ctypes + allocator): must stay below the device time or the GPU starves
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        step_dev()
+    host_ms = (time.perf_counter() - t0) / 3 * 1e3
+    torch.cuda.synchronize()
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
@@ -307,6 +314,7 @@ def run_b200(args):
         "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": out_h.numel() * 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
+        "host_enqueue_ms_per_step": host_ms,
         "clocks": clocks,
         "roofline": roofline,
         "cpu_baseline": cpu,

@@ -26,8 +26,8 @@ U = c_uint32
 # name -> argtypes (all of these return an int status; 0 == OK).  Order == include/b200_inpaint.h.
 SIGNATURES = {
     # ---- tcgen05 implicit-GEMM convolutions (csrc/conv_gemm.cu)
-    "b200_conv_s2_gemm": [P, I, I, I, I, P, I, P, I, I, I, P, POINTER(c_int), S],
-    "b200_convt_s2_gemm": [P, I, I, I, I, I, P, I, P, I, I, I, P, POINTER(c_int), S],
+    "b200_conv_s2_gemm": [P, I, I, I, I, P, I, P, I, I, I, P, POINTER(c_int), P, S],
+    "b200_convt_s2_gemm": [P, I, I, I, I, I, P, I, P, I, I, I, P, POINTER(c_int), P, S],
     "b200_wgrad_gemm": [P, I, I, I, I, I, P, I, P, POINTER(c_int), I, I, S],
     "b200_debug_tma_probe": [P, I, I, I, I, I, I, I, I, I, I, I, I, I, P, S],
     # ---- weight layouts (csrc/pack.cu)
@@ -39,6 +39,7 @@ SIGNATURES = {
     "b200_bn_finalize": [P, I, L, I, P, P, P, P, P, F, F, P, S],
     "b200_bn_eval_coeffs": [I, P, P, P, P, F, P, S],
     "b200_bn_act": [P, L, I, P, P, I, P, I, I, P, I, I, I, U, S],
+    "b200_bn_bwd_fused": [P, L, I, P, P, P, I, I, P, I, I, I, P, P, P, I, P, S],
     "b200_bn_act_bwd": [P, L, I, P, P, I, P, I, I, P, I, I, I, U, P, P, P, P, I, P, S],
     # ---- single-channel-side convolutions and the discriminator head (csrc/conv_direct.cu)
     "b200_conv_c1_fwd": [P, P, I, I, I, P, I, I, P, P, I, I, S],
@@ -73,6 +74,13 @@ VALUE_FUNCS = {
     "b200_wgrad_c1_blocks": (c_int, []),
     "b200_recon_scratch_floats": (c_int, []),
 }
+
+
+class EpiBwd(ctypes.Structure):
+    """ctypes mirror of ``b200_epi_bwd`` (include/b200_inpaint.h)."""
+
+    _fields_ = [("y", c_void_p), ("ldy", c_int), ("scale", c_void_p), ("shift", c_void_p), ("act", c_int), ("g2", c_void_p), ("ldg2", c_int),
+                ("offg2", c_int), ("dropout", c_int), ("seed", c_uint32), ("col0", c_int), ("Cy", c_int)]
 
 
 class B200Error(RuntimeError):

@@ -16,8 +16,8 @@
 // whose out-of-image halo TMA zero-fills.  No im2col buffer, no padded copies.
 // Accumulation is fp32 in TMEM; one elected thread issues tcgen05.mma (M=128, N<=256, K=16).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> global).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..9 = epilogue (TMEM -> registers -> global), two per TMEM lane quadrant.
 #include "common.cuh"
 
 #include <mutex>
@@ -26,6 +26,24 @@
 namespace b200 {
 
 enum { MODE_CONV_S2 = 0, MODE_CONVT = 1, MODE_WGRAD = 2 };
+
+// Optional backward-of-activation epilogue of the data-gradient GEMMs (mirrors b200_epi_bwd in include/b200_inpaint.h).
+// Output columns >= col0 are gradients w.r.t. act(dropout(bn(y)))[:, col - col0]; the epilogue turns them into the gradient
+// w.r.t. the BatchNorm output z = y*scale + shift (`dz`), stores dz instead, and (when stats are requested) accumulates the
+// per-channel sums  sum dz  and  sum dz*y  that the BatchNorm backward needs — so no separate pass re-reads the gradient.
+struct EpiBwd {
+  const __nv_bfloat16* y;  // forward conv output (dense, pixel stride ldy); null = plain epilogue
+  int ldy;
+  const float* scale;      // forward BatchNorm scale / shift per channel of y (null: z = y)
+  const float* shift;
+  int act;                 // 0 none, 1 LeakyReLU(0.2), 2 ReLU
+  const __nv_bfloat16* g2; // optional second gradient (skip connection through ReLU of leaky(z)): added where z > 0
+  int ldg2, offg2;
+  int dropout;             // Dropout(0.5) between BatchNorm and ReLU: keep-mask regenerated from (seed, element index)
+  uint32_t seed;
+  int col0;
+  int Cy;                  // channels of y
+};
 
 struct IGemmParams {
   int mode;
@@ -52,13 +70,27 @@ struct IGemmParams {
   int kpb;               // 64-wide k-blocks per pipeline stage (2 for narrow N tiles: halves the per-stage barrier overhead
                          // of the single issuing thread, which otherwise exceeds the MMA time of a 128 x 64 x 64 block)
   float* stats;          // optional (fprop modes): per-CTA column sums of the stored bf16 outputs,
-                         // [gridDim.x][2][Cout] (sum, sum of squares) for the BatchNorm that follows
+                         // [gridDim.x][2][Cout] (sum, sum of squares) for the BatchNorm that follows;
+                         // with `bwd`: (sum dz, sum dz*y) of the fused columns instead
+  EpiBwd bwd;
 };
 
 constexpr int kNumSMs = 148;
+constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quadrant, alternating 32-column chunks
+constexpr int kThreads = 64 + 32 * kEpiWarps;      // warp 0 = TMA, warp 1 = MMA, warps 2.. = epilogue
 constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 bf16 (K-major) or 2 x (64 px x 64 ch) (MN-major)
-constexpr int kStatSmemBytes = 2 * 4 * 2 * 256 * 4;  // [tile parity][epilogue warp][sum|sumsq][column]
-constexpr int kStatAccBytes = 2 * 512 * 4;           // per-CTA running [sum|sumsq][Cout <= 512]
+constexpr int kStatSmemBytes = 2 * 4 * 2 * 256 * 4;  // [tile parity][TMEM quadrant][sum|sumsq][column]
+constexpr int kStatAccBytes = 2 * 1024 * 4;          // per-CTA running [sum|sumsq][Cout <= 1024]
+constexpr int kScaleShiftBytes = 2 * 512 * 4;        // forward BatchNorm scale / shift of the fused backward epilogue
+constexpr int kStatTileBytes = 2 * 2048;             // per epilogue warp: 32 rows x 32 bf16 of dz (and of y), 16-byte chunks swizzled
+
+// Epilogue variants (compile-time: the per-element code has no branches and each variant is a small kernel)
+enum { ACT_BWD_NONE = 0, ACT_BWD_LEAKY = 1, ACT_BWD_RELU = 2 };
+template <bool STATS_, bool BWD_, int ACT_, bool G2_, bool BN_>
+struct Epi {
+  static constexpr bool STATS = STATS_, BWD = BWD_, G2 = G2_, BN = BN_;
+  static constexpr int ACT = ACT_;
+};
 
 struct TileCoord {
   int w0, h0, b0, n0, m0, phase, kb_begin, kb_count, row;
@@ -96,22 +128,66 @@ __device__ __forceinline__ TileCoord decode_tile(const IGemmParams& p, int t) {
   return c;
 }
 
-// lane j ends up with sum over the 32 lanes of v[j] (31 shuffles).
-__device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
+// Column sums of a warp's 32 x 32 bf16 tile whose rows live one per lane, through a shared-memory transpose: lane r stores its
+// row (4 chunks of 16 bytes, XOR-swizzled so both the 128-bit stores and loads are bank-conflict free); lane (rg, cg) then reads
+// chunk cg (8 columns) of rows rg, rg+8, rg+16, rg+24 and three shuffle stages fold the 8 row groups.
+// s[k] / q[k] = sum over the 32 rows of x and x*x (or x*y) for column 8*(lane & 3) + k — identical in every lane with the same cg.
+template <bool WITH_Y>
+__device__ __forceinline__ void tile_column_sums(uint8_t* wbuf, const uint32_t (&o)[16], const uint32_t (&yw)[16], int lane, float (&s)[8],
+                                                 float (&q)[8]) {
+  // store: row = lane, 4 chunks; physical chunk = logical ^ ((lane >> 1) & 3) keeps the 8-lane phases of STS.128 / LDS.128 conflict-free
+  const int sw = (lane >> 1) & 3;
+  uint4* rowp = reinterpret_cast<uint4*>(wbuf + lane * 64);
 #pragma unroll
-  for (int h = 16; h >= 1; h >>= 1) {
-    const bool up = (lane & h) != 0;
+  for (int j = 0; j < 4; ++j) rowp[j ^ sw] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+  if (WITH_Y) {
+    uint4* rowy = reinterpret_cast<uint4*>(wbuf + 2048 + lane * 64);
 #pragma unroll
-    for (int k = 0; k < h; ++k) {
-      const float send = up ? v[k] : v[k + h];
-      const float keep = up ? v[k + h] : v[k];
-      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+    for (int j = 0; j < 4; ++j) rowy[j ^ sw] = make_uint4(yw[4 * j], yw[4 * j + 1], yw[4 * j + 2], yw[4 * j + 3]);
+  }
+  __syncwarp();
+  const int cg = lane & 3, rg = lane >> 2;  // column chunk (8 columns), row group (rows rg + 8 i)
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s[k] = q[k] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = i * 8 + rg;
+    const int ph = cg ^ ((row >> 1) & 3);
+    const uint4 d = *reinterpret_cast<const uint4*>(wbuf + row * 64 + ph * 16);
+    const uint32_t dw[4] = {d.x, d.y, d.z, d.w};
+    uint32_t ywd[4] = {0u, 0u, 0u, 0u};
+    if (WITH_Y) {
+      const uint4 y4 = *reinterpret_cast<const uint4*>(wbuf + 2048 + row * 64 + ph * 16);
+      ywd[0] = y4.x, ywd[1] = y4.y, ywd[2] = y4.z, ywd[3] = y4.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack_bf16x2(dw[k]);
+      s[2 * k] += f.x;
+      s[2 * k + 1] += f.y;
+      if (WITH_Y) {
+        const float2 g = unpack_bf16x2(ywd[k]);
+        q[2 * k] = fmaf(f.x, g.x, q[2 * k]);
+        q[2 * k + 1] = fmaf(f.y, g.y, q[2 * k + 1]);
+      } else {
+        q[2 * k] = fmaf(f.x, f.x, q[2 * k]);
+        q[2 * k + 1] = fmaf(f.y, f.y, q[2 * k + 1]);
+      }
     }
   }
-  return v[0];
+  __syncwarp();  // the buffer may be overwritten by the next chunk
+  // 8 row groups (lane bits 2..4) -> one
+#pragma unroll
+  for (int h = 4; h <= 16; h <<= 1)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s[k] += __shfl_xor_sync(0xffffffffu, s[k], h);
+      q[k] += __shfl_xor_sync(0xffffffffu, q[k], h);
+    }
 }
 
-__global__ void __launch_bounds__(192, 1)
+template <class E>
+__global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const IGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -124,6 +200,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint32_t* tmem_ptr_smem = (uint32_t*)(tmem_empty_bar + 2);
   float* stat_smem = (float*)(tmem_ptr_smem + 4);   // kStatSmemBytes + kStatAccBytes, only touched when p.stats
   float* stat_acc = stat_smem + kStatSmemBytes / 4;
+  float* bn_ss = stat_acc + kStatAccBytes / 4;      // interleaved (scale, shift)[Cy <= 512]
+  uint8_t* stat_tile = (uint8_t*)(bn_ss + kScaleShiftBytes / 4);  // [epilogue warp][kStatTileBytes]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -137,7 +215,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], 4);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty_bar[b], kEpiWarps);  // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -240,28 +318,41 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else {
     // ===================== epilogue (overlaps the next tile's main loop) =====================
-    const int quad = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    const int quad = warp & 3;          // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    const int half = (warp - 2) >> 2;   // which of the alternating 32-column chunks this warp takes
     const int r = quad * 32 + lane;
-    const int et = threadIdx.x - 64;  // 0..127
-    if (p.stats) {
-      for (int e = et; e < 2 * p.Cout; e += 128) stat_acc[e] = 0.f;
+    const int et = threadIdx.x - 64;    // 0 .. kEpiThreads-1
+    constexpr int kEpiThreads = 32 * kEpiWarps;
+    if (E::STATS) {
+      for (int e = et; e < 2 * p.Cout; e += kEpiThreads) stat_acc[e] = 0.f;
     }
+    if (E::BWD && E::BN) {
+      for (int e = et; e < p.bwd.Cy; e += kEpiThreads) {
+        bn_ss[2 * e] = __ldg(p.bwd.scale + e);
+        bn_ss[2 * e + 1] = __ldg(p.bwd.shift + e);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+    }
+    uint8_t* wbuf = stat_tile + (warp - 2) * kStatTileBytes;
     int lt = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++lt) {
       const TileCoord c = decode_tile(p, t);
       const int buf = lt & 1;
-      mbar_wait(&tmem_full_bar[buf], (uint32_t)((lt >> 1) & 1));
-      tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.BN);
       if (p.mode == MODE_WGRAD) {
+        mbar_wait(&tmem_full_bar[buf], (uint32_t)((lt >> 1) & 1));
+        tc_fence_after();
         float* dst = (float*)p.out + ((size_t)c.row * p.m_tiles * 128 + (size_t)(c.m0 + r)) * p.ldc + c.n0;
-        for (int cc = 0; cc < p.BN; cc += 32) {
+        for (int cc = half * 32; cc < p.BN; cc += 64) {
           uint32_t v[32];
           tmem_ld_32x32(taddr + cc, v);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(dst + cc + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
       } else {
         const int bl = r >> (p.th_sh + p.tw_sh), rem = r & ((1 << (p.th_sh + p.tw_sh)) - 1);
         const int hl = rem >> p.tw_sh, wl = rem & (p.tw - 1);
@@ -275,10 +366,70 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         __nv_bfloat16* dst = (__nv_bfloat16*)p.out + pix * p.ldc + c.n0;
         const bool valid = (b < p.B);
         float* st = stat_smem + ((lt & 1) * 4 + quad) * 512;
-        for (int cc = 0; cc < p.BN; cc += 32) {
+        // fused activation backward: this row's slice of the forward tensor y (and of the skip gradient) is fetched one
+        // 32-channel chunk ahead — the first chunk while the tile's MMAs are still running
+        uint4 ynext[4], gnext[4];
+        auto fetch = [&](int cc) {
+          const int cb = c.n0 + cc - p.bwd.col0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ynext[j] = gnext[j] = make_uint4(0u, 0u, 0u, 0u);
+          if (cb >= 0 && cc < p.BN && valid) {
+            const uint4* yp = reinterpret_cast<const uint4*>(p.bwd.y + pix * p.bwd.ldy + cb);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ynext[j] = __ldg(yp + j);
+            if (E::G2) {
+              const uint4* gp = reinterpret_cast<const uint4*>(p.bwd.g2 + pix * p.bwd.ldg2 + p.bwd.offg2 + cb);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) gnext[j] = __ldg(gp + j);
+            }
+          }
+        };
+        if (E::BWD) fetch(half * 32);
+        mbar_wait(&tmem_full_bar[buf], (uint32_t)((lt >> 1) & 1));
+        tc_fence_after();
+        for (int cc = half * 32; cc < p.BN; cc += 64) {
           uint32_t v[32];
           tmem_ld_32x32(taddr + cc, v);  // .sync.aligned: all lanes participate even if the row is masked
           tmem_ld_wait();
+          const int cb = c.n0 + cc - p.bwd.col0;  // first channel of y this chunk is the gradient of (fused columns only)
+          const bool fused = E::BWD && cb >= 0;
+          uint32_t yw[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) yw[j] = 0u;
+          if (E::BWD) {
+            uint32_t gw[16];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              yw[4 * j] = ynext[j].x, yw[4 * j + 1] = ynext[j].y, yw[4 * j + 2] = ynext[j].z, yw[4 * j + 3] = ynext[j].w;
+              gw[4 * j] = gnext[j].x, gw[4 * j + 1] = gnext[j].y, gw[4 * j + 2] = gnext[j].z, gw[4 * j + 3] = gnext[j].w;
+            }
+            fetch(cc + 64);
+            if (fused) {
+              // ---- backward of [BatchNorm ->] [dropout ->] activation, evaluated at the forward's stored conv output
+#pragma unroll
+              for (int k = 0; k < 16; ++k) {
+                const float2 yf = unpack_bf16x2(yw[k]), gf = unpack_bf16x2(gw[k]);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                  const int jj = 2 * k + e;
+                  const float yy = e ? yf.y : yf.x;
+                  float z = yy;
+                  if (E::BN) {
+                    const float2 ss = *reinterpret_cast<const float2*>(bn_ss + 2 * (cb + jj));
+                    z = fmaf(yy, ss.x, ss.y);
+                  }
+                  float g = __uint_as_float(v[jj]);
+                  if (E::ACT == ACT_BWD_LEAKY) {
+                    g = z > 0.f ? (E::G2 ? g + (e ? gf.y : gf.x) : g) : 0.2f * g;
+                  } else if (E::ACT == ACT_BWD_RELU) {
+                    g = z > 0.f ? g : 0.f;
+                    if (p.bwd.dropout) g = dropout_keep(p.bwd.seed, (uint64_t)(pix * p.bwd.Cy + cb + jj)) ? 2.f * g : 0.f;
+                  }
+                  v[jj] = __float_as_uint(g);
+                }
+              }
+            }
+          }
           uint32_t o[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) o[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
@@ -286,39 +437,41 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
             for (int j = 0; j < 16; j += 4) *reinterpret_cast<uint4*>(dst + cc + 2 * j) = make_uint4(o[j], o[j + 1], o[j + 2], o[j + 3]);
           }
-          if (p.stats) {
-            float s[32], q[32];
+          if (E::STATS) {
+            // per-channel sums of the values as stored (masked rows and unfused columns count as zero)
+            if (!valid || (E::BWD && !fused)) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float2 f = unpack_bf16x2(o[j]);  // statistics of the values as stored
-              s[2 * j] = valid ? f.x : 0.f;
-              s[2 * j + 1] = valid ? f.y : 0.f;
-              q[2 * j] = s[2 * j] * s[2 * j];
-              q[2 * j + 1] = s[2 * j + 1] * s[2 * j + 1];
+              for (int j = 0; j < 16; ++j) o[j] = 0u;
             }
-            const float cs = transpose_reduce32(s, lane);
-            const float cq = transpose_reduce32(q, lane);
-            st[cc + lane] = cs;
-            st[256 + cc + lane] = cq;
+            float cs[8], cq[8];
+            tile_column_sums<E::BWD>(wbuf, o, yw, lane, cs, cq);
+            if (lane < 4) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                st[cc + lane * 8 + k] = cs[k];
+                st[256 + cc + lane * 8 + k] = cq[k];
+              }
+            }
           }
         }
-        if (p.stats) {
-          asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps
+        tc_fence_before();  // the accumulator has been read: hand the TMEM buffer back before the cross-warp statistics
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+        if (E::STATS) {
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // all epilogue warps
           const float* sb = stat_smem + (lt & 1) * 4 * 512;
-          for (int e = et; e < 2 * p.BN; e += 128) {  // element (k, n0 + col) is always owned by the same thread
+          for (int e = et; e < 2 * p.BN; e += kEpiThreads) {  // element (k, n0 + col) is always owned by the same thread
             const int k = e >= p.BN, col = e - k * p.BN;
             const float a = (sb[0 * 512 + k * 256 + col] + sb[1 * 512 + k * 256 + col]) + (sb[2 * 512 + k * 256 + col] + sb[3 * 512 + k * 256 + col]);
             stat_acc[k * p.Cout + c.n0 + col] += a;
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
     }
-    if (p.stats) {  // one deterministic partial row per CTA (static tile schedule)
+    if (E::STATS) {  // one deterministic partial row per CTA (static tile schedule)
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // the last tile's accumulation (other threads' elements) is complete
       float* gdst = p.stats + (size_t)blockIdx.x * 2 * p.Cout;
-      for (int e = et; e < 2 * p.Cout; e += 128) gdst[e] = stat_acc[e];
+      for (int e = et; e < 2 * p.Cout; e += kEpiThreads) gdst[e] = stat_acc[e];
     }
   }
 
@@ -426,6 +579,13 @@ static int ilog2(int v) {
   return s;
 }
 
+template <class E>
+static void launch_variant(const CUtensorMap& a, const CUtensorMap& b, const IGemmParams& p, int grid, size_t smem, cudaStream_t stream) {
+  static std::once_flag once;
+  std::call_once(once, [] { cudaFuncSetAttribute(igemm_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+  igemm_kernel<E><<<grid, kThreads, smem, stream>>>(a, b, p);
+}
+
 static int launch(const CUtensorMap& a, const CUtensorMap& b, IGemmParams& p, cudaStream_t stream, int* grid_out) {
   if (!is_pow2(p.tw) || !is_pow2(p.th) || !is_pow2(p.tiles_w) || !is_pow2(p.tiles_h) || !is_pow2(p.C_k) || !is_pow2(p.cpt)) {
     b200_set_error("igemm: image sides and channel counts must be powers of two");
@@ -439,7 +599,10 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, IGemmParams& p, cu
   p.cpt_sh = ilog2(p.cpt);
   p.kpb = (p.mode != MODE_WGRAD && p.BN <= 128 && p.kb_per_tile % 2 == 0) ? 2 : 1;
   const int stage_bytes = p.kpb * (kATileBytes + p.BN * 128);
-  const int extra = 1024 + 256 + kStatSmemBytes + kStatAccBytes;
+  const bool has_stats = p.stats != nullptr, has_bwd = p.bwd.y != nullptr;
+  // shared memory behind the pipeline stages: barriers, the statistics buffers, and for the fused backward the BatchNorm
+  // coefficients; the per-warp transpose tiles only when statistics are reduced
+  const int extra = 1024 + 256 + kStatSmemBytes + kStatAccBytes + kScaleShiftBytes + (has_stats ? kEpiWarps * kStatTileBytes : 0);
   if (p.stages <= 0) {
     p.stages = (227 * 1024 - extra) / stage_bytes;
     if (p.stages > 8) p.stages = 8;
@@ -452,11 +615,30 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, IGemmParams& p, cu
   while ((int)cols < 2 * p.BN) cols <<= 1;
   p.tmem_cols = cols;
   const size_t smem = (size_t)p.stages * stage_bytes + extra;
-  static std::once_flag once;
-  std::call_once(once, [] { cudaFuncSetAttribute(igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
   const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
   if (grid_out) *grid_out = grid;
-  igemm_kernel<<<grid, 192, smem, stream>>>(a, b, p);
+  const bool bn = p.bwd.scale != nullptr, g2 = p.bwd.g2 != nullptr;
+  const int act = p.bwd.act;
+  if (!has_bwd) {
+    if (has_stats) launch_variant<Epi<true, false, 0, false, false>>(a, b, p, grid, smem, stream);
+    else launch_variant<Epi<false, false, 0, false, false>>(a, b, p, grid, smem, stream);
+  } else if (act == ACT_BWD_LEAKY && bn && g2 && has_stats) {
+    launch_variant<Epi<true, true, ACT_BWD_LEAKY, true, true>>(a, b, p, grid, smem, stream);
+  } else if (act == ACT_BWD_LEAKY && bn && !g2 && has_stats) {
+    launch_variant<Epi<true, true, ACT_BWD_LEAKY, false, true>>(a, b, p, grid, smem, stream);
+  } else if (act == ACT_BWD_LEAKY && !bn && g2 && !has_stats) {
+    launch_variant<Epi<false, true, ACT_BWD_LEAKY, true, false>>(a, b, p, grid, smem, stream);
+  } else if (act == ACT_BWD_LEAKY && !bn && !g2 && !has_stats) {
+    launch_variant<Epi<false, true, ACT_BWD_LEAKY, false, false>>(a, b, p, grid, smem, stream);
+  } else if (act == ACT_BWD_RELU && bn && !g2 && has_stats) {
+    launch_variant<Epi<true, true, ACT_BWD_RELU, false, true>>(a, b, p, grid, smem, stream);
+  } else if (act == ACT_BWD_RELU && !bn && !g2 && !has_stats) {
+    launch_variant<Epi<false, true, ACT_BWD_RELU, false, false>>(a, b, p, grid, smem, stream);
+  } else {
+    b200_set_error("igemm: unsupported fused backward epilogue (supported: LeakyReLU [+skip] with/without BatchNorm statistics, ReLU [+dropout] "
+                   "with/without BatchNorm statistics; statistics are required exactly when a BatchNorm scale/shift is given)");
+    return B200_ERR_ARG;
+  }
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -473,12 +655,50 @@ using namespace b200;
 
 extern "C" {
 
+// C-ABI mirror of EpiBwd (include/b200_inpaint.h)
+struct b200_epi_bwd {
+  const void* y;
+  int ldy;
+  const float* scale;
+  const float* shift;
+  int act;
+  const void* g2;
+  int ldg2, offg2;
+  int dropout;
+  unsigned seed;
+  int col0;
+  int Cy;
+};
+
+static int set_bwd(IGemmParams& p, const b200_epi_bwd* e, int Cout, const char* who) {
+  p.bwd = EpiBwd{};
+  if (!e || !e->y) return B200_OK;
+  if (e->Cy > 512 || e->Cy % 32 || e->col0 % 32 || e->col0 + e->Cy != Cout || e->ldy % 8 || e->ldg2 % 8 || e->offg2 % 8 || e->act < 0 || e->act > 2 ||
+      (p.stats && Cout > 1024)) {
+    b200_set_error((std::string(who) + ": bad fused activation-backward epilogue (needs col0 + Cy == Cout, Cy <= 512, 32-channel granularity)").c_str());
+    return B200_ERR_ARG;
+  }
+  p.bwd.y = (const __nv_bfloat16*)e->y;
+  p.bwd.ldy = e->ldy;
+  p.bwd.scale = e->scale;
+  p.bwd.shift = e->shift;
+  p.bwd.act = e->act;
+  p.bwd.g2 = (const __nv_bfloat16*)e->g2;
+  p.bwd.ldg2 = e->ldg2;
+  p.bwd.offg2 = e->offg2;
+  p.bwd.dropout = e->dropout;
+  p.bwd.seed = e->seed;
+  p.bwd.col0 = e->col0;
+  p.bwd.Cy = e->Cy;
+  return B200_OK;
+}
+
 int b200_igemm_stat_rows(void) { return kNumSMs; }
 
 // y[B,H/2,W/2,ldy] (bf16) = conv4x4/s2/p1(x[B,H,W,Cin] bf16, wpk[Cout][16*Cin] bf16 with k = (kh*4+kw)*Cin + ci)
 // stats (optional): [b200_igemm_stat_rows()][2][Cout] fp32 per-CTA column sums / sums of squares of y; *stat_rows = rows written.
 int b200_conv_s2_gemm(const void* x, int B, int H, int W, int Cin, const void* wpk, int Cout, void* y, int ldy, int bn_hint, int stages, float* stats,
-                      int* stat_rows, cudaStream_t stream) {
+                      int* stat_rows, const b200_epi_bwd* bwd, cudaStream_t stream) {
   if (!is_pow2(H) || !is_pow2(W) || H < 2 || W < 2 || Cin % 64 || Cout % 32 || ldy % 8 || B < 1) {
     b200_set_error("conv_s2_gemm: unsupported shape");
     return B200_ERR_ARG;
@@ -497,7 +717,7 @@ int b200_conv_s2_gemm(const void* x, int B, int H, int W, int Cin, const void* w
   p.cpt = Cin / 64;
   p.kb_per_tile = p.kb_total = 16 * p.cpt;
   p.BN = pick_bn(Cout, bn_hint);
-  if (Cout % p.BN || p.BN % 32 || p.BN > 256 || (stats && Cout > 512)) {
+  if (Cout % p.BN || p.BN % 32 || p.BN > 256 || (stats && Cout > 1024)) {
     b200_set_error("conv_s2_gemm: bad N tile");
     return B200_ERR_ARG;
   }
@@ -510,8 +730,9 @@ int b200_conv_s2_gemm(const void* x, int B, int H, int W, int Cin, const void* w
   p.m_tiles = 1;
   p.num_tiles = p.num_ptiles * p.n_tiles;
   p.stats = stats;
-  CUtensorMap ta, tb;
   int rc;
+  if ((rc = set_bwd(p, bwd, Cout, "conv_s2_gemm"))) return rc;
+  CUtensorMap ta, tb;
   if ((rc = map_nhwc_parity(&ta, x, B, H, W, Cin, p.tw, p.th, p.nb))) return rc;
   if ((rc = map_weights(&tb, wpk, Cout, 16 * Cin, p.BN))) return rc;
   return launch(ta, tb, p, stream, stat_rows);
@@ -519,7 +740,7 @@ int b200_conv_s2_gemm(const void* x, int B, int H, int W, int Cin, const void* w
 
 // y[B,2Hi,2Wi,ldy] (bf16) = convT4x4/s2/p1(z[B,Hi,Wi,Cin] (pixel stride ldz), wpk[4 phases][Cout][4*Cin]); stats as above.
 int b200_convt_s2_gemm(const void* z, int B, int Hi, int Wi, int Cin, int ldz, const void* wpk, int Cout, void* y, int ldy, int bn_hint, int stages,
-                       float* stats, int* stat_rows, cudaStream_t stream) {
+                       float* stats, int* stat_rows, const b200_epi_bwd* bwd, cudaStream_t stream) {
   if (!is_pow2(Hi) || !is_pow2(Wi) || Cin % 64 || Cout % 32 || ldy % 8 || ldz % 8 || B < 1) {
     b200_set_error("convt_s2_gemm: unsupported shape");
     return B200_ERR_ARG;
@@ -538,7 +759,7 @@ int b200_convt_s2_gemm(const void* z, int B, int Hi, int Wi, int Cin, int ldz, c
   p.cpt = Cin / 64;
   p.kb_per_tile = p.kb_total = 4 * p.cpt;
   p.BN = pick_bn(Cout, bn_hint);
-  if (Cout % p.BN || p.BN % 32 || p.BN > 256 || (stats && Cout > 512)) {
+  if (Cout % p.BN || p.BN % 32 || p.BN > 256 || (stats && Cout > 1024)) {
     b200_set_error("convt_s2_gemm: bad N tile");
     return B200_ERR_ARG;
   }
@@ -551,8 +772,9 @@ int b200_convt_s2_gemm(const void* z, int B, int Hi, int Wi, int Cin, int ldz, c
   p.m_tiles = 1;
   p.num_tiles = p.num_ptiles * p.n_tiles * 4;
   p.stats = stats;
-  CUtensorMap ta, tb;
   int rc;
+  if ((rc = set_bwd(p, bwd, Cout, "convt_s2_gemm"))) return rc;
+  CUtensorMap ta, tb;
   if ((rc = map_nhwc(&ta, z, B, Hi, Wi, Cin, ldz, p.tw, p.th, p.nb))) return rc;
   if ((rc = map_weights(&tb, wpk, 4 * Cout, 4 * Cin, p.BN))) return rc;
   return launch(ta, tb, p, stream, stat_rows);
@@ -599,6 +821,7 @@ int b200_wgrad_gemm(const void* S, int B, int Hs, int Ws, int Cs, int lds, const
   p.phases = 1;
   p.num_tiles = p.m_tiles * p.n_tiles * splits;
   p.stats = nullptr;
+  p.bwd = EpiBwd{};
   CUtensorMap ta, tb;
   int rc;
   if ((rc = map_nhwc(&ta, S, B, Hs, Ws, Cs, lds, p.tw, p.th, p.nb))) return rc;

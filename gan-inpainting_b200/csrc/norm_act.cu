@@ -75,14 +75,20 @@ __global__ void __launch_bounds__(kStatThreads) bn_stats_kernel(const __nv_bfloa
 // Sum the per-block partials of 32 consecutive channels: thread (w, l) walks blocks w, w+32, ... of channel c0+l
 // (coalesced 128-byte rows), fp64 accumulate, fixed-order tree over the 32 walkers -> deterministic.
 constexpr int kFinThreads = 1024;
-__device__ __forceinline__ void reduce_partials(const float* __restrict__ partial, int nblk, int C, int c, double& s, double& q) {
+// element (blk, k, c) lives at partial[blk * row_stride + k * k_stride + c]
+__device__ __forceinline__ void reduce_partials(const float* __restrict__ partial, int nblk, int C, int c, double& s, double& q, int row_stride = 0,
+                                                int k_stride = 0) {
+  if (row_stride == 0) {
+    row_stride = 2 * C;
+    k_stride = C;
+  }
   __shared__ double sh[2][32][33];
   const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
   double a = 0.0, b = 0.0;
   if (c < C) {
     for (int blk = w; blk < nblk; blk += 32) {
-      a += (double)partial[((size_t)blk * 2 + 0) * C + c];
-      b += (double)partial[((size_t)blk * 2 + 1) * C + c];
+      a += (double)partial[(size_t)blk * row_stride + c];
+      b += (double)partial[(size_t)blk * row_stride + k_stride + c];
     }
   }
   sh[0][w][l] = a;
@@ -320,10 +326,10 @@ __global__ void __launch_bounds__(kStatThreads) bn_bwd_reduce_kernel(const BwdPa
 __global__ void __launch_bounds__(kFinThreads) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int C, double count,
                                                                       const float* __restrict__ stats, const float* __restrict__ gamma,
                                                                       float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate,
-                                                                      float* __restrict__ coef) {
+                                                                      float* __restrict__ coef, int row_stride, int k_stride) {
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   double sdz, sdzy;
-  reduce_partials(partial, nblk, C, c, sdz, sdzy);
+  reduce_partials(partial, nblk, C, c, sdz, sdzy, row_stride, k_stride);
   if (threadIdx.x >= 32 || c >= C) return;
   const double mean = stats[0 * C + c], rstd = stats[1 * C + c];
   const double dg = rstd * (sdzy - mean * sdz);  // sum dz * xhat
@@ -475,10 +481,39 @@ int b200_bn_act_bwd(const void* y, long long P, int C, const float* stats /*[4][
     const int nblk = b200_bn_stat_blocks(P, C);
     bn_bwd_reduce_kernel<<<nblk, kStatThreads, 0, stream>>>(p);
     B200_CHECK_LAUNCH();
-    bn_bwd_finalize_kernel<<<(C + 31) / 32, kFinThreads, 0, stream>>>((const float*)partial, nblk, C, (double)P, stats, gamma, dgamma, dbeta, accumulate, coef);
+    bn_bwd_finalize_kernel<<<(C + 31) / 32, kFinThreads, 0, stream>>>((const float*)partial, nblk, C, (double)P, stats, gamma, dgamma, dbeta, accumulate, coef, 0, 0);
     B200_CHECK_LAUNCH();
     p.coef = coef;
   }
+  bn_bwd_apply_kernel<<<grid_for(P * (C >> 3), 256), 256, 0, stream>>>(p);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+// BatchNorm backward when the producing data-gradient GEMM already wrote dz (gradient w.r.t. the BatchNorm output) and the
+// per-CTA partial rows (sum dz, sum dz*y) — b200_conv_s2_gemm / b200_convt_s2_gemm with a b200_epi_bwd.  Element (row, k, c) of
+// the partials is partial[row * row_stride + k * k_stride + c].  Produces dgamma / dbeta and dy = gradient w.r.t. the conv output y.
+int b200_bn_bwd_fused(const void* y, long long P, int C, const float* stats, const float* gamma, const void* dz, int lddz, int offdz, const float* partial,
+                      int rows, int row_stride, int k_stride, float* coef, float* dgamma, float* dbeta, int accumulate, void* dy, cudaStream_t stream) {
+  const int cs = chunk_shift(C);
+  if (cs < 0 || !stats || lddz % 8 || offdz % 8 || rows < 1 || P * (C >> 3) >= (1LL << 31)) {
+    b200_set_error("bn_bwd_fused: C must be a power of two in [8, 2048]; strides / offsets multiples of 8");
+    return B200_ERR_ARG;
+  }
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, kFinThreads, 0, stream>>>(partial, rows, C, (double)P, stats, gamma, dgamma, dbeta, accumulate, coef, row_stride,
+                                                                    k_stride);
+  B200_CHECK_LAUNCH();
+  BwdParams p{};
+  p.y = (const __nv_bfloat16*)y;
+  p.P = (int)P;
+  p.C = C;
+  p.cshift = cs;
+  p.act = ACT_NONE;  // g1 already is dz
+  p.g1 = (const __nv_bfloat16*)dz;
+  p.ldg1 = lddz;
+  p.offg1 = offdz;
+  p.coef = coef;
+  p.dy = (__nv_bfloat16*)dy;
   bn_bwd_apply_kernel<<<grid_for(P * (C >> 3), 256), 256, 0, stream>>>(p);
   B200_CHECK_LAUNCH();
   return B200_OK;

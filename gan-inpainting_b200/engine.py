@@ -105,25 +105,54 @@ class BnPlan:
         return stats
 
 
-def conv_s2(x, wpk, cout, out=None, ldy=None, plan: Optional[BnPlan] = None):
+class ActBwd:
+    """Fused backward-of-activation epilogue of a data-gradient GEMM (``b200_epi_bwd``): the GEMM's output columns
+    ``[col0, col0 + Cy)`` are gradients w.r.t. ``act(dropout(bn(y)))``; the epilogue stores ``dz`` (gradient w.r.t. the
+    BatchNorm output) instead and, for a training-mode BatchNorm, leaves the per-CTA (sum dz, sum dz*y) rows in the scratch."""
+
+    def __init__(self, y, Cy, stats, act, col0=0, g2=None, ldg2=0, offg2=0, dropout=False, seed=0, scratch: Optional["Scratch"] = None):
+        self.Cy, self.col0, self.has_bn = Cy, col0, stats is not None
+        self.keep = (y, stats, g2)  # the raw pointers below must outlive the launch
+        self.c = _lib.EpiBwd(y.data_ptr(), Cy, stats.data_ptr() + 2 * Cy * 4 if stats is not None else None,
+                             stats.data_ptr() + 3 * Cy * 4 if stats is not None else None, act, g2.data_ptr() if g2 is not None else None, ldg2, offg2,
+                             int(dropout), int(seed) & 0xFFFFFFFF, col0, Cy)
+        self.scratch = scratch
+        self.rows = ctypes.c_int(0)
+
+    def args(self):
+        want = self.has_bn and self.scratch is not None
+        return (ptr(self.scratch.bn_partial) if want else None, ctypes.byref(self.rows) if want else None, ctypes.byref(self.c))
+
+
+def bn_bwd_fused(y, C, stats, gamma, dz, lddz, offdz, epi: ActBwd, cout_total, dgamma, dbeta, accumulate, scratch: "Scratch"):
+    """Finish a BatchNorm backward whose dz and partial sums came out of a GEMM epilogue: dgamma / dbeta, and dy."""
+    P = y.numel() // C
+    dy = _empty(y.shape, bf16, y.device)
+    part = ctypes.c_void_p(scratch.bn_partial.data_ptr() + epi.col0 * 4)
+    call("b200_bn_bwd_fused", ptr(y), P, C, ptr(stats), ptr(gamma), ptr(dz), lddz, offdz, part, epi.rows.value, 2 * cout_total, cout_total, ptr(scratch.coef),
+         ptr(dgamma), ptr(dbeta), int(accumulate), ptr(dy), stream())
+    return dy
+
+
+def conv_s2(x, wpk, cout, out=None, ldy=None, plan: Optional[BnPlan] = None, epi: Optional[ActBwd] = None):
     """x [B,H,W,Cin] bf16 -> [B,H/2,W/2,cout]; wpk [cout][16*Cin]."""
     B, H, W, Cin = x.shape
     if out is None:
         out = _empty((B, H // 2, W // 2, cout), bf16, x.device)
         ldy = cout
     bn = pick_bn(_m_tiles(B, H // 2, W // 2), cout)
-    call("b200_conv_s2_gemm", ptr(x), B, H, W, Cin, ptr(wpk), cout, ptr(out), ldy, bn, 0, ptr(plan.scratch.bn_partial) if plan else None,
-         ctypes.byref(plan.rows) if plan else None, stream())
+    extra = epi.args() if epi is not None else (ptr(plan.scratch.bn_partial) if plan else None, ctypes.byref(plan.rows) if plan else None, None)
+    call("b200_conv_s2_gemm", ptr(x), B, H, W, Cin, ptr(wpk), cout, ptr(out), ldy, bn, 0, *extra, stream())
     return out
 
 
-def convt_s2(z, ldz, cin, wpk, cout, plan: Optional[BnPlan] = None):
+def convt_s2(z, ldz, cin, wpk, cout, plan: Optional[BnPlan] = None, epi: Optional[ActBwd] = None):
     """z [B,Hi,Wi,>=cin] (pixel stride ldz) -> [B,2Hi,2Wi,cout]; wpk [4][cout][4*cin]."""
     B, Hi, Wi = z.shape[:3]
     out = _empty((B, 2 * Hi, 2 * Wi, cout), bf16, z.device)
     bn = pick_bn(_m_tiles(B, Hi, Wi), cout, phases=4)
-    call("b200_convt_s2_gemm", ptr(z), B, Hi, Wi, cin, ldz, ptr(wpk), cout, ptr(out), cout, bn, 0, ptr(plan.scratch.bn_partial) if plan else None,
-         ctypes.byref(plan.rows) if plan else None, stream())
+    extra = epi.args() if epi is not None else (ptr(plan.scratch.bn_partial) if plan else None, ctypes.byref(plan.rows) if plan else None, None)
+    call("b200_convt_s2_gemm", ptr(z), B, Hi, Wi, cin, ldz, ptr(wpk), cout, ptr(out), cout, bn, 0, *extra, stream())
     return out
 
 
@@ -330,30 +359,45 @@ class GeneratorEngine:
         dcat = _empty(c.cat[1].shape, bf16, dev)
         call("b200_conv_c1_fwd", ptr(dpre), None, B, R, R, ptr(up1.weight.data), 2 * w[1], ACT_NONE, ptr(dcat), None, 0, 0, stream())
         dcats = {1: dcat}
-        # ---- decoder u2 .. uN
+        # ---- decoder u2 .. uN.  The data-gradient GEMM of level l also evaluates the activation backward of what feeds its
+        # up half (relu(drop(bn(yu[l+1]))), or relu(y[N]) for the innermost level) and the BatchNorm reductions.
+        epi = None
         for l in range(2, N + 1):
             bn = self.un[l - 1]
-            dyu = bn_act_bwd(c.yu[l], w[l - 1], c.su[l], bn.weight.data, ACT_RELU, dcats[l - 1], 2 * w[l - 1], w[l - 1], None, 0, 0,
-                             c.dropout and l in self.dropout_levels, c.seed * 16 + l, G(bn.weight), G(bn.bias), accumulate, sc)
+            drop = c.dropout and l in self.dropout_levels
+            if epi is None:  # yu[2]: its gradient comes from the 1-channel kernel above
+                dyu = bn_act_bwd(c.yu[l], w[l - 1], c.su[l], bn.weight.data, ACT_RELU, dcats[l - 1], 2 * w[l - 1], w[l - 1], None, 0, 0, drop, c.seed * 16 + l,
+                                 G(bn.weight), G(bn.bias), accumulate, sc)
+            else:
+                dyu = bn_bwd_fused(c.yu[l], w[l - 1], c.su[l], bn.weight.data, dcats[l - 1], 2 * w[l - 1], w[l - 1], epi, 2 * w[l - 1], G(bn.weight), G(bn.bias),
+                                   accumulate, sc)
             done(bn.bias)
             zin, cin = (c.r_in, w[N]) if l == N else (c.cat[l], 2 * w[l])
             wgrad(zin, cin, cin, dyu, G(self.uc[l - 1].weight), accumulate, sc)
             done(self.uc[l - 1].weight)
-            dcats[l] = conv_s2(dyu, self.packed_u[l].gather, cin)
-        # ---- encoder dN .. d2
-        dy = bn_act_bwd(c.y[N], w[N], None, None, ACT_RELU, dcats[N], w[N], 0, None, 0, 0, False, 0, None, None, False, sc)
+            if l < N:
+                epi = ActBwd(c.yu[l + 1], w[l], c.su[l + 1], ACT_RELU, col0=w[l], dropout=c.dropout and (l + 1) in self.dropout_levels,
+                             seed=c.seed * 16 + l + 1, scratch=sc)
+            else:
+                epi = ActBwd(c.y[N], w[N], None, ACT_RELU)
+            dcats[l] = conv_s2(dyu, self.packed_u[l].gather, cin, epi=epi)
+        # ---- encoder dN .. d2: dcats[N] already is the gradient w.r.t. y[N]
+        dy = dcats[N]
         for l in range(N, 1, -1):
             if l < N:
                 bn = self.dn[l - 1]
-                dy = bn_act_bwd(c.y[l], w[l], c.sd[l], bn.weight.data, ACT_LEAKY, da, w[l], 0, dcats[l], 2 * w[l], 0, False, 0, G(bn.weight), G(bn.bias),
-                                accumulate, sc)
+                dy = bn_bwd_fused(c.y[l], w[l], c.sd[l], bn.weight.data, dz, w[l], 0, epi, w[l], G(bn.weight), G(bn.bias), accumulate, sc)
                 done(bn.weight)
             wgrad(dy, w[l], w[l], c.a[l - 1], G(self.dc[l - 1].weight), accumulate, sc)
             done(self.dc[l - 1].weight)
-            da = convt_s2(dy, w[l], w[l], self.packed_d[l].phase, w[l - 1])
+            # gradient w.r.t. a[l-1] = leaky(bn(y[l-1])), merged with the skip gradient (through relu of the same tensor)
+            if l - 1 >= 2:
+                epi = ActBwd(c.y[l - 1], w[l - 1], c.sd[l - 1], ACT_LEAKY, g2=dcats[l - 1], ldg2=2 * w[l - 1], offg2=0, scratch=sc)
+            else:
+                epi = ActBwd(c.a[1], w[1], None, ACT_LEAKY, g2=dcats[1], ldg2=2 * w[1], offg2=0)
+            dz = convt_s2(dy, w[l], w[l], self.packed_d[l].phase, w[l - 1], epi=epi)
         # ---- d1
-        dz1 = bn_act_bwd(c.a[1], w[1], None, None, ACT_LEAKY, da, w[1], 0, dcats[1], 2 * w[1], 0, False, 0, None, None, False, sc)
-        call("b200_wgrad_c1", ptr(dz1), B, side(1), side(1), w[1], w[1], ptr(c.x), None, ptr(sc.c1_partial), ptr(G(self.dc[0].weight)), acc, stream())
+        call("b200_wgrad_c1", ptr(dz), B, side(1), side(1), w[1], w[1], ptr(c.x), None, ptr(sc.c1_partial), ptr(G(self.dc[0].weight)), acc, stream())
         done(self.dc[0].weight)
 
 
@@ -442,16 +486,22 @@ class DiscriminatorEngine:
             done(self.hc.weight)
         da = _empty(c.a[3].shape, bf16, dev)
         call("b200_head_bwd_input", ptr(dlin), ptr(self.E), B, S * S * 512, ptr(da), stream())
+        epi = None
         for i in range(3, 0, -1):
             C = 64 << i
             bn = self.norms[i]
-            dy = bn_act_bwd(c.y[i], C, c.st[i], bn.weight.data, ACT_LEAKY, da, C, 0, None, 0, 0, False, 0, G(bn.weight) if G else None, G(bn.bias) if G else None,
-                            accumulate, sc)
+            if epi is None:  # y[3]: its gradient comes from the head kernel above
+                dy = bn_act_bwd(c.y[i], C, c.st[i], bn.weight.data, ACT_LEAKY, da, C, 0, None, 0, 0, False, 0, G(bn.weight) if G else None,
+                                G(bn.bias) if G else None, accumulate, sc)
+            else:
+                dy = bn_bwd_fused(c.y[i], C, c.st[i], bn.weight.data, da, C, 0, epi, C, G(bn.weight) if G else None, G(bn.bias) if G else None, accumulate, sc)
             if G is not None:
                 wgrad(dy, C, C, c.a[i - 1], G(self.convs[i].weight), accumulate, sc)
                 done(self.convs[i].weight)
-            da = convt_s2(dy, C, C, self.packed[i].phase, C // 2)
-        dz = bn_act_bwd(c.a[0], 64, None, None, ACT_LEAKY, da, 64, 0, None, 0, 0, False, 0, None, None, False, sc)
+            # data gradient with the LeakyReLU (and BatchNorm reductions) of the layer below evaluated in the GEMM epilogue
+            epi = ActBwd(c.y[i - 1], C // 2, c.st[i - 1], ACT_LEAKY, scratch=sc) if i - 1 >= 1 else ActBwd(c.a[0], 64, None, ACT_LEAKY)
+            da = convt_s2(dy, C, C, self.packed[i].phase, C // 2, epi=epi)
+        dz = da
         if G is not None:
             call("b200_wgrad_c1", ptr(dz), B, R // 2, R // 2, 64, 64, ptr(c.x), ptr(c.xmul), ptr(sc.c1_partial), ptr(G(self.convs[0].weight)), acc, stream())
             done(self.convs[0].weight)

@@ -62,15 +62,34 @@ long long b200_launch_count(void);  /* kernels launched by this library since lo
 /* nn.Conv2d(Cin, Cout, 4, 2, 1, bias=False) forward — networks.py:285-286 (generator d2..d7), :340-348 (PatchGAN c2..c4);
  * also the data gradient of nn.ConvTranspose2d.  x [B,H,W,Cin]; wpk [Cout][16*Cin] from b200_pack_gather;
  * y [B,H/2,W/2,*] with pixel stride ldy. */
+/* Optional fused backward-of-activation epilogue of the two data-gradient uses (autograd of networks.py:287-289, 310-314, 338-349):
+ * output columns >= col0 are gradients w.r.t. act(dropout(bn(y)))[:, col - col0]; the epilogue stores dz (gradient w.r.t. the
+ * BatchNorm output z = y*scale + shift) instead, and with `stats` accumulates (sum dz, sum dz*y) per channel for b200_bn_bwd_fused.
+ * LeakyReLU: dz = z > 0 ? g + g2 : 0.2 g (g2 = optional skip-connection gradient); ReLU: dz = z > 0 ? g : 0, with
+ * dropout dz = keep ? 2 dz : 0.  y == NULL disables it. */
+typedef struct b200_epi_bwd {
+  const void* y;      /* forward conv output, bf16, pixel stride ldy */
+  int ldy;
+  const float* scale; /* forward BatchNorm scale / shift (stats_out + 2C / + 3C); NULL: no norm */
+  const float* shift;
+  int act;
+  const void* g2;
+  int ldg2, offg2;
+  int dropout;
+  unsigned seed;
+  int col0;
+  int Cy;             /* channels of y; col0 + Cy == Cout */
+} b200_epi_bwd;
+
 int b200_igemm_stat_rows(void);
 int b200_conv_s2_gemm(const void* x, int B, int H, int W, int Cin, const void* wpk, int Cout, void* y, int ldy, int bn_hint, int stages, float* stats,
-                      int* stat_rows, b200_stream_t stream);
+                      int* stat_rows, const b200_epi_bwd* bwd, b200_stream_t stream);
 
 /* nn.ConvTranspose2d(Cin, Cout, 4, 2, 1, bias=False) forward as 4 sub-pixel phases — networks.py:300-309 (u7..u2);
  * also the data gradient of nn.Conv2d.  z [B,Hi,Wi,*] with pixel stride ldz; wpk [4][Cout][4*Cin] from b200_pack_phase;
  * y [B,2Hi,2Wi,*] with pixel stride ldy. */
 int b200_convt_s2_gemm(const void* z, int B, int Hi, int Wi, int Cin, int ldz, const void* wpk, int Cout, void* y, int ldy, int bn_hint, int stages,
-                       float* stats, int* stat_rows, b200_stream_t stream);
+                       float* stats, int* stat_rows, const b200_epi_bwd* bwd, b200_stream_t stream);
 
 /* Weight gradient of both layer kinds (autograd of the call sites above; wgan_l1.py:138,141,183):
  *   partial[s][cs][(kh*4+kw)*Cl + cl] = sum over the pixels of split s of S[b,i,j,cs] * L[b,2i+kh-1,2j+kw-1,cl]
@@ -117,6 +136,11 @@ int b200_bn_act(const void* y, long long P, int C, const float* scale, const flo
 int b200_bn_act_bwd(const void* y, long long P, int C, const float* stats, const float* gamma, int act, const void* g1, int ldg1, int offg1, const void* g2,
                     int ldg2, int offg2, int dropout, unsigned seed, void* partial, float* coef, float* dgamma, float* dbeta, int accumulate, void* dy,
                     b200_stream_t stream);
+
+/* BatchNorm backward after a data-gradient GEMM with a b200_epi_bwd epilogue: dz [P][C] (pixel stride lddz, channel offset offdz)
+ * and the GEMM's partial rows (element (row, k, c) at partial[row*row_stride + k*k_stride + c]) -> dgamma, dbeta, dy. */
+int b200_bn_bwd_fused(const void* y, long long P, int C, const float* stats, const float* gamma, const void* dz, int lddz, int offdz, const float* partial,
+                      int rows, int row_stride, int k_stride, float* coef, float* dgamma, float* dbeta, int accumulate, void* dy, b200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * layers with one channel on one side + the discriminator head (csrc/conv_direct.cu)

@@ -97,6 +97,84 @@ def test_conv_epilogue_batchnorm_statistics(dev, kind, B, H, Cin, Cout):
     assert int(bn.num_batches_tracked) == 1
 
 
+def _bn_bwd_reference(y, dz, gamma, eps=1e-5):
+    """dgamma, dbeta, dy of training-mode BatchNorm given dz = gradient w.r.t. its output (all [P, C] fp32)."""
+    n = y.shape[0]
+    mean, var = y.mean(0), y.var(0, unbiased=False)
+    rstd = 1.0 / torch.sqrt(var + eps)
+    xhat = (y - mean) * rstd
+    dgamma, dbeta = (dz * xhat).sum(0), dz.sum(0)
+    return dgamma, dbeta, gamma * rstd * (dz - dbeta / n - xhat * dgamma / n)
+
+
+@pytest.mark.parametrize("B,H,Cin,Cy,skip,norm", [(3, 8, 128, 64, True, True), (20, 16, 128, 64, False, True), (2, 4, 512, 256, True, False)])
+def test_fused_leaky_bn_backward_in_conv_dgrad_epilogue(dev, B, H, Cin, Cy, skip, norm):
+    """Conv2d data gradient (4-phase kernel) whose epilogue applies the LeakyReLU backward of the layer below, merges the skip-connection
+    gradient and reduces (sum dz, sum dz*y) for that layer's BatchNorm; b200_bn_bwd_fused finishes dgamma / dbeta / dy."""
+    eng = _eng()
+    torch.manual_seed(11)
+    sc = eng.Scratch.get(dev)
+    y = bf(torch.randn(B, 2 * H, 2 * H, Cy, device=dev) * 1.5 + 0.3)           # forward conv output of the layer below
+    gamma, beta = torch.rand(Cy, device=dev) + 0.5, torch.randn(Cy, device=dev) * 0.3
+    st = eng.bn_stats(y, Cy, gamma, beta, None, None, None, 0.1, 1e-5, sc) if norm else None
+    dyin = bf(torch.randn(B, H, H, Cin, device=dev))                             # gradient w.r.t. the conv output of this layer
+    w = torch.randn(Cin, Cy, 4, 4, device=dev) / math.sqrt(Cin * 4)
+    g2 = bf(torch.randn(B, 2 * H, 2 * H, 2 * Cy, device=dev)) if skip else None
+    epi = eng.ActBwd(y, Cy, st, 1, g2=g2, ldg2=2 * Cy, offg2=0, scratch=sc)
+    dz = eng.convt_s2(dyin, Cin, Cin, _packs(w).phase, Cy, epi=epi)
+    g = nhwc(torch.nn.grad.conv2d_input((B, Cy, 2 * H, 2 * H), bf(w).float(), nchw(dyin.float()), stride=2, padding=1))
+    yf = y.float()
+    z = yf * st[2] + st[3] if norm else yf
+    ref = torch.where(z > 0, g + (g2[..., :Cy].float() if skip else 0.0), 0.2 * g)
+    assert rel(dz, ref) < BF16_TOL
+    if norm:
+        dgamma, dbeta = torch.zeros(Cy, device=dev), torch.zeros(Cy, device=dev)
+        dy = eng.bn_bwd_fused(y, Cy, st, gamma, dz, Cy, 0, epi, Cy, dgamma, dbeta, False, sc)
+        rg, rb, rdy = _bn_bwd_reference(yf.reshape(-1, Cy), dz.float().reshape(-1, Cy), gamma)
+        assert rel(dgamma, rg) < 1e-3 and rel(dbeta, rb) < 1e-3
+        assert rel(dy.reshape(-1, Cy), rdy) < BF16_TOL
+
+
+@pytest.mark.parametrize("B,H,Cy,Cin,drop,norm", [(3, 16, 128, 64, True, True), (24, 16, 128, 128, False, True), (2, 4, 512, 512, False, False),
+                                                   (80, 32, 128, 64, False, True)])
+def test_fused_relu_dropout_bn_backward_in_convt_dgrad_epilogue(dev, B, H, Cy, Cin, drop, norm):
+    """ConvTranspose2d data gradient (gather kernel): output = [skip half | up half]; the up half goes through the backward of
+    relu(dropout(bn(y))) in the epilogue (networks.py:304-314), the skip half is stored untouched."""
+    eng, lib = _eng(), _lib()
+    torch.manual_seed(12)
+    sc = eng.Scratch.get(dev)
+    Ho = H // 2
+    col0 = Cy if norm else 0            # the innermost level has no concat: all columns fused, no norm
+    Cout = col0 + Cy
+    y = bf(torch.randn(B, Ho, Ho, Cy, device=dev) + 0.2)
+    gamma, beta = torch.rand(Cy, device=dev) + 0.5, torch.randn(Cy, device=dev) * 0.3
+    st = eng.bn_stats(y, Cy, gamma, beta, None, None, None, 0.1, 1e-5, sc) if norm else None
+    dyin = bf(torch.randn(B, H, H, Cin, device=dev))
+    w = torch.randn(Cout, Cin, 4, 4, device=dev) / math.sqrt(Cin * 16)           # ConvTranspose2d weight (in = Cout here, out = Cin)
+    seed = 77
+    epi = eng.ActBwd(y, Cy, st, 2, col0=col0, dropout=drop, seed=seed, scratch=sc)
+    out = eng.conv_s2(dyin, _packs(w).gather, Cout, epi=epi)
+    g = nhwc(F.conv2d(nchw(dyin.float()), bf(w).float(), stride=2, padding=1))
+    if col0:
+        assert rel(out[..., :col0], g[..., :col0]) < BF16_TOL
+    yf = y.float()
+    z = yf * st[2] + st[3] if norm else yf
+    ref = torch.where(z > 0, g[..., col0:], torch.zeros_like(z))
+    if drop:
+        ones = torch.ones_like(y)
+        keep = torch.empty_like(y)
+        eng.bn_act(ones, Cy, None, 0, keep, Cy, 0, dropout=True, seed=seed)
+        ref = ref * keep.float()
+    assert rel(out[..., col0:], ref) < BF16_TOL
+    if norm:
+        dgamma, dbeta = torch.zeros(Cy, device=dev), torch.zeros(Cy, device=dev)
+        dz = out[..., col0:].float().reshape(-1, Cy)
+        dy = eng.bn_bwd_fused(y, Cy, st, gamma, out, Cout, col0, epi, Cout, dgamma, dbeta, False, sc)
+        rg, rb, rdy = _bn_bwd_reference(yf.reshape(-1, Cy), dz, gamma)
+        assert rel(dgamma, rg) < 1e-3 and rel(dbeta, rb) < 1e-3
+        assert rel(dy.reshape(-1, Cy), rdy) < BF16_TOL
+
+
 @pytest.mark.parametrize("B,H,Cin,Cout", [(2, 16, 64, 128), (4, 8, 256, 512)])
 def test_conv_dgrad_is_phase_convt(dev, B, H, Cin, Cout):
     """Conv2d data gradient == the 4-phase transposed-conv kernel with the phase-packed Conv2d weight."""

@@ -88,7 +88,7 @@ def test_generator_vs_reference_golden(dev, golden):
     assert rel(ev, golden["unet_eval_out"]) < 1.5e-2, rel(ev, golden["unet_eval_out"])
 
 
-@pytest.mark.parametrize("res,batch", [(128, 8), (256, 4)])
+@pytest.mark.parametrize("res,batch", [(128, 8), (256, 8)])
 def test_generator_vs_oracle_live(dev, res, batch):
     nets, steps, synth = _oracle()
     ground, mask = synth.make_batch(batch, res, seed=77)
