@@ -270,9 +270,10 @@ def run_b200(args):
     kernel_ms = {}
     if rank == 0:
         _lib.PROFILE = hook
-        step_dev()
-        torch.cuda.synchronize()
-        _lib.PROFILE = None
+    step_dev()  # every rank takes part (the step contains the gradient all-reduces); only rank 0 is instrumented
+    torch.cuda.synchronize()
+    _lib.PROFILE = None
+    if rank == 0:
         kernel_ms = {k: sum(a.elapsed_time(b) for a, b in v) for k, v in prof.items()}
     if dist:
         dist.barrier()
