@@ -33,13 +33,14 @@ SIGNATURES = {
     # ---- weight layouts (csrc/pack.cu)
     "b200_pack_gather": [P, I, I, P, S],
     "b200_pack_phase": [P, I, I, P, S],
+    "b200_pack_all": [P, I, I, S],
     "b200_wgrad_reduce": [P, I, I, I, P, I, S],
     # ---- BatchNorm + activation (csrc/norm_act.cu)
     "b200_bn_stats": [P, L, I, P, P, P, P, P, P, F, F, P, S],
     "b200_bn_finalize": [P, I, L, I, P, P, P, P, P, F, F, P, S],
     "b200_bn_eval_coeffs": [I, P, P, P, P, F, P, S],
     "b200_bn_act": [P, L, I, P, P, I, P, I, I, P, I, I, I, U, S],
-    "b200_bn_bwd_fused": [P, L, I, P, P, P, I, I, P, I, I, I, P, P, P, I, P, S],
+    "b200_bn_bwd_fused": [P, L, I, P, P, P, I, I, I, P, I, I, I, P, P, P, I, P, S],
     "b200_bn_act_bwd": [P, L, I, P, P, I, P, I, I, P, I, I, I, U, P, P, P, P, I, P, S],
     # ---- single-channel-side convolutions and the discriminator head (csrc/conv_direct.cu)
     "b200_conv_c1_fwd": [P, P, I, I, I, P, I, I, P, P, I, I, S],
@@ -80,7 +81,7 @@ class EpiBwd(ctypes.Structure):
     """ctypes mirror of ``b200_epi_bwd`` (include/b200_inpaint.h)."""
 
     _fields_ = [("y", c_void_p), ("ldy", c_int), ("scale", c_void_p), ("shift", c_void_p), ("act", c_int), ("g2", c_void_p), ("ldg2", c_int),
-                ("offg2", c_int), ("dropout", c_int), ("seed", c_uint32), ("col0", c_int), ("Cy", c_int)]
+                ("offg2", c_int), ("dropout", c_int), ("seed", c_uint32), ("col0", c_int), ("Cy", c_int), ("dz32", c_void_p)]
 
 
 class B200Error(RuntimeError):

@@ -365,12 +365,22 @@ __global__ void __launch_bounds__(256) wgrad_c1_kernel(const __nv_bfloat16* __re
   }
 }
 
-__global__ void partial_sum_kernel(const float* __restrict__ partial, int nblk, int n, float* __restrict__ out, int accumulate) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
+// out[k] (+)= sum_b partial[b][k]: block = 32 outputs, warp w sums rows w, w+8, ... (fp64), fixed-order combine (deterministic)
+__global__ void __launch_bounds__(256) partial_sum_kernel(const float* __restrict__ partial, int nblk, int n, float* __restrict__ out, int accumulate) {
+  __shared__ double red[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + lane;
   double s = 0.0;
-  for (int b = 0; b < nblk; ++b) s += (double)partial[(size_t)b * n + k];
-  out[k] = accumulate ? out[k] + (float)s : (float)s;
+  if (k < n)
+    for (int b = warp; b < nblk; b += 8) s += (double)partial[(size_t)b * n + k];
+  red[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && k < n) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][lane];
+    out[k] = accumulate ? out[k] + (float)t : (float)t;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -478,17 +488,28 @@ __global__ void __launch_bounds__(256) head_bwd_dE_kernel(const float* __restric
 }
 
 // dW5[c][kh][kw] = sum_{oh,ow} dE[oh+kh][ow+kw][c] * Wl[oh*n+ow]
-__global__ void head_bwd_w5_kernel(const float* __restrict__ dE, const float* __restrict__ wl, int S, int C, float* __restrict__ dw5, int accumulate) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // (tap, c) with c fastest for coalesced dE reads
-  if (idx >= 16 * C) return;
-  const int c = idx % C, tap = idx / C;
+// block = (tap, 32 channels); warp w walks output rows w, w+8, ...; lane = channel (coalesced 128-byte reads of dE)
+__global__ void __launch_bounds__(256) head_bwd_w5_kernel(const float* __restrict__ dE, const float* __restrict__ wl, int S, int C, float* __restrict__ dw5,
+                                                          int accumulate) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane, tap = blockIdx.y;
   const int kh = tap >> 2, kw = tap & 3;
   const int n = S - 3;
   float s = 0.f;
-  for (int oh = 0; oh < n; ++oh)
-    for (int ow = 0; ow < n; ++ow) s = fmaf(__ldg(dE + ((size_t)(oh + kh) * S + (ow + kw)) * C + c), __ldg(wl + oh * n + ow), s);
-  float* dst = dw5 + (size_t)c * 16 + tap;
-  *dst = accumulate ? *dst + s : s;
+  if (c < C) {
+    for (int oh = warp; oh < n; oh += 8)
+      for (int ow = 0; ow < n; ++ow) s = fmaf(__ldg(dE + ((size_t)(oh + kh) * S + (ow + kw)) * C + c), __ldg(wl + oh * n + ow), s);
+  }
+  red[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][lane];
+    float* dst = dw5 + (size_t)c * 16 + tap;
+    *dst = accumulate ? *dst + t : t;
+  }
 }
 
 // dWl[oh*n+ow] = sum_{c,kh,kw} dE[oh+kh][ow+kw][c] * W5[c][kh][kw];   block per output.
@@ -579,7 +600,7 @@ int b200_wgrad_c1(const void* z, int B, int H, int W, int C, int ldz, const floa
   else
     wgrad_c1_kernel<128><<<nblk, 256, smem, stream>>>((const __nv_bfloat16*)z, B, H, W, ldz, g, gmul, partial);
   B200_CHECK_LAUNCH();
-  partial_sum_kernel<<<(C * 16 + 255) / 256, 256, 0, stream>>>(partial, nblk, C * 16, dw, accumulate);
+  partial_sum_kernel<<<(C * 16 + 31) / 32, 256, 0, stream>>>(partial, nblk, C * 16, dw, accumulate);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -628,7 +649,7 @@ int b200_head_bwd_params(const float* dlin, const void* a, int B, int S, int C, 
   const int n = S * S * C;
   head_bwd_dE_kernel<<<(n / 8 + 255) / 256, 256, 0, stream>>>(dlin, (const __nv_bfloat16*)a, n, B, dE);
   B200_CHECK_LAUNCH();
-  head_bwd_w5_kernel<<<(16 * C + 127) / 128, 128, 0, stream>>>(dE, wl, S, C, dw5, accumulate);
+  head_bwd_w5_kernel<<<dim3((C + 31) / 32, 16), 256, 0, stream>>>(dE, wl, S, C, dw5, accumulate);
   B200_CHECK_LAUNCH();
   const int nn = (S - 3) * (S - 3);
   head_bwd_wl_kernel<<<nn + 1, 256, 0, stream>>>(dE, w5, dlin, B, S, C, dwl, dbias, accumulate);

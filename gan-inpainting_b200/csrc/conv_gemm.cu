@@ -43,6 +43,8 @@ struct EpiBwd {
   uint32_t seed;
   int col0;
   int Cy;                  // channels of y
+  float* dz32;             // optional: dz is ALSO the input of a BatchNorm backward -> stored unrounded, fp32 [pixel][Cy] (then the
+                           // bf16 output keeps only the unfused columns); null: dz replaces the fused columns of the bf16 output
 };
 
 struct IGemmParams {
@@ -67,6 +69,8 @@ struct IGemmParams {
   int num_tiles;         // work items of the persistent tile loop
   // every divisor on the single-thread producer / issuer paths is a power of two: shifts instead of integer division
   int tw_sh, th_sh, tiles_w_sh, tiles_h_sh, ck_sh, cpt_sh;
+  int stat_parity;       // 2: the per-quadrant statistics buffer is double buffered over tiles; 1: single + a second barrier per tile
+  int off_acc, off_ss, off_tile, tile_bytes;  // byte offsets of the epilogue's shared-memory regions behind the barriers (host-sized per variant)
   int kpb;               // 64-wide k-blocks per pipeline stage (2 for narrow N tiles: halves the per-stage barrier overhead
                          // of the single issuing thread, which otherwise exceeds the MMA time of a 128 x 64 x 64 block)
   float* stats;          // optional (fprop modes): per-CTA column sums of the stored bf16 outputs,
@@ -79,10 +83,7 @@ constexpr int kNumSMs = 148;
 constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quadrant, alternating 32-column chunks
 constexpr int kThreads = 64 + 32 * kEpiWarps;      // warp 0 = TMA, warp 1 = MMA, warps 2.. = epilogue
 constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 bf16 (K-major) or 2 x (64 px x 64 ch) (MN-major)
-constexpr int kStatSmemBytes = 2 * 4 * 2 * 256 * 4;  // [tile parity][TMEM quadrant][sum|sumsq][column]
-constexpr int kStatAccBytes = 2 * 1024 * 4;          // per-CTA running [sum|sumsq][Cout <= 1024]
-constexpr int kScaleShiftBytes = 2 * 512 * 4;        // forward BatchNorm scale / shift of the fused backward epilogue
-constexpr int kStatTileBytes = 2 * 2048;             // per epilogue warp: 32 rows x 32 bf16 of dz (and of y), 16-byte chunks swizzled
+constexpr int kStatTileBytes = 4096 + 2048;           // per epilogue warp: 32 x 32 fp32 of dz + 32 x 32 bf16 of y (forward: 32 x 32 bf16 only)
 
 // Epilogue variants (compile-time: the per-element code has no branches and each variant is a small kernel)
 enum { ACT_BWD_NONE = 0, ACT_BWD_LEAKY = 1, ACT_BWD_RELU = 2 };
@@ -186,6 +187,40 @@ __device__ __forceinline__ void tile_column_sums(uint8_t* wbuf, const uint32_t (
     }
 }
 
+// Same for the fused backward: dz rows are fp32 (unrounded, exactly what the BatchNorm apply pass will read), y rows bf16.
+// lane (cq, rg) reads 4 columns (chunk cq) of rows rg, rg+4, ..., rg+28; two shuffle stages fold the 4 row groups.
+// s[k] / q[k] = sum over the 32 rows of dz and dz*y for column 4*(lane & 7) + k.
+__device__ __forceinline__ void tile_column_sums_f32(uint8_t* wbuf, const uint32_t (&v)[32], const uint32_t (&yw)[16], int lane, float (&s)[4], float (&q)[4]) {
+  uint4* rowz = reinterpret_cast<uint4*>(wbuf + lane * 128);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) rowz[j ^ (lane & 7)] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  const int sw = (lane >> 1) & 3;
+  uint4* rowy = reinterpret_cast<uint4*>(wbuf + 4096 + lane * 64);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) rowy[j ^ sw] = make_uint4(yw[4 * j], yw[4 * j + 1], yw[4 * j + 2], yw[4 * j + 3]);
+  __syncwarp();
+  const int cq = lane & 7, rg = lane >> 3;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) s[k] = q[k] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = rg + 4 * i;
+    const float4 d = *reinterpret_cast<const float4*>(wbuf + row * 128 + ((cq ^ (row & 7)) * 16));
+    const uint2 yy = *reinterpret_cast<const uint2*>(wbuf + 4096 + row * 64 + (((cq >> 1) ^ ((row >> 1) & 3)) * 16) + (cq & 1) * 8);
+    const float2 y0 = unpack_bf16x2(yy.x), y1 = unpack_bf16x2(yy.y);
+    s[0] += d.x, s[1] += d.y, s[2] += d.z, s[3] += d.w;
+    q[0] = fmaf(d.x, y0.x, q[0]), q[1] = fmaf(d.y, y0.y, q[1]), q[2] = fmaf(d.z, y1.x, q[2]), q[3] = fmaf(d.w, y1.y, q[3]);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int h = 8; h <= 16; h <<= 1)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      s[k] += __shfl_xor_sync(0xffffffffu, s[k], h);
+      q[k] += __shfl_xor_sync(0xffffffffu, q[k], h);
+    }
+}
+
 template <class E>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const IGemmParams p) {
@@ -198,10 +233,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* tmem_full_bar = empty_bar + p.stages;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
   uint32_t* tmem_ptr_smem = (uint32_t*)(tmem_empty_bar + 2);
-  float* stat_smem = (float*)(tmem_ptr_smem + 4);   // kStatSmemBytes + kStatAccBytes, only touched when p.stats
-  float* stat_acc = stat_smem + kStatSmemBytes / 4;
-  float* bn_ss = stat_acc + kStatAccBytes / 4;      // interleaved (scale, shift)[Cy <= 512]
-  uint8_t* stat_tile = (uint8_t*)(bn_ss + kScaleShiftBytes / 4);  // [epilogue warp][kStatTileBytes]
+  uint8_t* epi_smem = (uint8_t*)(tmem_ptr_smem + 4);
+  float* stat_smem = (float*)epi_smem;                        // [parity][TMEM quadrant][sum | sumsq][BN]
+  float* stat_acc = (float*)(epi_smem + p.off_acc);           // per-CTA running [sum | sumsq][Cout]
+  float* bn_ss = (float*)(epi_smem + p.off_ss);               // interleaved (scale, shift)[Cy]
+  uint8_t* stat_tile = epi_smem + p.off_tile;                 // [epilogue warp][tile_bytes]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -333,7 +369,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
     }
-    uint8_t* wbuf = stat_tile + (warp - 2) * kStatTileBytes;
+    uint8_t* wbuf = stat_tile + (warp - 2) * p.tile_bytes;
     int lt = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++lt) {
       const TileCoord c = decode_tile(p, t);
@@ -365,7 +401,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         __nv_bfloat16* dst = (__nv_bfloat16*)p.out + pix * p.ldc + c.n0;
         const bool valid = (b < p.B);
-        float* st = stat_smem + ((lt & 1) * 4 + quad) * 512;
+        const int sp = (p.stat_parity == 2) ? (lt & 1) : 0;
+        float* st = stat_smem + (sp * 4 + quad) * 2 * p.BN;
         // fused activation backward: this row's slice of the forward tensor y (and of the skip gradient) is fetched one
         // 32-channel chunk ahead — the first chunk while the tile's MMAs are still running
         uint4 ynext[4], gnext[4];
@@ -434,22 +471,43 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
           for (int j = 0; j < 16; ++j) o[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
           if (valid) {
+            if (E::BWD && E::STATS && fused && p.bwd.dz32 != nullptr) {
+              float* d32 = p.bwd.dz32 + pix * p.bwd.Cy + cb;
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) *reinterpret_cast<uint4*>(dst + cc + 2 * j) = make_uint4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(d32 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) *reinterpret_cast<uint4*>(dst + cc + 2 * j) = make_uint4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+            }
           }
-          if (E::STATS) {
-            // per-channel sums of the values as stored (masked rows and unfused columns count as zero)
-            if (!valid || (E::BWD && !fused)) {
+          if (E::STATS && E::BWD) {
+            // (sum dz, sum dz*y) of the unrounded dz; masked rows and unfused columns count as zero
+            if (!valid || !fused) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = 0u;
+            }
+            float cs[4], cq[4];
+            tile_column_sums_f32(wbuf, v, yw, lane, cs, cq);
+            if (lane < 8) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                st[cc + lane * 4 + k] = cs[k];
+                st[p.BN + cc + lane * 4 + k] = cq[k];
+              }
+            }
+          } else if (E::STATS) {
+            // per-channel sums of the values as stored (masked rows count as zero)
+            if (!valid) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) o[j] = 0u;
             }
             float cs[8], cq[8];
-            tile_column_sums<E::BWD>(wbuf, o, yw, lane, cs, cq);
+            tile_column_sums<false>(wbuf, o, yw, lane, cs, cq);
             if (lane < 4) {
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
                 st[cc + lane * 8 + k] = cs[k];
-                st[256 + cc + lane * 8 + k] = cq[k];
+                st[p.BN + cc + lane * 8 + k] = cq[k];
               }
             }
           }
@@ -459,12 +517,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
         if (E::STATS) {
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // all epilogue warps
-          const float* sb = stat_smem + (lt & 1) * 4 * 512;
+          const float* sb = stat_smem + sp * 4 * 2 * p.BN;
+          const int qs = 2 * p.BN;  // quadrant stride
           for (int e = et; e < 2 * p.BN; e += kEpiThreads) {  // element (k, n0 + col) is always owned by the same thread
             const int k = e >= p.BN, col = e - k * p.BN;
-            const float a = (sb[0 * 512 + k * 256 + col] + sb[1 * 512 + k * 256 + col]) + (sb[2 * 512 + k * 256 + col] + sb[3 * 512 + k * 256 + col]);
+            const float a = (sb[e] + sb[qs + e]) + (sb[2 * qs + e] + sb[3 * qs + e]);
             stat_acc[k * p.Cout + c.n0 + col] += a;
           }
+          if (p.stat_parity == 1) asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // before the next tile rewrites the buffer
         }
       }
     }
@@ -600,9 +660,26 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, IGemmParams& p, cu
   p.kpb = (p.mode != MODE_WGRAD && p.BN <= 128 && p.kb_per_tile % 2 == 0) ? 2 : 1;
   const int stage_bytes = p.kpb * (kATileBytes + p.BN * 128);
   const bool has_stats = p.stats != nullptr, has_bwd = p.bwd.y != nullptr;
-  // shared memory behind the pipeline stages: barriers, the statistics buffers, and for the fused backward the BatchNorm
-  // coefficients; the per-warp transpose tiles only when statistics are reduced
-  const int extra = 1024 + 256 + kStatSmemBytes + kStatAccBytes + kScaleShiftBytes + (has_stats ? kEpiWarps * kStatTileBytes : 0);
+  // shared memory behind the pipeline stages, sized per epilogue variant: barriers, the per-quadrant statistics buffer
+  // (double buffered over tiles unless that would cost a pipeline stage), the per-CTA running sums, the BatchNorm
+  // coefficients of the fused backward, and the per-warp transpose tiles
+  const int tile_bytes = !has_stats ? 0 : (has_bwd ? kStatTileBytes : 2048);
+  auto layout = [&](int parity) {
+    int off = has_stats ? parity * 4 * 2 * p.BN * 4 : 0;
+    p.stat_parity = parity;
+    p.off_acc = off;
+    off += has_stats ? 2 * p.Cout * 4 : 0;
+    p.off_ss = off;
+    off += (has_bwd && p.bwd.scale) ? 2 * p.bwd.Cy * 4 : 0;
+    off = (off + 15) & ~15;
+    p.off_tile = off;
+    p.tile_bytes = tile_bytes;
+    off += kEpiWarps * tile_bytes;
+    return 1024 + 256 + off;
+  };
+  int extra = layout(2);
+  if (has_stats && (227 * 1024 - layout(1)) / stage_bytes > (227 * 1024 - extra) / stage_bytes) extra = layout(1);
+  else extra = layout(2);
   if (p.stages <= 0) {
     p.stages = (227 * 1024 - extra) / stage_bytes;
     if (p.stages > 8) p.stages = 8;
@@ -668,6 +745,7 @@ struct b200_epi_bwd {
   unsigned seed;
   int col0;
   int Cy;
+  void* dz32;
 };
 
 static int set_bwd(IGemmParams& p, const b200_epi_bwd* e, int Cout, const char* who) {
@@ -690,6 +768,7 @@ static int set_bwd(IGemmParams& p, const b200_epi_bwd* e, int Cout, const char* 
   p.bwd.seed = e->seed;
   p.bwd.col0 = e->col0;
   p.bwd.Cy = e->Cy;
+  p.bwd.dz32 = (float*)e->dz32;
   return B200_OK;
 }
 

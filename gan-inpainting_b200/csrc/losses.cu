@@ -104,12 +104,15 @@ __global__ void __launch_bounds__(256) recon_reduce_kernel(int kind, const float
 
 // out[0] = loss, out[1] = denominator as float, out[2..3] = exact (mask != 0) pixel count (LocalLoss) or N as two int words
 __global__ void recon_finalize_kernel(int kind, const float* __restrict__ partial, int nblk, double n, float eps, float* __restrict__ out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  // one warp: lane-strided fp64 partial sums in a fixed order, then a fixed shuffle tree (deterministic)
   double s = 0.0, c = 0.0;
-  for (int b = 0; b < nblk; ++b) {
+  for (int b = threadIdx.x; b < nblk; b += 32) {
     s += (double)partial[2 * b];
     c += (double)partial[2 * b + 1];  // per-block counts are exact integers < 2^24
   }
+  s = warp_sum_d(s);
+  c = warp_sum_d(c);
+  if (threadIdx.x != 0) return;
   double loss;
   if (kind == RECON_L1) {
     loss = s / n;
@@ -245,9 +248,10 @@ __global__ void __launch_bounds__(256) gstep_seed_kernel(const SeedParams p, flo
 }
 
 __global__ void scalar_sum_kernel(const float* __restrict__ partial, int nblk, float* __restrict__ out, int accumulate) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double s = 0.0;
-  for (int b = 0; b < nblk; ++b) s += (double)partial[b];
+  for (int b = threadIdx.x; b < nblk; b += 32) s += (double)partial[b];
+  s = warp_sum_d(s);
+  if (threadIdx.x != 0) return;
   *out = accumulate ? *out + (float)s : (float)s;
 }
 

@@ -349,6 +349,32 @@ __global__ void __launch_bounds__(kFinThreads) bn_bwd_finalize_kernel(const floa
   coef[2 * C + c] = (float)(-a * db / count + a * rstd * mean * dg / count);
 }
 
+// dy = kdz*dz + ky*y + k0 with dz read as fp32 (the unrounded output of a fused GEMM epilogue)
+__global__ void __launch_bounds__(256) bn_bwd_apply_f32_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ dz, int lddz, int offdz, int P,
+                                                               int C, int cshift, const float* __restrict__ coef, __nv_bfloat16* __restrict__ dy) {
+  const unsigned total = (unsigned)P << cshift;
+  const unsigned cmask = (1u << cshift) - 1u;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const size_t pix = idx >> cshift;
+    const int c0 = (int)(idx & cmask) * 8;
+    float yv[8];
+    load8(y + pix * C + c0, yv);
+    const float4 z0 = __ldg(reinterpret_cast<const float4*>(dz + pix * lddz + offdz + c0)), z1 = __ldg(reinterpret_cast<const float4*>(dz + pix * lddz + offdz + c0 + 4));
+    const float* k = coef + c0;
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(k)), a1 = __ldg(reinterpret_cast<const float4*>(k + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(k + C)), b1 = __ldg(reinterpret_cast<const float4*>(k + C + 4));
+    const float4 d0 = __ldg(reinterpret_cast<const float4*>(k + 2 * C)), d1 = __ldg(reinterpret_cast<const float4*>(k + 2 * C + 4));
+    const float zz[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+    const float ka[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float kb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const float kd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = fmaf(ka[i], zz[i], fmaf(kb[i], yv[i], kd[i]));
+    *reinterpret_cast<uint4*>(dy + pix * C + c0) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+  }
+}
+
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdParams p) {
   const unsigned total = (unsigned)p.P << p.cshift;
   const unsigned cmask = (1u << p.cshift) - 1u;
@@ -358,9 +384,15 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdParams p) {
     float yv[8], dz[8];
     compute_dz(p, pix, c0, yv, dz);
     if (p.coef) {
-      const float* k = p.coef;
+      const float* k = p.coef + c0;
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(k)), a1 = __ldg(reinterpret_cast<const float4*>(k + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(k + p.C)), b1 = __ldg(reinterpret_cast<const float4*>(k + p.C + 4));
+      const float4 d0 = __ldg(reinterpret_cast<const float4*>(k + 2 * p.C)), d1 = __ldg(reinterpret_cast<const float4*>(k + 2 * p.C + 4));
+      const float ka[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float kb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const float kd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) dz[i] = fmaf(__ldg(k + c0 + i), dz[i], fmaf(__ldg(k + p.C + c0 + i), yv[i], __ldg(k + 2 * p.C + c0 + i)));
+      for (int i = 0; i < 8; ++i) dz[i] = fmaf(ka[i], dz[i], fmaf(kb[i], yv[i], kd[i]));
     }
     uint4 o = make_uint4(pack_bf16x2(dz[0], dz[1]), pack_bf16x2(dz[2], dz[3]), pack_bf16x2(dz[4], dz[5]), pack_bf16x2(dz[6], dz[7]));
     *reinterpret_cast<uint4*>(p.dy + pix * p.C + c0) = o;
@@ -493,8 +525,9 @@ int b200_bn_act_bwd(const void* y, long long P, int C, const float* stats /*[4][
 // BatchNorm backward when the producing data-gradient GEMM already wrote dz (gradient w.r.t. the BatchNorm output) and the
 // per-CTA partial rows (sum dz, sum dz*y) — b200_conv_s2_gemm / b200_convt_s2_gemm with a b200_epi_bwd.  Element (row, k, c) of
 // the partials is partial[row * row_stride + k * k_stride + c].  Produces dgamma / dbeta and dy = gradient w.r.t. the conv output y.
-int b200_bn_bwd_fused(const void* y, long long P, int C, const float* stats, const float* gamma, const void* dz, int lddz, int offdz, const float* partial,
-                      int rows, int row_stride, int k_stride, float* coef, float* dgamma, float* dbeta, int accumulate, void* dy, cudaStream_t stream) {
+int b200_bn_bwd_fused(const void* y, long long P, int C, const float* stats, const float* gamma, const void* dz, int lddz, int offdz, int dz_is_f32,
+                      const float* partial, int rows, int row_stride, int k_stride, float* coef, float* dgamma, float* dbeta, int accumulate, void* dy,
+                      cudaStream_t stream) {
   const int cs = chunk_shift(C);
   if (cs < 0 || !stats || lddz % 8 || offdz % 8 || rows < 1 || P * (C >> 3) >= (1LL << 31)) {
     b200_set_error("bn_bwd_fused: C must be a power of two in [8, 2048]; strides / offsets multiples of 8");
@@ -503,6 +536,12 @@ int b200_bn_bwd_fused(const void* y, long long P, int C, const float* stats, con
   bn_bwd_finalize_kernel<<<(C + 31) / 32, kFinThreads, 0, stream>>>(partial, rows, C, (double)P, stats, gamma, dgamma, dbeta, accumulate, coef, row_stride,
                                                                     k_stride);
   B200_CHECK_LAUNCH();
+  if (dz_is_f32) {
+    bn_bwd_apply_f32_kernel<<<grid_for(P * (C >> 3), 256), 256, 0, stream>>>((const __nv_bfloat16*)y, (const float*)dz, lddz, offdz, (int)P, C, cs, coef,
+                                                                              (__nv_bfloat16*)dy);
+    B200_CHECK_LAUNCH();
+    return B200_OK;
+  }
   BwdParams p{};
   p.y = (const __nv_bfloat16*)y;
   p.P = (int)P;

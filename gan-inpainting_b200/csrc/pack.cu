@@ -44,6 +44,50 @@ __global__ void __launch_bounds__(256) pack_phase_kernel(const float* __restrict
   }
 }
 
+// Both operand layouts of every 4x4 layer of a network in ONE launch (the fused optimizers rewrite all master weights at once).
+// table[l] = {src fp32 [D0][D1][16], gather bf16 [D0][16*D1], phase bf16 [4][D1][4*D0], D0, D1, first tile}; tile = 16 d0 x 32 d1.
+struct PackEntry {
+  const float* src;
+  __nv_bfloat16* gather;
+  __nv_bfloat16* phase;
+  long long D0, D1, tile0;
+};
+
+__global__ void __launch_bounds__(256) pack_all_kernel(const PackEntry* __restrict__ table, int nlayers) {
+  constexpr int TS = 33, RS = 16 * TS + 1;  // tile[d0][tap][d1] with padded strides (shared-memory banks)
+  __shared__ float tile[16 * RS];
+  int l = 0;
+  while (l + 1 < nlayers && (long long)blockIdx.x >= table[l + 1].tile0) ++l;
+  const PackEntry e = table[l];
+  const int D0 = (int)e.D0, D1 = (int)e.D1;
+  const int t_in = blockIdx.x - (int)e.tile0;
+  const int tiles_d1 = D1 / 32;
+  const int d0_0 = (t_in / tiles_d1) * 16, d1_0 = (t_in % tiles_d1) * 32;
+  // read: 16 rows of 512 contiguous floats (32 d1 x 16 taps)
+  for (int i = threadIdx.x; i < 16 * 128; i += 256) {
+    const int r = i >> 7, c4 = i & 127;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(e.src + ((size_t)(d0_0 + r) * D1 + d1_0) * 16) + c4);
+    const int d1 = c4 >> 2, t0 = (c4 & 3) * 4;
+    float* dst = tile + r * RS + t0 * TS + d1;
+    dst[0] = v.x, dst[TS] = v.y, dst[2 * TS] = v.z, dst[3 * TS] = v.w;
+  }
+  __syncthreads();
+  // gather layout: dst[d0][t * D1 + d1], 32 consecutive d1 per (d0, t): thread = (d0, t, d1 pair)
+  for (int i = threadIdx.x; i < 16 * 16 * 16; i += 256) {
+    const int dp = i & 15, t = (i >> 4) & 15, r = i >> 8;
+    const float* src = tile + r * RS + t * TS + 2 * dp;
+    *reinterpret_cast<uint32_t*>(e.gather + (size_t)(d0_0 + r) * 16 * D1 + (size_t)t * D1 + d1_0 + 2 * dp) = pack_bf16x2(src[0], src[1]);
+  }
+  // phase layout: dst[ph][d1][ab * D0 + d0], tap(ph, ab) = (3 - p - 2a) * 4 + (3 - q - 2b): thread = (ph*4+ab, d1, d0 pair)
+  for (int i = threadIdx.x; i < 16 * 32 * 8; i += 256) {
+    const int rp = i & 7, n = (i >> 3) & 31, pt = i >> 8;
+    const int ph = pt >> 2, ab = pt & 3;
+    const int tap = (3 - (ph >> 1) - 2 * (ab >> 1)) * 4 + (3 - (ph & 1) - 2 * (ab & 1));
+    const float* src = tile + (2 * rp) * RS + tap * TS + n;
+    *reinterpret_cast<uint32_t*>(e.phase + ((size_t)ph * D1 + d1_0 + n) * (4 * (size_t)D0) + (size_t)ab * D0 + d0_0 + 2 * rp) = pack_bf16x2(src[0], src[RS]);
+  }
+}
+
 // partial fp32 [splits][Cs][16*Cl] (column = t*Cl + cl)  ->  grad fp32 [Cs][Cl][16]
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int Cs, int Cl, float* __restrict__ grad,
                                                            int accumulate) {
@@ -80,6 +124,18 @@ int b200_pack_phase(const float* w, int D0, int D1, void* out, cudaStream_t stre
     return B200_ERR_ARG;
   }
   pack_phase_kernel<<<dim3(D0 / 16, D1 / 16), 256, 0, stream>>>(w, D0, D1, (__nv_bfloat16*)out);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+// table: device array of nlayers entries {src, gather, phase, D0, D1, tile0} (int64 each; D0 % 16 == 0, D1 % 32 == 0,
+// tile0 = number of 16 x 32 tiles of the layers before); total_tiles = sum over layers of (D0/16)*(D1/32).
+int b200_pack_all(const void* table, int nlayers, int total_tiles, cudaStream_t stream) {
+  if (nlayers < 1 || total_tiles < 1) {
+    b200_set_error("pack_all: empty table");
+    return B200_ERR_ARG;
+  }
+  pack_all_kernel<<<total_tiles, 256, 0, stream>>>((const PackEntry*)table, nlayers);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

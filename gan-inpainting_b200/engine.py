@@ -112,10 +112,12 @@ class ActBwd:
 
     def __init__(self, y, Cy, stats, act, col0=0, g2=None, ldg2=0, offg2=0, dropout=False, seed=0, scratch: Optional["Scratch"] = None):
         self.Cy, self.col0, self.has_bn = Cy, col0, stats is not None
+        # a BatchNorm backward follows: dz is kept unrounded (fp32) for it — one bf16 rounding less per layer of the gradient chain
+        self.dz32 = _empty(tuple(y.shape[:-1]) + (Cy,), f32, y.device) if (self.has_bn and scratch is not None) else None
         self.keep = (y, stats, g2)  # the raw pointers below must outlive the launch
         self.c = _lib.EpiBwd(y.data_ptr(), Cy, stats.data_ptr() + 2 * Cy * 4 if stats is not None else None,
                              stats.data_ptr() + 3 * Cy * 4 if stats is not None else None, act, g2.data_ptr() if g2 is not None else None, ldg2, offg2,
-                             int(dropout), int(seed) & 0xFFFFFFFF, col0, Cy)
+                             int(dropout), int(seed) & 0xFFFFFFFF, col0, Cy, self.dz32.data_ptr() if self.dz32 is not None else None)
         self.scratch = scratch
         self.rows = ctypes.c_int(0)
 
@@ -129,8 +131,12 @@ def bn_bwd_fused(y, C, stats, gamma, dz, lddz, offdz, epi: ActBwd, cout_total, d
     P = y.numel() // C
     dy = _empty(y.shape, bf16, y.device)
     part = ctypes.c_void_p(scratch.bn_partial.data_ptr() + epi.col0 * 4)
-    call("b200_bn_bwd_fused", ptr(y), P, C, ptr(stats), ptr(gamma), ptr(dz), lddz, offdz, part, epi.rows.value, 2 * cout_total, cout_total, ptr(scratch.coef),
-         ptr(dgamma), ptr(dbeta), int(accumulate), ptr(dy), stream())
+    if epi.dz32 is not None:  # the epilogue left dz unrounded in its own fp32 tensor
+        dz, lddz, offdz, f32in = epi.dz32, C, 0, 1
+    else:
+        f32in = 0
+    call("b200_bn_bwd_fused", ptr(y), P, C, ptr(stats), ptr(gamma), ptr(dz), lddz, offdz, f32in, part, epi.rows.value, 2 * cout_total, cout_total,
+         ptr(scratch.coef), ptr(dgamma), ptr(dbeta), int(accumulate), ptr(dy), stream())
     return dy
 
 
@@ -229,6 +235,29 @@ class _Packed:
         call("b200_pack_phase", ptr(w), d0, d1, ptr(self.phase), stream())
 
 
+class PackTable:
+    """Device-side work list of ``b200_pack_all``: refreshes the bf16 operand copies of all 4x4 layers of a network with one launch.
+    Rebuilt only when a weight or packed buffer moves (its addresses are baked into the table)."""
+
+    def __init__(self):
+        self.key, self.table, self.n, self.tiles = None, None, 0, 0
+
+    def refresh(self, pairs):
+        """pairs: [(fp32 weight [D0, D1, 4, 4], _Packed)]"""
+        key = tuple((w.data_ptr(), pk.gather.data_ptr(), pk.phase.data_ptr()) for w, pk in pairs)
+        if key != self.key:
+            rows, tile0 = [], 0
+            for w, pk in pairs:
+                d0, d1 = w.shape[:2]
+                if d0 % 16 or d1 % 32:
+                    raise _lib.B200Error("pack_all: channel counts must be multiples of 16 / 32")
+                rows.append([w.data_ptr(), pk.gather.data_ptr(), pk.phase.data_ptr(), d0, d1, tile0])
+                tile0 += (d0 // 16) * (d1 // 32)
+            self.table = torch.tensor(rows, dtype=torch.int64, device=pairs[0][0].device)
+            self.key, self.n, self.tiles = key, len(rows), tile0
+        call("b200_pack_all", ptr(self.table), self.n, self.tiles, stream())
+
+
 # ================================================================================================
 # generator
 # ================================================================================================
@@ -248,6 +277,7 @@ class GeneratorEngine:
         self.dropout_levels = set(dropout_levels)
         self.packed_d: Dict[int, _Packed] = {}
         self.packed_u: Dict[int, _Packed] = {}
+        self._pack_table = PackTable()
         self._versions = None
         self.calls = 0
         for l in range(2, self.N + 1):
@@ -263,12 +293,13 @@ class GeneratorEngine:
         ver = (_lib.WEIGHT_EPOCH,) + tuple((w._version, w.data_ptr()) for w in ws)
         if not force and ver == self._versions:
             return
+        pairs = []
         for l in range(2, self.N + 1):
             if l not in self.packed_d or self.packed_d[l].gather.device != self.dc[l - 1].weight.device:
                 self.packed_d[l] = _Packed(self.dc[l - 1].weight)
                 self.packed_u[l] = _Packed(self.uc[l - 1].weight)
-            self.packed_d[l].refresh(self.dc[l - 1].weight.data)
-            self.packed_u[l].refresh(self.uc[l - 1].weight.data)
+            pairs += [(self.dc[l - 1].weight.data, self.packed_d[l]), (self.uc[l - 1].weight.data, self.packed_u[l])]
+        self._pack_table.refresh(pairs)
         self._versions = ver
 
     # ---- forward
@@ -339,7 +370,7 @@ class GeneratorEngine:
         return bn_eval(C, bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, bn.eps, y.device)
 
     # ---- backward
-    def backward(self, c: GenCtx, dpre: torch.Tensor, grads: Dict[object, torch.Tensor], accumulate: bool = False, on_ready=None):
+    def backward(self, c: GenCtx, dpre: torch.Tensor, grads: Dict[object, torch.Tensor], accumulate: bool = False, on_ready=None, trace=None):
         """dpre: fp32 [B,1,R,R] gradient w.r.t. the pre-tanh output.  ``grads`` maps each parameter (by
         ``id`` of the nn.Parameter) to the fp32 tensor its gradient is written / accumulated into; the bias of
         the last layer is handled by the caller (gstep_seed reduces it)."""
@@ -381,6 +412,8 @@ class GeneratorEngine:
             else:
                 epi = ActBwd(c.y[N], w[N], None, ACT_RELU)
             dcats[l] = conv_s2(dyu, self.packed_u[l].gather, cin, epi=epi)
+            if trace is not None:
+                trace[f"dyu{l}"], trace[f"dcat{l}"] = dyu, dcats[l]
         # ---- encoder dN .. d2: dcats[N] already is the gradient w.r.t. y[N]
         dy = dcats[N]
         for l in range(N, 1, -1):
@@ -396,6 +429,8 @@ class GeneratorEngine:
             else:
                 epi = ActBwd(c.a[1], w[1], None, ACT_LEAKY, g2=dcats[1], ldg2=2 * w[1], offg2=0)
             dz = convt_s2(dy, w[l], w[l], self.packed_d[l].phase, w[l - 1], epi=epi)
+            if trace is not None:
+                trace[f"dy{l}"], trace[f"dz{l - 1}"] = dy, dz
         # ---- d1
         call("b200_wgrad_c1", ptr(dz), B, side(1), side(1), w[1], w[1], ptr(c.x), None, ptr(sc.c1_partial), ptr(G(self.dc[0].weight)), acc, stream())
         done(self.dc[0].weight)
@@ -413,6 +448,7 @@ class DiscriminatorEngine:
         """convs: the four k4s2p1 nn.Conv2d; norms: [None, bn2, bn3, bn4]; head_conv: Conv2d(512,1,4,1,0); head_linear: nn.Linear."""
         self.convs, self.norms, self.hc, self.hl = convs, norms, head_conv, head_linear
         self.packed: Dict[int, _Packed] = {}
+        self._pack_table = PackTable()
         self._versions = None
         self.E = None
         self.calls = 0
@@ -422,10 +458,12 @@ class DiscriminatorEngine:
         ver = (_lib.WEIGHT_EPOCH,) + tuple((w._version, w.data_ptr()) for w in ws)
         if not force and ver == self._versions:
             return
+        pairs = []
         for i in range(1, 4):
             if i not in self.packed or self.packed[i].gather.device != self.convs[i].weight.device:
                 self.packed[i] = _Packed(self.convs[i].weight)
-            self.packed[i].refresh(self.convs[i].weight.data)
+            pairs.append((self.convs[i].weight.data, self.packed[i]))
+        self._pack_table.refresh(pairs)
         n = int(round(self.hl.in_features ** 0.5))
         S, C = n + 3, self.hc.in_channels
         if self.E is None or self.E.numel() != S * S * C:

@@ -79,6 +79,7 @@ typedef struct b200_epi_bwd {
   unsigned seed;
   int col0;
   int Cy;             /* channels of y; col0 + Cy == Cout */
+  void* dz32;         /* optional (with stats): dz stored unrounded as fp32 [pixel][Cy] for b200_bn_bwd_fused instead of bf16 in place */
 } b200_epi_bwd;
 
 int b200_igemm_stat_rows(void);
@@ -109,6 +110,9 @@ int b200_debug_tma_probe(const void* x, int B, int H, int W, int C, int kind, in
  * ------------------------------------------------------------------------------------------------------------------ */
 int b200_pack_gather(const float* w, int D0, int D1, void* out /* bf16 [D0][16*D1] */, b200_stream_t stream);
 int b200_pack_phase(const float* w, int D0, int D1, void* out /* bf16 [4][D1][4*D0] */, b200_stream_t stream);
+/* both layouts of every 4x4 layer of a network in one launch: table = device array of nlayers x {src, gather, phase, D0, D1, tile0}
+ * (six 64-bit words each; D0 % 16 == 0, D1 % 32 == 0; tile0 = number of 16x32 tiles of the layers before) */
+int b200_pack_all(const void* table, int nlayers, int total_tiles, b200_stream_t stream);
 /* grad[cs][cl][kh][kw] (+)= sum_s partial[s][cs][(kh*4+kw)*Cl + cl]   (deterministic split reduction) */
 int b200_wgrad_reduce(const float* partial, int splits, int Cs, int Cl, float* grad, int accumulate, b200_stream_t stream);
 
@@ -137,10 +141,11 @@ int b200_bn_act_bwd(const void* y, long long P, int C, const float* stats, const
                     int ldg2, int offg2, int dropout, unsigned seed, void* partial, float* coef, float* dgamma, float* dbeta, int accumulate, void* dy,
                     b200_stream_t stream);
 
-/* BatchNorm backward after a data-gradient GEMM with a b200_epi_bwd epilogue: dz [P][C] (pixel stride lddz, channel offset offdz)
+/* BatchNorm backward after a data-gradient GEMM with a b200_epi_bwd epilogue: dz [P][C] (bf16, or fp32 when dz_is_f32; pixel stride lddz, channel offset offdz)
  * and the GEMM's partial rows (element (row, k, c) at partial[row*row_stride + k*k_stride + c]) -> dgamma, dbeta, dy. */
-int b200_bn_bwd_fused(const void* y, long long P, int C, const float* stats, const float* gamma, const void* dz, int lddz, int offdz, const float* partial,
-                      int rows, int row_stride, int k_stride, float* coef, float* dgamma, float* dbeta, int accumulate, void* dy, b200_stream_t stream);
+int b200_bn_bwd_fused(const void* y, long long P, int C, const float* stats, const float* gamma, const void* dz, int lddz, int offdz, int dz_is_f32,
+                      const float* partial, int rows, int row_stride, int k_stride, float* coef, float* dgamma, float* dbeta, int accumulate, void* dy,
+                      b200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * layers with one channel on one side + the discriminator head (csrc/conv_direct.cu)

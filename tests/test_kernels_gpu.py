@@ -42,6 +42,18 @@ def _packs(w):
     return p
 
 
+def test_pack_all_equals_single_layer_packs(dev):
+    """One-launch repack of all layers (after the fused optimizer step) is bit-identical to the per-layer kernels."""
+    eng = _eng()
+    torch.manual_seed(5)
+    ws = [torch.randn(d0, d1, 4, 4, device=dev) for d0, d1 in ((128, 64), (64, 256), (512, 512), (1024, 512), (16, 32))]
+    ref = [_packs(w) for w in ws]
+    new = [eng._Packed(w) for w in ws]
+    eng.PackTable().refresh(list(zip(ws, new)))
+    for a, b in zip(ref, new):
+        assert torch.equal(a.gather, b.gather) and torch.equal(a.phase, b.phase)
+
+
 @pytest.mark.parametrize("B,H,Cin,Cout", [(2, 16, 64, 128), (3, 8, 256, 512), (8, 2, 512, 512), (2, 64, 64, 128), (5, 4, 512, 512), (48, 32, 128, 256)])
 def test_conv_s2_fprop(dev, B, H, Cin, Cout):
     eng = _eng()
@@ -107,7 +119,8 @@ def _bn_bwd_reference(y, dz, gamma, eps=1e-5):
     return dgamma, dbeta, gamma * rstd * (dz - dbeta / n - xhat * dgamma / n)
 
 
-@pytest.mark.parametrize("B,H,Cin,Cy,skip,norm", [(3, 8, 128, 64, True, True), (20, 16, 128, 64, False, True), (2, 4, 512, 256, True, False)])
+@pytest.mark.parametrize("B,H,Cin,Cy,skip,norm", [(3, 8, 128, 64, True, True), (20, 16, 128, 64, False, True), (2, 4, 512, 256, True, False),
+                                                      (8, 32, 256, 128, True, True), (8, 64, 128, 64, True, False)])
 def test_fused_leaky_bn_backward_in_conv_dgrad_epilogue(dev, B, H, Cin, Cy, skip, norm):
     """Conv2d data gradient (4-phase kernel) whose epilogue applies the LeakyReLU backward of the layer below, merges the skip-connection
     gradient and reduces (sum dz, sum dz*y) for that layer's BatchNorm; b200_bn_bwd_fused finishes dgamma / dbeta / dy."""
@@ -122,11 +135,13 @@ def test_fused_leaky_bn_backward_in_conv_dgrad_epilogue(dev, B, H, Cin, Cy, skip
     g2 = bf(torch.randn(B, 2 * H, 2 * H, 2 * Cy, device=dev)) if skip else None
     epi = eng.ActBwd(y, Cy, st, 1, g2=g2, ldg2=2 * Cy, offg2=0, scratch=sc)
     dz = eng.convt_s2(dyin, Cin, Cin, _packs(w).phase, Cy, epi=epi)
+    if norm:
+        dz = epi.dz32  # a BatchNorm backward follows: the epilogue keeps dz unrounded in its own fp32 tensor
     g = nhwc(torch.nn.grad.conv2d_input((B, Cy, 2 * H, 2 * H), bf(w).float(), nchw(dyin.float()), stride=2, padding=1))
     yf = y.float()
     z = yf * st[2] + st[3] if norm else yf
     ref = torch.where(z > 0, g + (g2[..., :Cy].float() if skip else 0.0), 0.2 * g)
-    assert rel(dz, ref) < BF16_TOL
+    assert rel(dz, ref) < (1e-5 if norm else BF16_TOL)
     if norm:
         dgamma, dbeta = torch.zeros(Cy, device=dev), torch.zeros(Cy, device=dev)
         dy = eng.bn_bwd_fused(y, Cy, st, gamma, dz, Cy, 0, epi, Cy, dgamma, dbeta, False, sc)
@@ -165,10 +180,11 @@ def test_fused_relu_dropout_bn_backward_in_convt_dgrad_epilogue(dev, B, H, Cy, C
         keep = torch.empty_like(y)
         eng.bn_act(ones, Cy, None, 0, keep, Cy, 0, dropout=True, seed=seed)
         ref = ref * keep.float()
-    assert rel(out[..., col0:], ref) < BF16_TOL
+    fused_out = epi.dz32 if norm else out[..., col0:]
+    assert rel(fused_out, ref) < (1e-5 if norm else BF16_TOL)
     if norm:
         dgamma, dbeta = torch.zeros(Cy, device=dev), torch.zeros(Cy, device=dev)
-        dz = out[..., col0:].float().reshape(-1, Cy)
+        dz = fused_out.reshape(-1, Cy)
         dy = eng.bn_bwd_fused(y, Cy, st, gamma, out, Cout, col0, epi, Cout, dgamma, dbeta, False, sc)
         rg, rb, rdy = _bn_bwd_reference(yf.reshape(-1, Cy), dz, gamma)
         assert rel(dgamma, rg) < 1e-3 and rel(dbeta, rb) < 1e-3
