@@ -22,101 +22,139 @@ enum { ACT_NONE = 0, ACT_LEAKY = 1, ACT_RELU = 2, ACT_TANH = 3 };
 // ------------------------------------------------------------------------------------------------
 // conv_c1_fwd: y[pix][c] = sum_t patch[pix][t] * w[c][t]  (t = kh*4+kw, K = 16) on the warp-level bf16 MMA
 // (m16n8k16), fp32 operands carried as bf16 hi+lo pairs (3 MMAs: hi*hi + lo*hi + hi*lo), fp32 accumulation.
-// Block = 256 output pixels (TOH x TOW); the (2*TOH+2) x (2*TOW+2) input window is staged in shared memory (zero
-// halo, mask multiply applied once).  Warp = two 16-pixel row segments; the n-columns of the MMA are permuted so that
-// a lane ends up with C/4 CONSECUTIVE channels of a pixel and stores them with 128-bit stores (a quad covers the pixel's
-// whole channel vector).  The kernel is bound by the bf16 output stream (2*C bytes per pixel).
+// Persistent blocks walk 256-pixel output tiles (TOH x TOW); the (2*TOH+2) x (2*TOW+2) input window (and the window of the
+// optional multiplier, the local discriminator's mask) of the NEXT tile is fetched with zero-filling cp.async while the
+// current one is multiplied.  Warp = two 16-pixel row segments; the n-columns of the MMA are permuted so that a lane ends up
+// with consecutive channels of a pixel and stores them with 128-bit stores (a quad covers 64 contiguous bytes).  The weight
+// fragments live in shared memory.  The kernel is bound by the bf16 output stream (2*C bytes per pixel).
 // ------------------------------------------------------------------------------------------------
 constexpr int kXsFloats = 34 * 68;  // covers 18 x 68 (8 x 32 tile) and 34 x 36 (16 x 16 tile)
 
 template <int C>
-__global__ void __launch_bounds__(256) conv_c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ xmul, int H, int W, int tow_shift,
-                                                          const float* __restrict__ w, int act, __nv_bfloat16* __restrict__ y,
-                                                          __nv_bfloat16* __restrict__ y2, int ld2, int off2) {
+__global__ void __launch_bounds__(256, 3) conv_c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ xmul, int B, int H, int W, int tow_shift,
+                                                             const float* __restrict__ w, int act, __nv_bfloat16* __restrict__ y,
+                                                             __nv_bfloat16* __restrict__ y2, int ld2, int off2) {
   constexpr int NT = C / 8;   // n-tiles
   constexpr int CPL = C / 4;  // consecutive channels per lane
-  __shared__ __align__(16) float xs[kXsFloats];
+  __shared__ __align__(16) float xs[2][kXsFloats];
+  __shared__ __align__(16) float xm[2][kXsFloats];
+  __shared__ uint32_t bsm[NT * 4 * 32];  // [n-tile][hi b0, hi b1, lo b0, lo b1][lane]
   const int TOW = 1 << tow_shift, TOH = 256 >> tow_shift;
   const int Ho = H >> 1, Wo = W >> 1;
   const int tiles_w = Wo >> tow_shift, tiles_h = Ho / TOH;
-  const int tw_i = blockIdx.x % tiles_w;
-  const int th_i = (blockIdx.x / tiles_w) % tiles_h;
-  const int b = blockIdx.x / (tiles_w * tiles_h);
-  const int oh0 = th_i * TOH, ow0 = tw_i << tow_shift;
+  const int ntiles = B * tiles_w * tiles_h;
   const int rows = 2 * TOH + 2, cols = 2 * TOW + 2, xstride = 2 * TOW + 4;
-  const int ih0 = 2 * oh0 - 1, iw0 = 2 * ow0 - 1;
-  const float* xb = x + (size_t)b * H * W;
-  const float* mb = xmul ? xmul + (size_t)b * H * W : nullptr;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int r = warp; r < rows; r += 8) {
-    const int ih = ih0 + r;
-    const bool rok = ih >= 0 && ih < H;
-    for (int cI = lane; cI < cols; cI += 32) {
-      const int iw = iw0 + cI;
-      float v = 0.f;
-      if (rok && iw >= 0 && iw < W) {
-        v = __ldg(xb + (size_t)ih * W + iw);
-        if (mb) v *= __ldg(mb + (size_t)ih * W + iw);
-      }
-      xs[r * xstride + cI] = v;
-    }
-  }
   const int g = lane >> 2, q = lane & 3;
-  // B fragments: MMA column g of n-tile j carries channel (g>>1)*CPL + 2j + (g&1)
-  uint32_t bhi[NT][2], blo[NT][2];
-#pragma unroll
-  for (int j = 0; j < NT; ++j) {
-    const float* wc = w + (size_t)((g >> 1) * CPL + 2 * j + (g & 1)) * 16 + 2 * q;
+
+  auto stage = [&](int tile, int buf) {
+    const int tw_i = tile % tiles_w;
+    const int th_i = (tile / tiles_w) % tiles_h;
+    const int b = tile / (tiles_w * tiles_h);
+    const int ih0 = 2 * (th_i * TOH) - 1, iw0 = 2 * (tw_i << tow_shift) - 1;
+    const float* xb = x + (size_t)b * H * W;
+    const float* mb = xmul ? xmul + (size_t)b * H * W : nullptr;
+    for (int e = threadIdx.x; e < rows * cols; e += 256) {
+      const int r = e / cols, cI = e - r * cols;
+      const int ih = ih0 + r, iw = iw0 + cI;
+      const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
+      const size_t off = ok ? (size_t)ih * W + iw : 0;
+      cp_async4_zfill(&xs[buf][r * xstride + cI], xb + off, ok);
+      if (mb) cp_async4_zfill(&xm[buf][r * xstride + cI], mb + off, ok);
+    }
+    cp_async_commit();
+  };
+  if ((int)blockIdx.x < ntiles) stage(blockIdx.x, 0);
+
+  // B fragments -> shared memory: MMA column g of n-tile j carries channel (g>>1)*CPL + 2j + (g&1)
+  for (int e = threadIdx.x; e < NT * 32; e += 256) {
+    const int j = e >> 5, l = e & 31;
+    const int gg = l >> 2, qq = l & 3;
+    const float* wc = w + (size_t)((gg >> 1) * CPL + 2 * j + (gg & 1)) * 16 + 2 * qq;
     const float2 w0 = __ldg(reinterpret_cast<const float2*>(wc));
     const float2 w1 = __ldg(reinterpret_cast<const float2*>(wc + 8));
-    split_bf16x2(w0.x, w0.y, bhi[j][0], blo[j][0]);
-    split_bf16x2(w1.x, w1.y, bhi[j][1], blo[j][1]);
+    uint32_t h0, l0, h1, l1;
+    split_bf16x2(w0.x, w0.y, h0, l0);
+    split_bf16x2(w1.x, w1.y, h1, l1);
+    bsm[(j * 4 + 0) * 32 + l] = h0;
+    bsm[(j * 4 + 1) * 32 + l] = h1;
+    bsm[(j * 4 + 2) * 32 + l] = l0;
+    bsm[(j * 4 + 3) * 32 + l] = l1;
   }
-  __syncthreads();
 
   const int kh = q >> 1, kw = (q & 1) * 2;  // taps 2q, 2q+1 (and +8: kh + 2)
+  int buf = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+    const int next = tile + gridDim.x;
+    if (next < ntiles) {
+      stage(next, buf ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const int tw_i = tile % tiles_w;
+    const int th_i = (tile / tiles_w) % tiles_h;
+    const int b = tile / (tiles_w * tiles_h);
+    const int oh0 = th_i * TOH, ow0 = tw_i << tow_shift;
+    const float* xw = xs[buf];
+    const float* mw = xm[buf];
 #pragma unroll 1
-  for (int m = 0; m < 2; ++m) {
-    const int mt = warp * 2 + m;  // 16 m-tiles of 16 pixels per block
-    const int ol_h = (mt * 16) >> tow_shift, ol_w0 = (mt * 16) & (TOW - 1);
-    uint32_t ahi[4], alo[4];
+    for (int m = 0; m < 2; ++m) {
+      const int mt = warp * 2 + m;  // 16 m-tiles of 16 pixels per block
+      const int ol_h = (mt * 16) >> tow_shift, ol_w0 = (mt * 16) & (TOW - 1);
+      uint32_t ahi[4], alo[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int pw = ol_w0 + g + (i & 1) * 8, kk = kh + (i >> 1) * 2;
-      const float2 v = *reinterpret_cast<const float2*>(xs + (2 * ol_h + kk) * xstride + 2 * pw + kw);
-      split_bf16x2(v.x, v.y, ahi[i], alo[i]);
-    }
-    float acc[NT][4];
+      for (int i = 0; i < 4; ++i) {
+        const int pw = ol_w0 + g + (i & 1) * 8, kk = kh + (i >> 1) * 2;
+        const int o = (2 * ol_h + kk) * xstride + 2 * pw + kw;
+        float2 v = *reinterpret_cast<const float2*>(xw + o);
+        if (xmul) {
+          const float2 mm = *reinterpret_cast<const float2*>(mw + o);
+          v.x *= mm.x;
+          v.y *= mm.y;
+        }
+        split_bf16x2(v.x, v.y, ahi[i], alo[i]);
+      }
+      const size_t pix0 = ((size_t)b * Ho + (oh0 + ol_h)) * Wo + (ow0 + ol_w0 + g);
 #pragma unroll
-    for (int j = 0; j < NT; ++j) {
-      acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-      mma_bf16_16816(acc[j], alo, bhi[j][0], bhi[j][1]);
-      mma_bf16_16816(acc[j], ahi, blo[j][0], blo[j][1]);
-      mma_bf16_16816(acc[j], ahi, bhi[j][0], bhi[j][1]);
-    }
-    if (act == ACT_LEAKY) {
+      for (int hn = 0; hn < NT; hn += 8) {  // 8 n-tiles (16 consecutive channels per lane) at a time: 32 accumulators
+        float acc[8][4];
 #pragma unroll
-      for (int j = 0; j < NT; ++j)
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t* bj = bsm + ((hn + j) * 4) * 32 + lane;
+          const uint32_t h0 = bj[0], h1 = bj[32], l0 = bj[64], l1 = bj[96];
+          acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+          mma_bf16_16816(acc[j], alo, h0, h1);
+          mma_bf16_16816(acc[j], ahi, l0, l1);
+          mma_bf16_16816(acc[j], ahi, h0, h1);
+        }
+        if (act == ACT_LEAKY) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc[j][i] = acc[j][i] > 0.f ? acc[j][i] : 0.2f * acc[j][i];
-    }
+          for (int j = 0; j < 8; ++j)
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {  // pixel g (d0,d1) and pixel g+8 (d2,d3)
-      const size_t pix = ((size_t)b * Ho + (oh0 + ol_h)) * Wo + (ow0 + ol_w0 + g + half * 8);
-      uint32_t o[NT];
+            for (int i = 0; i < 4; ++i) acc[j][i] = acc[j][i] > 0.f ? acc[j][i] : 0.2f * acc[j][i];
+        }
 #pragma unroll
-      for (int j = 0; j < NT; ++j) o[j] = pack_bf16x2(acc[j][2 * half], acc[j][2 * half + 1]);
-      uint4* dst = reinterpret_cast<uint4*>(y + pix * C + q * CPL);
+        for (int half = 0; half < 2; ++half) {  // pixel g (d0,d1) and pixel g+8 (d2,d3)
+          const size_t pix = pix0 + half * 8;
+          uint32_t o[8];
 #pragma unroll
-      for (int j = 0; j < NT; j += 4) dst[j >> 2] = make_uint4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-      if (y2) {  // relu copy into the decoder's concat buffer (skip connection)
+          for (int j = 0; j < 8; ++j) o[j] = pack_bf16x2(acc[j][2 * half], acc[j][2 * half + 1]);
+          uint4* dst = reinterpret_cast<uint4*>(y + pix * C + q * CPL + 2 * hn);
+          dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+          dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+          if (y2) {  // relu copy into the decoder's concat buffer (skip connection)
 #pragma unroll
-        for (int j = 0; j < NT; ++j) o[j] = pack_bf16x2(fmaxf(acc[j][2 * half], 0.f), fmaxf(acc[j][2 * half + 1], 0.f));
-        uint4* dst2 = reinterpret_cast<uint4*>(y2 + pix * ld2 + off2 + q * CPL);
-#pragma unroll
-        for (int j = 0; j < NT; j += 4) dst2[j >> 2] = make_uint4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+            for (int j = 0; j < 8; ++j) o[j] = pack_bf16x2(fmaxf(acc[j][2 * half], 0.f), fmaxf(acc[j][2 * half + 1], 0.f));
+            uint4* dst2 = reinterpret_cast<uint4*>(y2 + pix * ld2 + off2 + q * CPL + 2 * hn);
+            dst2[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            dst2[1] = make_uint4(o[4], o[5], o[6], o[7]);
+          }
+        }
       }
     }
+    __syncthreads();  // everyone is done with `buf` before the next iteration's prefetch overwrites it
   }
 }
 
@@ -133,7 +171,7 @@ constexpr int kTT = 16;             // tile side (input pixels)
 constexpr int kTH = kTT + 2;        // with halo
 
 template <int C>
-__global__ void __launch_bounds__(256) convt_c1_fwd_kernel(const __nv_bfloat16* __restrict__ z, int B, int H, int W, int ldz, const float* __restrict__ w,
+__global__ void __launch_bounds__(256, 2) convt_c1_fwd_kernel(const __nv_bfloat16* __restrict__ z, int B, int H, int W, int ldz, const float* __restrict__ w,
                                                            const float* __restrict__ bias, int act, const float* __restrict__ base,
                                                            const float* __restrict__ mul, float* __restrict__ y, float* __restrict__ comp) {
   constexpr int NG = C / 32;  // 32-channel groups
@@ -146,18 +184,23 @@ __global__ void __launch_bounds__(256) convt_c1_fwd_kernel(const __nv_bfloat16* 
   const int b = blockIdx.x / (tiles_w * tiles_h);
   const int i0 = th_i * kTT - 1, j0 = tw_i * kTT - 1;  // image coordinates of the halo origin
 
-  // B fragments [group][k-step][n-tile]: b0 = {w[ch][tap], w[ch+1][tap]}, b1 = {w[ch+2][tap], w[ch+3][tap]}, tap = nt*8 + g
-  uint32_t bhi[NG][2][2][2], blo[NG][2][2][2];
-#pragma unroll
-  for (int gi = 0; gi < NG; ++gi)
-#pragma unroll
-    for (int s = 0; s < 2; ++s)
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
-        const float* wc = w + (size_t)(gi * 32 + q * 8 + 4 * s) * 16 + nt * 8 + g;
-        split_bf16x2(__ldg(wc), __ldg(wc + 16), bhi[gi][s][nt][0], blo[gi][s][nt][0]);
-        split_bf16x2(__ldg(wc + 32), __ldg(wc + 48), bhi[gi][s][nt][1], blo[gi][s][nt][1]);
-      }
+  // B fragments [group][k-step][n-tile] in shared memory (per lane): b0 = {w[ch][tap], w[ch+1][tap]}, b1 = {w[ch+2][tap], w[ch+3][tap]},
+  // tap = nt*8 + g; entry ((gi*2 + s)*2 + nt)*4 + {hi b0, hi b1, lo b0, lo b1}
+  __shared__ uint32_t bsm[NG * 16 * 32];
+  for (int e = threadIdx.x; e < NG * 4 * 32; e += 256) {
+    const int l = e & 31, grp = e >> 5;  // grp = (gi*2 + s)*2 + nt
+    const int nt = grp & 1, sk = (grp >> 1) & 1, gi = grp >> 2;
+    const int gg = l >> 2, qq = l & 3;
+    const float* wc = w + (size_t)(gi * 32 + qq * 8 + 4 * sk) * 16 + nt * 8 + gg;
+    uint32_t h0, l0, h1, l1;
+    split_bf16x2(__ldg(wc), __ldg(wc + 16), h0, l0);
+    split_bf16x2(__ldg(wc + 32), __ldg(wc + 48), h1, l1);
+    bsm[(grp * 4 + 0) * 32 + l] = h0;
+    bsm[(grp * 4 + 1) * 32 + l] = h1;
+    bsm[(grp * 4 + 2) * 32 + l] = l0;
+    bsm[(grp * 4 + 3) * 32 + l] = l1;
+  }
+  __syncthreads();
 
   constexpr int npix = kTH * kTH;
   constexpr int nmt = (npix + 15) / 16;
@@ -194,8 +237,9 @@ __global__ void __launch_bounds__(256) convt_c1_fwd_kernel(const __nv_bfloat16* 
         const uint32_t a[4] = {pa[2 * s], pb[2 * s], pa[2 * s + 1], pb[2 * s + 1]};
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {
-          mma_bf16_16816(acc[nt], a, blo[gi][s][nt][0], blo[gi][s][nt][1]);
-          mma_bf16_16816(acc[nt], a, bhi[gi][s][nt][0], bhi[gi][s][nt][1]);
+          const uint32_t* bj = bsm + (((gi * 2 + s) * 2 + nt) * 4) * 32 + lane;
+          mma_bf16_16816(acc[nt], a, bj[64], bj[96]);
+          mma_bf16_16816(acc[nt], a, bj[0], bj[32]);
         }
       }
     }
@@ -555,11 +599,12 @@ int b200_conv_c1_fwd(const float* x, const float* xmul, int B, int H, int W, con
     b200_set_error("conv_c1_fwd: C must be 64/128; output must tile by 8x32 (or 16x16); concat stride / offset multiples of 8");
     return B200_ERR_ARG;
   }
-  const int grid = B * (Ho / TOH) * (Wo / TOW);
+  const int ntiles = B * (Ho / TOH) * (Wo / TOW);
+  const int grid = ntiles < 148 * 3 ? ntiles : 148 * 3;  // persistent: three resident blocks per SM
   if (C == 64)
-    conv_c1_fwd_kernel<64><<<grid, 256, 0, stream>>>(x, xmul, H, W, tow_shift, w, act, (__nv_bfloat16*)y, (__nv_bfloat16*)y2, ld2, off2);
+    conv_c1_fwd_kernel<64><<<grid, 256, 0, stream>>>(x, xmul, B, H, W, tow_shift, w, act, (__nv_bfloat16*)y, (__nv_bfloat16*)y2, ld2, off2);
   else
-    conv_c1_fwd_kernel<128><<<grid, 256, 0, stream>>>(x, xmul, H, W, tow_shift, w, act, (__nv_bfloat16*)y, (__nv_bfloat16*)y2, ld2, off2);
+    conv_c1_fwd_kernel<128><<<grid, 256, 0, stream>>>(x, xmul, B, H, W, tow_shift, w, act, (__nv_bfloat16*)y, (__nv_bfloat16*)y2, ld2, off2);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
