@@ -26,8 +26,9 @@ U = c_uint32
 # name -> argtypes (all of these return an int status; 0 == OK).  Order == include/b200_inpaint.h.
 SIGNATURES = {
     # ---- tcgen05 implicit-GEMM convolutions (csrc/conv_gemm.cu)
-    "b200_conv_s2_gemm": [P, I, I, I, I, P, I, P, I, I, I, P, POINTER(c_int), P, S],
-    "b200_convt_s2_gemm": [P, I, I, I, I, I, P, I, P, I, I, I, P, POINTER(c_int), P, S],
+    "b200_conv_s2_gemm": [P, I, I, I, I, P, I, P, I, I, I, P, POINTER(c_int), P, I, P, S],
+    "b200_convt_s2_gemm": [P, I, I, I, I, I, P, I, P, I, I, I, P, POINTER(c_int), P, I, P, S],
+    "b200_splitk_reduce": [P, I, L, I, P, I, S],
     "b200_wgrad_gemm": [P, I, I, I, I, I, P, I, P, POINTER(c_int), I, I, S],
     "b200_debug_tma_probe": [P, I, I, I, I, I, I, I, I, I, I, I, I, I, P, S],
     # ---- weight layouts (csrc/pack.cu)

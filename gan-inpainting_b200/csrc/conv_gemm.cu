@@ -69,6 +69,10 @@ struct IGemmParams {
   int num_tiles;         // work items of the persistent tile loop
   // every divisor on the single-thread producer / issuer paths is a power of two: shifts instead of integer division
   int tw_sh, th_sh, tiles_w_sh, tiles_h_sh, ck_sh, cpt_sh;
+  int ksplit;            // fprop modes: K is split over `ksplit` work items per output tile (small-M layers: few output tiles,
+                         // long K); each writes an fp32 partial tile to `partial` [ksplit][pixels][Cout], b200_splitk_reduce sums them
+  float* partial;
+  long long P_total;     // pixels of the output tensor
   int stat_parity;       // 2: the per-quadrant statistics buffer is double buffered over tiles; 1: single + a second barrier per tile
   int off_acc, off_ss, off_tile, tile_bytes;  // byte offsets of the epilogue's shared-memory regions behind the barriers (host-sized per variant)
   int kpb;               // 64-wide k-blocks per pipeline stage (2 for narrow N tiles: halves the per-stage barrier overhead
@@ -94,14 +98,14 @@ struct Epi {
 };
 
 struct TileCoord {
-  int w0, h0, b0, n0, m0, phase, kb_begin, kb_count, row;
+  int w0, h0, b0, n0, m0, phase, kb_begin, kb_count, row, ks;
 };
 
 // Work item t of the persistent loop.  fprop/dgrad: the pixel tile is the slow index so the CTAs running at the same
 // time read the same activations (4 phases x n_tiles) out of L2; wgrad: the pixel range (split) is the slow index.
 __device__ __forceinline__ TileCoord decode_tile(const IGemmParams& p, int t) {
   TileCoord c;
-  c.w0 = c.h0 = c.b0 = c.m0 = c.phase = 0;
+  c.w0 = c.h0 = c.b0 = c.m0 = c.phase = c.ks = 0;
   c.kb_begin = 0;
   c.kb_count = p.kb_per_tile;
   if (p.mode == MODE_WGRAD) {
@@ -115,6 +119,12 @@ __device__ __forceinline__ TileCoord decode_tile(const IGemmParams& p, int t) {
     c.row = split;
   } else {
     const int per_pt = p.phases * p.n_tiles;
+    if (p.ksplit > 1) {  // the K split is the slowest index: concurrently running CTAs still share their activation tiles
+      const int per_split = p.num_ptiles * per_pt;
+      c.ks = t / per_split;
+      t -= c.ks * per_split;
+      c.kb_begin = c.ks * p.kb_per_tile;
+    }
     const int pt = t / per_pt, r = t - pt * per_pt;
     c.phase = r / p.n_tiles;
     c.n0 = (r - c.phase * p.n_tiles) * p.BN;
@@ -470,7 +480,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           uint32_t o[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) o[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-          if (valid) {
+          if (!E::BWD && !E::STATS && p.ksplit > 1) {
+            if (valid) {  // split-K: fp32 partial tile
+              float* d32 = p.partial + ((size_t)c.ks * p.P_total + pix) * p.Cout + c.n0 + cc;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(d32 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+          } else if (valid) {
             if (E::BWD && E::STATS && fused && p.bwd.dz32 != nullptr) {
               float* d32 = p.bwd.dz32 + pix * p.bwd.Cy + cb;
 #pragma unroll
@@ -541,6 +557,24 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// out[pix][c] (bf16, pixel stride ldy) = sum_ks partial[ks][pix][c]
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int ksplit, long long P, int C, __nv_bfloat16* __restrict__ out,
+                                                            int ldy) {
+  const long long chunks = P * (C >> 3);
+  const long long stride = (long long)P * C;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < chunks; idx += (long long)gridDim.x * blockDim.x) {
+    const long long pix = idx / (C >> 3);
+    const int c0 = (int)(idx - pix * (C >> 3)) * 8;
+    const float* src = partial + pix * C + c0;
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < ksplit; ++k) {
+      const float4 u = __ldg(reinterpret_cast<const float4*>(src + k * stride)), w = __ldg(reinterpret_cast<const float4*>(src + k * stride + 4));
+      a[0] += u.x, a[1] += u.y, a[2] += u.z, a[3] += u.w, a[4] += w.x, a[5] += w.y, a[6] += w.z, a[7] += w.w;
+    }
+    *reinterpret_cast<uint4*>(out + pix * ldy + c0) = make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]), pack_bf16x2(a[6], a[7]));
   }
 }
 
@@ -776,8 +810,25 @@ int b200_igemm_stat_rows(void) { return kNumSMs; }
 
 // y[B,H/2,W/2,ldy] (bf16) = conv4x4/s2/p1(x[B,H,W,Cin] bf16, wpk[Cout][16*Cin] bf16 with k = (kh*4+kw)*Cin + ci)
 // stats (optional): [b200_igemm_stat_rows()][2][Cout] fp32 per-CTA column sums / sums of squares of y; *stat_rows = rows written.
+static int set_split(IGemmParams& p, int ksplit, float* partial, long long P_total, const char* who) {
+  p.ksplit = 1;
+  p.partial = nullptr;
+  p.P_total = P_total;
+  if (ksplit <= 1) return B200_OK;
+  if (!partial || p.stats || p.bwd.y || p.kb_total % ksplit || ((p.kb_total / ksplit) & 1)) {
+    b200_set_error((std::string(who) + ": split-K needs a partial buffer, no fused epilogue, and an even number of k-blocks per split").c_str());
+    return B200_ERR_ARG;
+  }
+  p.ksplit = ksplit;
+  p.partial = partial;
+  p.kb_per_tile = p.kb_total / ksplit;
+  p.num_tiles *= ksplit;
+  return B200_OK;
+}
+
+// ksplit > 1: K is split; `partial` (ksplit * pixels * Cout floats) receives fp32 partial sums and y is NOT written — finish with b200_splitk_reduce.
 int b200_conv_s2_gemm(const void* x, int B, int H, int W, int Cin, const void* wpk, int Cout, void* y, int ldy, int bn_hint, int stages, float* stats,
-                      int* stat_rows, const b200_epi_bwd* bwd, cudaStream_t stream) {
+                      int* stat_rows, const b200_epi_bwd* bwd, int ksplit, float* partial, cudaStream_t stream) {
   if (!is_pow2(H) || !is_pow2(W) || H < 2 || W < 2 || Cin % 64 || Cout % 32 || ldy % 8 || B < 1) {
     b200_set_error("conv_s2_gemm: unsupported shape");
     return B200_ERR_ARG;
@@ -811,6 +862,7 @@ int b200_conv_s2_gemm(const void* x, int B, int H, int W, int Cin, const void* w
   p.stats = stats;
   int rc;
   if ((rc = set_bwd(p, bwd, Cout, "conv_s2_gemm"))) return rc;
+  if ((rc = set_split(p, ksplit, partial, (long long)B * p.Hs * p.Ws, "conv_s2_gemm"))) return rc;
   CUtensorMap ta, tb;
   if ((rc = map_nhwc_parity(&ta, x, B, H, W, Cin, p.tw, p.th, p.nb))) return rc;
   if ((rc = map_weights(&tb, wpk, Cout, 16 * Cin, p.BN))) return rc;
@@ -819,7 +871,7 @@ int b200_conv_s2_gemm(const void* x, int B, int H, int W, int Cin, const void* w
 
 // y[B,2Hi,2Wi,ldy] (bf16) = convT4x4/s2/p1(z[B,Hi,Wi,Cin] (pixel stride ldz), wpk[4 phases][Cout][4*Cin]); stats as above.
 int b200_convt_s2_gemm(const void* z, int B, int Hi, int Wi, int Cin, int ldz, const void* wpk, int Cout, void* y, int ldy, int bn_hint, int stages,
-                       float* stats, int* stat_rows, const b200_epi_bwd* bwd, cudaStream_t stream) {
+                       float* stats, int* stat_rows, const b200_epi_bwd* bwd, int ksplit, float* partial, cudaStream_t stream) {
   if (!is_pow2(Hi) || !is_pow2(Wi) || Cin % 64 || Cout % 32 || ldy % 8 || ldz % 8 || B < 1) {
     b200_set_error("convt_s2_gemm: unsupported shape");
     return B200_ERR_ARG;
@@ -853,6 +905,7 @@ int b200_convt_s2_gemm(const void* z, int B, int Hi, int Wi, int Cin, int ldz, c
   p.stats = stats;
   int rc;
   if ((rc = set_bwd(p, bwd, Cout, "convt_s2_gemm"))) return rc;
+  if ((rc = set_split(p, ksplit, partial, (long long)B * 4 * Hi * Wi, "convt_s2_gemm"))) return rc;
   CUtensorMap ta, tb;
   if ((rc = map_nhwc(&ta, z, B, Hi, Wi, Cin, ldz, p.tw, p.th, p.nb))) return rc;
   if ((rc = map_weights(&tb, wpk, 4 * Cout, 4 * Cin, p.BN))) return rc;
@@ -901,11 +954,25 @@ int b200_wgrad_gemm(const void* S, int B, int Hs, int Ws, int Cs, int lds, const
   p.num_tiles = p.m_tiles * p.n_tiles * splits;
   p.stats = nullptr;
   p.bwd = EpiBwd{};
+  p.ksplit = 1;
+  p.partial = nullptr;
   CUtensorMap ta, tb;
   int rc;
   if ((rc = map_nhwc(&ta, S, B, Hs, Ws, Cs, lds, p.tw, p.th, p.nb))) return rc;
   if ((rc = map_nhwc_parity(&tb, L, B, 2 * Hs, 2 * Ws, Cl, p.tw, p.th, p.nb))) return rc;
   return launch(ta, tb, p, stream, nullptr);
+}
+
+int b200_splitk_reduce(const float* partial, int ksplit, long long P, int C, void* out, int ldy, cudaStream_t stream) {
+  if (ksplit < 1 || P < 1 || C % 8 || ldy % 8) {
+    b200_set_error("splitk_reduce: bad sizes");
+    return B200_ERR_ARG;
+  }
+  long long blocks = (P * (C >> 3) + 255) / 256;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  splitk_reduce_kernel<<<(int)blocks, 256, 0, stream>>>(partial, ksplit, P, C, (__nv_bfloat16*)out, ldy);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
 }
 
 // Debug: raw shared-memory image of one TMA box of the parity view (kind 0) or the plain view (kind 1).

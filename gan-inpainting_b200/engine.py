@@ -50,6 +50,7 @@ class Scratch:
         self.c1_partial = _empty(_lib.value("b200_wgrad_c1_blocks") * 128 * 16, f32, device)
         self.recon = _empty(_lib.value("b200_recon_scratch_floats"), f32, device)
         self.wgrad: Optional[torch.Tensor] = None
+        self.split: Optional[torch.Tensor] = None
 
     @classmethod
     def get(cls, device) -> "Scratch":
@@ -57,6 +58,11 @@ class Scratch:
         if idx not in cls._by_device:
             cls._by_device[idx] = Scratch(torch.device("cuda", idx))
         return cls._by_device[idx]
+
+    def split_buf(self, nfloats: int) -> torch.Tensor:
+        if self.split is None or self.split.numel() < nfloats:
+            self.split = _empty(nfloats, f32, self.device)
+        return self.split
 
     def wgrad_buf(self, nfloats: int) -> torch.Tensor:
         if self.wgrad is None or self.wgrad.numel() < nfloats:
@@ -75,6 +81,19 @@ def pick_bn(m_tiles: int, cout: int, phases: int = 1) -> int:
         if cout % bn == 0:
             return bn
     return cout
+
+
+def pick_ksplit(m_tiles: int, cout: int, phases: int, kb_total: int):
+    """K split of the innermost layers' fprop / dgrad GEMMs (a handful of 128-pixel tiles, K up to 8192): wide N tiles (least
+    operand traffic per flop) and enough K splits to occupy the SMs.  Returns (ksplit, bn); ksplit == 1: no split."""
+    bn = 256 if cout % 256 == 0 else (128 if cout % 128 == 0 else 64)
+    tiles = m_tiles * (cout // bn) * phases
+    if 2 * tiles > NUM_SMS or kb_total < 32:
+        return 1, 0
+    ks = 1
+    while tiles * ks * 2 <= NUM_SMS + tiles and kb_total % (ks * 2) == 0 and kb_total // (ks * 2) >= 8 and (kb_total // (ks * 2)) % 2 == 0:
+        ks *= 2
+    return (ks, bn) if ks > 1 else (1, 0)
 
 
 def _m_tiles(B: int, hs: int, ws: int, npix: int = 128) -> int:
@@ -96,8 +115,11 @@ class BnPlan:
         self.bn, self.scratch = bn, scratch
         self.rm, self.rv, self.nbt = (bn.running_mean, bn.running_var, bn.num_batches_tracked) if track else (None, None, None)
         self.rows = ctypes.c_int(0)
+        self.precomputed = None  # split-K layers: statistics from the standalone kernel
 
     def finalize(self, y, C):
+        if self.precomputed is not None:
+            return self.precomputed
         bn = self.bn
         stats = _empty((4, C), f32, y.device)
         call("b200_bn_finalize", ptr(self.scratch.bn_partial), self.rows.value, y.numel() // C, C, ptr(bn.weight.data), ptr(bn.bias.data), ptr(self.rm),
@@ -112,6 +134,8 @@ class ActBwd:
 
     def __init__(self, y, Cy, stats, act, col0=0, g2=None, ldg2=0, offg2=0, dropout=False, seed=0, scratch: Optional["Scratch"] = None):
         self.Cy, self.col0, self.has_bn = Cy, col0, stats is not None
+        self.y, self.stats, self.act, self.g2, self.ldg2, self.offg2, self.dropout, self.seed = y, stats, act, g2, ldg2, offg2, bool(dropout), int(seed)
+        self.raw = None  # split-K layers: the plain gradient, the activation / BatchNorm backward then runs as its own kernels
         # a BatchNorm backward follows: dz is kept unrounded (fp32) for it — one bf16 rounding less per layer of the gradient chain
         self.dz32 = _empty(tuple(y.shape[:-1]) + (Cy,), f32, y.device) if (self.has_bn and scratch is not None) else None
         self.keep = (y, stats, g2)  # the raw pointers below must outlive the launch
@@ -128,6 +152,9 @@ class ActBwd:
 
 def bn_bwd_fused(y, C, stats, gamma, dz, lddz, offdz, epi: ActBwd, cout_total, dgamma, dbeta, accumulate, scratch: "Scratch"):
     """Finish a BatchNorm backward whose dz and partial sums came out of a GEMM epilogue: dgamma / dbeta, and dy."""
+    if epi.raw is not None:  # the GEMM ran split-K without a fused epilogue
+        return bn_act_bwd(y, C, stats, gamma, epi.act, epi.raw, cout_total, epi.col0, epi.g2, epi.ldg2, epi.offg2, epi.dropout, epi.seed, dgamma, dbeta,
+                          accumulate, scratch)
     P = y.numel() // C
     dy = _empty(y.shape, bf16, y.device)
     part = ctypes.c_void_p(scratch.bn_partial.data_ptr() + epi.col0 * 4)
@@ -140,15 +167,39 @@ def bn_bwd_fused(y, C, stats, gamma, dz, lddz, offdz, epi: ActBwd, cout_total, d
     return dy
 
 
+def _split_epilogue(out, cout, plan, epi, sc):
+    """What the fused epilogue would have done, as separate kernels, after a split-K GEMM (tiny innermost layers)."""
+    if plan is not None:
+        bn = plan.bn
+        plan.precomputed = bn_stats(out, cout, bn.weight.data, bn.bias.data, plan.rm, plan.rv, plan.nbt, bn.momentum, bn.eps, sc)
+    if epi is not None:
+        if epi.has_bn:
+            epi.raw = out  # bn_bwd_fused finishes with the standalone BatchNorm backward
+        else:  # activation only (col0 == 0): return dz in place of the plain gradient
+            return bn_act_bwd(epi.y, epi.Cy, None, None, epi.act, out, cout, epi.col0, epi.g2, epi.ldg2, epi.offg2, False, 0, None, None, False, sc)
+    return out
+
+
 def conv_s2(x, wpk, cout, out=None, ldy=None, plan: Optional[BnPlan] = None, epi: Optional[ActBwd] = None):
     """x [B,H,W,Cin] bf16 -> [B,H/2,W/2,cout]; wpk [cout][16*Cin]."""
     B, H, W, Cin = x.shape
     if out is None:
         out = _empty((B, H // 2, W // 2, cout), bf16, x.device)
         ldy = cout
-    bn = pick_bn(_m_tiles(B, H // 2, W // 2), cout)
+    mt = _m_tiles(B, H // 2, W // 2)
+    # split-K pays only when nothing is fused into the epilogue (inference: eval-mode BatchNorm, no backward): in training the
+    # separate reduce + statistics / activation-backward kernels of these tiny layers cost what the faster GEMM saves (measured)
+    ks, bn = pick_ksplit(mt, cout, 1, 16 * (Cin // 64)) if (ldy == cout and plan is None and epi is None) else (1, 0)
+    if ks > 1:
+        sc = Scratch.get(x.device)
+        P = B * (H // 2) * (W // 2)
+        part = sc.split_buf(ks * P * cout)
+        call("b200_conv_s2_gemm", ptr(x), B, H, W, Cin, ptr(wpk), cout, ptr(out), ldy, bn, 0, None, None, None, ks, ptr(part), stream())
+        call("b200_splitk_reduce", ptr(part), ks, P, cout, ptr(out), ldy, stream())
+        return _split_epilogue(out, cout, plan, epi, sc)
+    bn = pick_bn(mt, cout)
     extra = epi.args() if epi is not None else (ptr(plan.scratch.bn_partial) if plan else None, ctypes.byref(plan.rows) if plan else None, None)
-    call("b200_conv_s2_gemm", ptr(x), B, H, W, Cin, ptr(wpk), cout, ptr(out), ldy, bn, 0, *extra, stream())
+    call("b200_conv_s2_gemm", ptr(x), B, H, W, Cin, ptr(wpk), cout, ptr(out), ldy, bn, 0, *extra, 1, None, stream())
     return out
 
 
@@ -156,9 +207,18 @@ def convt_s2(z, ldz, cin, wpk, cout, plan: Optional[BnPlan] = None, epi: Optiona
     """z [B,Hi,Wi,>=cin] (pixel stride ldz) -> [B,2Hi,2Wi,cout]; wpk [4][cout][4*cin]."""
     B, Hi, Wi = z.shape[:3]
     out = _empty((B, 2 * Hi, 2 * Wi, cout), bf16, z.device)
-    bn = pick_bn(_m_tiles(B, Hi, Wi), cout, phases=4)
+    mt = _m_tiles(B, Hi, Wi)
+    ks, bn = pick_ksplit(mt, cout, 4, 4 * (cin // 64)) if (plan is None and epi is None) else (1, 0)
+    if ks > 1:
+        sc = Scratch.get(z.device)
+        P = B * 4 * Hi * Wi
+        part = sc.split_buf(ks * P * cout)
+        call("b200_convt_s2_gemm", ptr(z), B, Hi, Wi, cin, ldz, ptr(wpk), cout, ptr(out), cout, bn, 0, None, None, None, ks, ptr(part), stream())
+        call("b200_splitk_reduce", ptr(part), ks, P, cout, ptr(out), cout, stream())
+        return _split_epilogue(out, cout, plan, epi, sc)
+    bn = pick_bn(mt, cout, phases=4)
     extra = epi.args() if epi is not None else (ptr(plan.scratch.bn_partial) if plan else None, ctypes.byref(plan.rows) if plan else None, None)
-    call("b200_convt_s2_gemm", ptr(z), B, Hi, Wi, cin, ldz, ptr(wpk), cout, ptr(out), cout, bn, 0, *extra, stream())
+    call("b200_convt_s2_gemm", ptr(z), B, Hi, Wi, cin, ldz, ptr(wpk), cout, ptr(out), cout, bn, 0, *extra, 1, None, stream())
     return out
 
 

@@ -25,6 +25,7 @@ from typing import Callable, Dict, Optional
 
 import torch
 
+from ..data import DevicePrefetcher
 from ..lib.models import networks
 from ..trainer import InpaintingTrainer
 
@@ -93,11 +94,12 @@ def run(state: dict, loaders: dict, title: str, recipe: str, recon: str, schedul
         ed = {"total": 0.0, "adv_real": 0.0, "adv_fake": 0.0, "update_count": 0}
         gh = {"avg_g": {n: 0.0 for n in g_names}, "avg_d": {n: 0.0 for n in d_names}}
         net_G.train()
-        for batch_idx, (ground, mask, _) in enumerate(train_loader):
+        # the next batch's host -> device copy overlaps this batch's kernels (the reference blocks on .to(device), wgan_l1.py:113-114)
+        for batch_idx, (ground, mask, _) in enumerate(DevicePrefetcher(train_loader, device)):
             if max_batches is not None and batch_idx >= max_batches:
                 break
             upd = schedule(batch_idx, g_iter)
-            tr.step(ground.to(device, non_blocking=True), mask.to(device, non_blocking=True), update_g=upd)
+            tr.step(ground, mask, update_g=upd)
             s = tr.read_scalars()
             d_iter += 1
             if upd:

@@ -84,13 +84,16 @@ typedef struct b200_epi_bwd {
 
 int b200_igemm_stat_rows(void);
 int b200_conv_s2_gemm(const void* x, int B, int H, int W, int Cin, const void* wpk, int Cout, void* y, int ldy, int bn_hint, int stages, float* stats,
-                      int* stat_rows, const b200_epi_bwd* bwd, b200_stream_t stream);
+                      int* stat_rows, const b200_epi_bwd* bwd, int ksplit, float* partial, b200_stream_t stream);
 
 /* nn.ConvTranspose2d(Cin, Cout, 4, 2, 1, bias=False) forward as 4 sub-pixel phases — networks.py:300-309 (u7..u2);
  * also the data gradient of nn.Conv2d.  z [B,Hi,Wi,*] with pixel stride ldz; wpk [4][Cout][4*Cin] from b200_pack_phase;
  * y [B,2Hi,2Wi,*] with pixel stride ldy. */
 int b200_convt_s2_gemm(const void* z, int B, int Hi, int Wi, int Cin, int ldz, const void* wpk, int Cout, void* y, int ldy, int bn_hint, int stages,
-                       float* stats, int* stat_rows, const b200_epi_bwd* bwd, b200_stream_t stream);
+                       float* stats, int* stat_rows, const b200_epi_bwd* bwd, int ksplit, float* partial, b200_stream_t stream);
+/* Split-K (the innermost layers: a handful of output tiles, K up to 8192): with ksplit > 1 the two entry points above write fp32
+ * partial tiles into `partial` [ksplit][pixels][Cout] (no fused epilogue, y untouched) and this kernel sums them into y (bf16). */
+int b200_splitk_reduce(const float* partial, int ksplit, long long P, int C, void* y, int ldy, b200_stream_t stream);
 
 /* Weight gradient of both layer kinds (autograd of the call sites above; wgan_l1.py:138,141,183):
  *   partial[s][cs][(kh*4+kw)*Cl + cl] = sum over the pixels of split s of S[b,i,j,cs] * L[b,2i+kh-1,2j+kw-1,cl]

@@ -191,6 +191,28 @@ def test_fused_relu_dropout_bn_backward_in_convt_dgrad_epilogue(dev, B, H, Cy, C
         assert rel(dy.reshape(-1, Cy), rdy) < BF16_TOL
 
 
+def test_split_k_small_layers(dev):
+    """Innermost layers (a few 128-pixel tiles, K = 8192): the wrappers split K over CTAs (fp32 partial tiles + b200_splitk_reduce)
+    when no epilogue is fused (inference); same result as the unsplit kernel."""
+    eng, lib = _eng(), _lib()
+    torch.manual_seed(13)
+    B, H, Cin, Cout = 8, 8, 512, 512
+    assert eng.pick_ksplit(eng._m_tiles(B, H // 2, H // 2), Cout, 1, 16 * Cin // 64)[0] > 1
+    x = bf(torch.randn(B, H, H, Cin, device=dev))
+    w = torch.randn(Cout, Cin, 4, 4, device=dev) / math.sqrt(Cin * 16)
+    pk = _packs(w)
+    y = eng.conv_s2(x, pk.gather, Cout)
+    y1 = torch.empty_like(y)
+    lib.call("b200_conv_s2_gemm", lib.ptr(x), B, H, H, Cin, lib.ptr(pk.gather), Cout, lib.ptr(y1), Cout, 64, 0, None, None, None, 1, None, lib.stream())
+    ref = nhwc(F.conv2d(nchw(x.float()), bf(w).float(), stride=2, padding=1))
+    assert rel(y, ref) < BF16_TOL and rel(y, y1) < 5e-3
+    z = bf(torch.randn(B, 2, 2, Cin, device=dev))
+    wt = torch.randn(Cin, Cout, 4, 4, device=dev) / math.sqrt(Cin * 4)
+    assert eng.pick_ksplit(eng._m_tiles(B, 2, 2), Cout, 4, 4 * Cin // 64)[0] > 1
+    yt = eng.convt_s2(z, Cin, Cin, _packs(wt).phase, Cout)
+    assert rel(yt, nhwc(F.conv_transpose2d(nchw(z.float()), bf(wt).float(), stride=2, padding=1))) < BF16_TOL
+
+
 @pytest.mark.parametrize("B,H,Cin,Cout", [(2, 16, 64, 128), (4, 8, 256, 512)])
 def test_conv_dgrad_is_phase_convt(dev, B, H, Cin, Cout):
     """Conv2d data gradient == the 4-phase transposed-conv kernel with the phase-packed Conv2d weight."""
