@@ -235,7 +235,9 @@ template <class E>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const IGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by pointer arithmetic (no integer round trip): the compiler keeps the shared address space and emits
+  // LDS / STS instead of generic loads / stores for everything the epilogue stages here
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int b_bytes = p.BN * 128;
   const int stage_bytes = p.kpb * (kATileBytes + b_bytes);
   uint64_t* full_bar = (uint64_t*)(smem + p.stages * stage_bytes);
@@ -431,7 +433,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
           }
         };
-        if (E::BWD) fetch(half * 32);
+        if (E::BWD) {
+          fetch(half * 32);
+          if (valid) {  // pull the rest of this row's y / skip-gradient slices towards L2 while the tile's MMAs are still running
+            for (int cc = half * 32 + 64; cc < p.BN; cc += 64) {
+              const int cb = c.n0 + cc - p.bwd.col0;
+              if (cb < 0) continue;
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.bwd.y + pix * p.bwd.ldy + cb));
+              if (E::G2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.bwd.g2 + pix * p.bwd.ldg2 + p.bwd.offg2 + cb));
+            }
+          }
+        }
         mbar_wait(&tmem_full_bar[buf], (uint32_t)((lt >> 1) & 1));
         tc_fence_after();
         for (int cc = half * 32; cc < p.BN; cc += 64) {
