@@ -72,11 +72,13 @@ __global__ void __launch_bounds__(kStatThreads) bn_stats_kernel(const __nv_bfloa
   }
 }
 
-// Sum the per-block partials of 32 consecutive channels: thread (w, l) walks blocks w, w+32, ... of channel c0+l
-// (coalesced 128-byte rows), fp64 accumulate, fixed-order tree over the 32 walkers -> deterministic.
+// Sum the per-block partials of 32 consecutive channels: thread (w, l) walks rows w, w+32, ... of channel c0+l (coalesced
+// 128-byte rows, independent loads), then 8 threads per channel fold the 32 walkers (4 adds + 3 shuffle steps) — a fixed
+// order, hence deterministic; fp64 throughout.  The result is valid in the threads with (threadIdx.x & 7) == 0 of the first
+// 256 threads: channel = blockIdx.x*32 + (threadIdx.x >> 3).
 constexpr int kFinThreads = 1024;
 // element (blk, k, c) lives at partial[blk * row_stride + k * k_stride + c]
-__device__ __forceinline__ void reduce_partials(const float* __restrict__ partial, int nblk, int C, int c, double& s, double& q, int row_stride = 0,
+__device__ __forceinline__ void reduce_partials(const float* __restrict__ partial, int nblk, int C, int c_lane, double& s, double& q, int row_stride = 0,
                                                 int k_stride = 0) {
   if (row_stride == 0) {
     row_stride = 2 * C;
@@ -85,10 +87,10 @@ __device__ __forceinline__ void reduce_partials(const float* __restrict__ partia
   __shared__ double sh[2][32][33];
   const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
   double a = 0.0, b = 0.0;
-  if (c < C) {
+  if (c_lane < C) {
     for (int blk = w; blk < nblk; blk += 32) {
-      a += (double)partial[(size_t)blk * row_stride + c];
-      b += (double)partial[(size_t)blk * row_stride + k_stride + c];
+      a += (double)partial[(size_t)blk * row_stride + c_lane];
+      b += (double)partial[(size_t)blk * row_stride + k_stride + c_lane];
     }
   }
   sh[0][w][l] = a;
@@ -96,10 +98,17 @@ __device__ __forceinline__ void reduce_partials(const float* __restrict__ partia
   __syncthreads();
   s = 0.0;
   q = 0.0;
-  if (w == 0) {
-    for (int k = 0; k < 32; ++k) {
-      s += sh[0][k][l];
-      q += sh[1][k][l];
+  if (threadIdx.x < 256) {
+    const int ch = threadIdx.x >> 3, part = threadIdx.x & 7;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      s += sh[0][part * 4 + k][ch];
+      q += sh[1][part * 4 + k][ch];
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
     }
   }
 }
@@ -111,10 +120,10 @@ __global__ void __launch_bounds__(kFinThreads) bn_finalize_kernel(const float* _
                                                                   float* __restrict__ running_mean, float* __restrict__ running_var,
                                                                   long long* __restrict__ num_batches_tracked, float momentum, float eps,
                                                                   float* __restrict__ stats_out) {
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   double s, q;
-  reduce_partials(partial, nblk, C, c, s, q);
-  if (threadIdx.x >= 32 || c >= C) return;
+  reduce_partials(partial, nblk, C, blockIdx.x * 32 + (threadIdx.x & 31), s, q);
+  const int c = blockIdx.x * 32 + (threadIdx.x >> 3);
+  if (threadIdx.x >= 256 || (threadIdx.x & 7) || c >= C) return;
   if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
   const double mean = s / count;
   double var = q / count - mean * mean;
@@ -327,10 +336,10 @@ __global__ void __launch_bounds__(kFinThreads) bn_bwd_finalize_kernel(const floa
                                                                       const float* __restrict__ stats, const float* __restrict__ gamma,
                                                                       float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate,
                                                                       float* __restrict__ coef, int row_stride, int k_stride) {
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   double sdz, sdzy;
-  reduce_partials(partial, nblk, C, c, sdz, sdzy, row_stride, k_stride);
-  if (threadIdx.x >= 32 || c >= C) return;
+  reduce_partials(partial, nblk, C, blockIdx.x * 32 + (threadIdx.x & 31), sdz, sdzy, row_stride, k_stride);
+  const int c = blockIdx.x * 32 + (threadIdx.x >> 3);
+  if (threadIdx.x >= 256 || (threadIdx.x & 7) || c >= C) return;
   const double mean = stats[0 * C + c], rstd = stats[1 * C + c];
   const double dg = rstd * (sdzy - mean * sdz);  // sum dz * xhat
   const double db = sdz;

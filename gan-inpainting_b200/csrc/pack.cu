@@ -91,19 +91,29 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const PackEntry* __restri
 // partial fp32 [splits][Cs][16*Cl] (column = t*Cl + cl)  ->  grad fp32 [Cs][Cl][16]
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int Cs, int Cl, float* __restrict__ grad,
                                                            int accumulate) {
-  // block: one cs, 16 cl:  reads 16 taps x 16 cl (64-byte runs), writes 256 contiguous floats
-  __shared__ float tile[16][17];
-  const int cs = blockIdx.y, cl0 = blockIdx.x * 16;
-  const int t = threadIdx.x >> 4, c = threadIdx.x & 15;
+  // block: one cs, 64 cl: thread (tap, cl quad) sums the splits with 128-bit loads (256-byte runs per tap), the 64 x 16 tile is
+  // transposed through shared memory and written as 4 KB of contiguous floats
+  __shared__ float tile[64][17];
+  const int cs = blockIdx.y, cl0 = blockIdx.x * 64;
+  const int t = threadIdx.x >> 4, cq = threadIdx.x & 15;
   const size_t split_stride = (size_t)Cs * 16 * Cl;
-  const float* src = partial + (size_t)cs * 16 * Cl + (size_t)t * Cl + cl0 + c;
-  float s = 0.f;
-  for (int k = 0; k < splits; ++k) s += src[k * split_stride];
-  tile[c][t] = s;
+  const float* src = partial + (size_t)cs * 16 * Cl + (size_t)t * Cl + cl0 + 4 * cq;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int k = 0; k < splits; ++k) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src + k * split_stride));
+    s.x += v.x, s.y += v.y, s.z += v.z, s.w += v.w;
+  }
+  tile[4 * cq][t] = s.x;
+  tile[4 * cq + 1][t] = s.y;
+  tile[4 * cq + 2][t] = s.z;
+  tile[4 * cq + 3][t] = s.w;
   __syncthreads();
-  const int oc = threadIdx.x >> 4, ot = threadIdx.x & 15;
-  float* dst = grad + ((size_t)cs * Cl + cl0 + oc) * 16 + ot;
-  *dst = accumulate ? *dst + tile[oc][ot] : tile[oc][ot];
+  float* dst = grad + ((size_t)cs * Cl + cl0) * 16;
+  for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+    const float v = tile[e >> 4][e & 15];
+    dst[e] = accumulate ? dst[e] + v : v;
+  }
 }
 
 }  // namespace b200
@@ -141,11 +151,11 @@ int b200_pack_all(const void* table, int nlayers, int total_tiles, cudaStream_t 
 }
 
 int b200_wgrad_reduce(const float* partial, int splits, int Cs, int Cl, float* grad, int accumulate, cudaStream_t stream) {
-  if (Cl % 16) {
-    b200_set_error("wgrad_reduce: Cl must be a multiple of 16");
+  if (Cl % 64) {
+    b200_set_error("wgrad_reduce: Cl must be a multiple of 64");
     return B200_ERR_ARG;
   }
-  wgrad_reduce_kernel<<<dim3(Cl / 16, Cs), 256, 0, stream>>>(partial, splits, Cs, Cl, grad, accumulate);
+  wgrad_reduce_kernel<<<dim3(Cl / 64, Cs), 256, 0, stream>>>(partial, splits, Cs, Cl, grad, accumulate);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
