@@ -298,11 +298,16 @@ def run_b200(args):
     gemm_ms = sum(kernel_ms.get(k, 0.0) for k in gemm_names)
     gemm_calls = sum(len(prof.get(k, [])) for k in gemm_names)
     achieved = fl["tensor"] * B / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+    traffic = None  # DRAM bytes per igemm launch from the committed ncu capture of this command (profiles/)
+    tpath = os.path.join(ROOT, "profiles", "r1_igemm_traffic.json")
+    if os.path.exists(tpath) and B == 64 and R == 256 and args.recipe == "wgan_l1":
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
     step_ms_instr = sum(kernel_ms.values())
     roofline = {
         "bound": "tensor", "kernel": "igemm_kernel (tcgen05 implicit GEMM: conv / convT phases / wgrad)", "achieved": achieved,
         "peak": peaks["tf_sustained"], "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)", "unit": "TFLOP/s",
-        "frac": (achieved / peaks["tf_sustained"]) if achieved else None, "traffic": None,
+        "frac": (achieved / peaks["tf_sustained"]) if achieved else None, "traffic": traffic,
+        "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_igemm_traffic.json)",
         "launches_per_step": gemm_calls, "avg_launch_ms": gemm_ms / max(gemm_calls, 1), "algorithmic_gflop_per_step": fl["tensor"] * B / 1e9,
         "share_of_step": gemm_ms / step_ms_instr if step_ms_instr else None,
         "step_breakdown_ms": {k: round(v, 4) for k, v in sorted(kernel_ms.items(), key=lambda kv: -kv[1])},

@@ -75,6 +75,7 @@ struct IGemmParams {
   long long P_total;     // pixels of the output tensor
   int stat_parity;       // 2: the per-quadrant statistics buffer is double buffered over tiles; 1: single + a second barrier per tile
   int off_acc, off_ss, off_tile, tile_bytes;  // byte offsets of the epilogue's shared-memory regions behind the barriers (host-sized per variant)
+  int pair;              // 1: CTA pairs (cta_group::2), num_tiles counts 256-pixel pair tiles
   int kpb;               // 64-wide k-blocks per pipeline stage (2 for narrow N tiles: halves the per-stage barrier overhead
                          // of the single issuing thread, which otherwise exceeds the MMA time of a 128 x 64 x 64 block)
   float* stats;          // optional (fprop modes): per-CTA column sums of the stored bf16 outputs,
@@ -103,7 +104,8 @@ struct TileCoord {
 
 // Work item t of the persistent loop.  fprop/dgrad: the pixel tile is the slow index so the CTAs running at the same
 // time read the same activations (4 phases x n_tiles) out of L2; wgrad: the pixel range (split) is the slow index.
-__device__ __forceinline__ TileCoord decode_tile(const IGemmParams& p, int t) {
+template <bool PAIR = false>
+__device__ __forceinline__ TileCoord decode_tile(const IGemmParams& p, int t, int rank = 0) {
   TileCoord c;
   c.w0 = c.h0 = c.b0 = c.m0 = c.phase = c.ks = 0;
   c.kb_begin = 0;
@@ -125,7 +127,9 @@ __device__ __forceinline__ TileCoord decode_tile(const IGemmParams& p, int t) {
       t -= c.ks * per_split;
       c.kb_begin = c.ks * p.kb_per_tile;
     }
-    const int pt = t / per_pt, r = t - pt * per_pt;
+    int pt = t / per_pt;
+    const int r = t - pt * per_pt;
+    if (PAIR) pt = 2 * pt + rank;  // a CTA pair owns two adjacent 128-pixel tiles (one 256-row MMA tile)
     c.phase = r / p.n_tiles;
     c.n0 = (r - c.phase * p.n_tiles) * p.BN;
     const int wt = pt & (p.tiles_w - 1);
@@ -231,15 +235,23 @@ __device__ __forceinline__ void tile_column_sums_f32(uint8_t* wbuf, const uint32
     }
 }
 
-template <class E>
+// PAIR: two CTAs of a cluster (the two SMs of a TPC) run ONE tcgen05.mma.cta_group::2 per K step over a 256-pixel x BN tile:
+// each CTA stages its own 128 pixel rows of A and HALF of the weight tile (BN/2 rows), so the operand bytes pulled through
+// L2 per flop drop by a third at BN = 256 — the GEMMs with 128 x BN single-CTA tiles are bound by exactly that traffic.
+// The even CTA issues the MMAs; TMA transaction bytes of both CTAs are counted on its barriers; tcgen05.commit multicasts
+// the "slot free" / "accumulator ready" arrivals to both CTAs; both epilogues release the accumulator on the even CTA.
+template <class E, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const IGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by pointer arithmetic (no integer round trip): the compiler keeps the shared address space and emits
   // LDS / STS instead of generic loads / stores for everything the epilogue stages here
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int b_bytes = p.BN * 128;
+  const int b_bytes = (PAIR ? p.BN / 2 : p.BN) * 128;  // per CTA
   const int stage_bytes = p.kpb * (kATileBytes + b_bytes);
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // first work item of this CTA (pair)
+  const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   uint64_t* full_bar = (uint64_t*)(smem + p.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full_bar = empty_bar + p.stages;   // [2]
@@ -263,31 +275,38 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], kEpiWarps);  // one arrival per epilogue warp
+      mbar_init(&tmem_empty_bar[b], PAIR ? 2 * kEpiWarps : kEpiWarps);  // one arrival per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr_smem, p.tmem_cols);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc2(tmem_ptr_smem, p.tmem_cols);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_ptr_smem, p.tmem_cols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      const uint32_t tx_bytes = (uint32_t)stage_bytes;
+      const uint32_t tx_bytes = (uint32_t)stage_bytes * (PAIR ? 2u : 1u);  // PAIR: both CTAs' bytes land on the even CTA's barrier
+      const int nB = PAIR ? rank * (p.BN / 2) : 0;                         // this CTA's half of the weight tile
       int s = 0;
       uint32_t par = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-        const TileCoord c = decode_tile(p, t);
+      for (int t = tile0; t < p.num_tiles; t += tile_step) {
+        const TileCoord c = decode_tile<PAIR>(p, t, rank);
         const int ph_p = c.phase >> 1, ph_q = c.phase & 1;
         for (int i = 0; i < c.kb_count; i += p.kpb) {
           mbar_wait(&empty_bar[s], par ^ 1u);
-          mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+          if (!PAIR || rank == 0) mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
           for (int u = 0; u < p.kpb; ++u) {
           uint8_t* sA = smem + s * stage_bytes + u * kATileBytes;
           uint8_t* sB = smem + s * stage_bytes + p.kpb * kATileBytes + u * b_bytes;
@@ -295,14 +314,25 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (p.mode == MODE_CONV_S2) {
             const int tap = kb >> p.cpt_sh, cc = kb & (p.cpt - 1);
             const int kh = tap >> 2, kw = tap & 3;
-            tma_load_5d(sA, &tmA, &full_bar[s], ((kw + 1) & 1) * p.C_k + cc * 64, c.w0 + ((kw + 1) >> 1) - 1, (kh + 1) & 1,
-                        c.h0 + ((kh + 1) >> 1) - 1, c.b0);
-            tma_load_2d(sB, &tmB, &full_bar[s], kb * 64, c.n0);
+            if (PAIR) {
+              tma2_load_5d(sA, &tmA, &full_bar[s], ((kw + 1) & 1) * p.C_k + cc * 64, c.w0 + ((kw + 1) >> 1) - 1, (kh + 1) & 1,
+                           c.h0 + ((kh + 1) >> 1) - 1, c.b0);
+              tma2_load_2d(sB, &tmB, &full_bar[s], kb * 64, c.n0 + nB);
+            } else {
+              tma_load_5d(sA, &tmA, &full_bar[s], ((kw + 1) & 1) * p.C_k + cc * 64, c.w0 + ((kw + 1) >> 1) - 1, (kh + 1) & 1,
+                          c.h0 + ((kh + 1) >> 1) - 1, c.b0);
+              tma_load_2d(sB, &tmB, &full_bar[s], kb * 64, c.n0);
+            }
           } else if (p.mode == MODE_CONVT) {
             const int tap = kb >> p.cpt_sh, cc = kb & (p.cpt - 1);
             const int ta = tap >> 1, tb = tap & 1;
-            tma_load_4d(sA, &tmA, &full_bar[s], cc * 64, c.w0 + ph_q + tb - 1, c.h0 + ph_p + ta - 1, c.b0);
-            tma_load_2d(sB, &tmB, &full_bar[s], kb * 64, c.phase * p.Cout + c.n0);
+            if (PAIR) {
+              tma2_load_4d(sA, &tmA, &full_bar[s], cc * 64, c.w0 + ph_q + tb - 1, c.h0 + ph_p + ta - 1, c.b0);
+              tma2_load_2d(sB, &tmB, &full_bar[s], kb * 64, c.phase * p.Cout + c.n0 + nB);
+            } else {
+              tma_load_4d(sA, &tmA, &full_bar[s], cc * 64, c.w0 + ph_q + tb - 1, c.h0 + ph_p + ta - 1, c.b0);
+              tma_load_2d(sB, &tmB, &full_bar[s], kb * 64, c.phase * p.Cout + c.n0);
+            }
           } else {
             const int wt = kb & (p.tiles_w - 1);
             const int ht = (kb >> p.tiles_w_sh) & (p.tiles_h - 1);
@@ -329,15 +359,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       const bool mn_major = (p.mode == MODE_WGRAD);
-      const uint32_t idesc = make_idesc_bf16(128, p.BN, mn_major ? 1 : 0, mn_major ? 1 : 0);
+      const uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, p.BN, mn_major ? 1 : 0, mn_major ? 1 : 0);
       const uint32_t lbo = mn_major ? 8192u : 16u;
       const uint32_t kstep = mn_major ? 2048u : 32u;  // bytes per K=16 slice inside a stage
       int s = 0, lt = 0;
       uint32_t par = 0;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++lt) {
-        const TileCoord c = decode_tile(p, t);
+      for (int t = tile0; t < p.num_tiles; t += tile_step, ++lt) {
+        const TileCoord c = decode_tile<PAIR>(p, t, rank);
         const int buf = lt & 1;
         mbar_wait(&tmem_empty_bar[buf], (uint32_t)(((lt >> 1) & 1) ^ 1));  // the epilogue has drained this accumulator
         tc_fence_after();
@@ -352,16 +382,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             for (int k = 0; k < 4; ++k) {
               const uint64_t da = make_smem_desc_sw128(a_addr + u * kATileBytes + k * kstep, lbo, 1024u);
               const uint64_t db = make_smem_desc_sw128(b_addr + u * b_bytes + k * kstep, lbo, 1024u);
-              umma_bf16(d_addr, da, db, idesc, (i > 0 || u > 0 || k > 0) ? 1u : 0u);
+              if (PAIR) umma_bf16_2cta(d_addr, da, db, idesc, (i > 0 || u > 0 || k > 0) ? 1u : 0u);
+              else umma_bf16(d_addr, da, db, idesc, (i > 0 || u > 0 || k > 0) ? 1u : 0u);
             }
           }
-          umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
+          if (PAIR) umma_commit_2cta(&empty_bar[s]);  // frees the slot in both CTAs
+          else umma_commit(&empty_bar[s]);            // frees the smem slot once these MMAs retire
           if (++s == p.stages) {
             s = 0;
             par ^= 1u;
           }
         }
-        umma_commit(&tmem_full_bar[buf]);  // accumulator complete
+        if (PAIR) umma_commit_2cta(&tmem_full_bar[buf]);
+        else umma_commit(&tmem_full_bar[buf]);  // accumulator complete
       }
     }
   } else {
@@ -383,8 +416,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     uint8_t* wbuf = stat_tile + (warp - 2) * p.tile_bytes;
     int lt = 0;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++lt) {
-      const TileCoord c = decode_tile(p, t);
+    for (int t = tile0; t < p.num_tiles; t += tile_step, ++lt) {
+      const TileCoord c = decode_tile<PAIR>(p, t, rank);
       const int buf = lt & 1;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.BN);
       if (p.mode == MODE_WGRAD) {
@@ -400,7 +433,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);  // (weight gradients never run as pairs)
       } else {
         const int bl = r >> (p.th_sh + p.tw_sh), rem = r & ((1 << (p.th_sh + p.tw_sh)) - 1);
         const int hl = rem >> p.tw_sh, wl = rem & (p.tw - 1);
@@ -542,7 +575,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         tc_fence_before();  // the accumulator has been read: hand the TMEM buffer back before the cross-warp statistics
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_leader(&tmem_empty_bar[buf]);
+          else mbar_arrive(&tmem_empty_bar[buf]);
+        }
         if (E::STATS) {
           asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // all epilogue warps
           const float* sb = stat_smem + sp * 4 * 2 * p.BN;
@@ -566,9 +602,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   // ---- teardown
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer may still be reading operands / TMEM this CTA's MMAs touched
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, p.tmem_cols);
+    if (PAIR) tmem_dealloc2(tmem_base, p.tmem_cols);
+    else tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
 
@@ -687,9 +725,38 @@ static int ilog2(int v) {
 
 template <class E>
 static void launch_variant(const CUtensorMap& a, const CUtensorMap& b, const IGemmParams& p, int grid, size_t smem, cudaStream_t stream) {
+  if (p.pair) {
+    static std::once_flag once2;
+    std::call_once(once2, [] { cudaFuncSetAttribute(igemm_kernel<E, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, igemm_kernel<E, true>, a, b, p);
+    return;
+  }
   static std::once_flag once;
-  std::call_once(once, [] { cudaFuncSetAttribute(igemm_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
-  igemm_kernel<E><<<grid, kThreads, smem, stream>>>(a, b, p);
+  std::call_once(once, [] { cudaFuncSetAttribute(igemm_kernel<E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+  igemm_kernel<E, false><<<grid, kThreads, smem, stream>>>(a, b, p);
+}
+
+// CTA pairs pay when the single-CTA tiles are bound by operand traffic: fprop / dgrad with enough pixel tiles to give every
+// TPC a pair tile.  B200_IGEMM_2CTA=0 disables them (A/B comparison).
+static bool want_pair(const IGemmParams& p, int ksplit) {
+  static const bool enabled = [] {
+    const char* e = getenv("B200_IGEMM_2CTA");
+    return !(e && e[0] == '0');
+  }();
+  if (!enabled || p.mode == MODE_WGRAD || ksplit > 1 || (p.num_ptiles & 1) || p.BN < 64) return false;
+  return (p.num_ptiles / 2) * p.n_tiles * p.phases >= kNumSMs / 2;
 }
 
 static int launch(const CUtensorMap& a, const CUtensorMap& b, IGemmParams& p, cudaStream_t stream, int* grid_out) {
@@ -704,7 +771,7 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, IGemmParams& p, cu
   p.ck_sh = ilog2(p.C_k);
   p.cpt_sh = ilog2(p.cpt);
   p.kpb = (p.mode != MODE_WGRAD && p.BN <= 128 && p.kb_per_tile % 2 == 0) ? 2 : 1;
-  const int stage_bytes = p.kpb * (kATileBytes + p.BN * 128);
+  const int stage_bytes = p.kpb * (kATileBytes + (p.pair ? p.BN / 2 : p.BN) * 128);  // per CTA
   const bool has_stats = p.stats != nullptr, has_bwd = p.bwd.y != nullptr;
   // shared memory behind the pipeline stages, sized per epilogue variant: barriers, the per-quadrant statistics buffer
   // (double buffered over tiles unless that would cost a pipeline stage), the per-CTA running sums, the BatchNorm
@@ -738,7 +805,7 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, IGemmParams& p, cu
   while ((int)cols < 2 * p.BN) cols <<= 1;
   p.tmem_cols = cols;
   const size_t smem = (size_t)p.stages * stage_bytes + extra;
-  const int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  const int grid = p.pair ? 2 * (p.num_tiles < kNumSMs / 2 ? p.num_tiles : kNumSMs / 2) : (p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs);
   if (grid_out) *grid_out = grid;
   const bool bn = p.bwd.scale != nullptr, g2 = p.bwd.g2 != nullptr;
   const int act = p.bwd.act;
@@ -875,9 +942,11 @@ int b200_conv_s2_gemm(const void* x, int B, int H, int W, int Cin, const void* w
   int rc;
   if ((rc = set_bwd(p, bwd, Cout, "conv_s2_gemm"))) return rc;
   if ((rc = set_split(p, ksplit, partial, (long long)B * p.Hs * p.Ws, "conv_s2_gemm"))) return rc;
+  p.pair = want_pair(p, ksplit) ? 1 : 0;
+  if (p.pair) p.num_tiles /= 2;
   CUtensorMap ta, tb;
   if ((rc = map_nhwc_parity(&ta, x, B, H, W, Cin, p.tw, p.th, p.nb))) return rc;
-  if ((rc = map_weights(&tb, wpk, Cout, 16 * Cin, p.BN))) return rc;
+  if ((rc = map_weights(&tb, wpk, Cout, 16 * Cin, p.pair ? p.BN / 2 : p.BN))) return rc;
   return launch(ta, tb, p, stream, stat_rows);
 }
 
@@ -918,9 +987,11 @@ int b200_convt_s2_gemm(const void* z, int B, int Hi, int Wi, int Cin, int ldz, c
   int rc;
   if ((rc = set_bwd(p, bwd, Cout, "convt_s2_gemm"))) return rc;
   if ((rc = set_split(p, ksplit, partial, (long long)B * 4 * Hi * Wi, "convt_s2_gemm"))) return rc;
+  p.pair = want_pair(p, ksplit) ? 1 : 0;
+  if (p.pair) p.num_tiles /= 2;
   CUtensorMap ta, tb;
   if ((rc = map_nhwc(&ta, z, B, Hi, Wi, Cin, ldz, p.tw, p.th, p.nb))) return rc;
-  if ((rc = map_weights(&tb, wpk, 4 * Cout, 4 * Cin, p.BN))) return rc;
+  if ((rc = map_weights(&tb, wpk, 4 * Cout, 4 * Cin, p.pair ? p.BN / 2 : p.BN))) return rc;
   return launch(ta, tb, p, stream, stat_rows);
 }
 
@@ -968,6 +1039,7 @@ int b200_wgrad_gemm(const void* S, int B, int Hs, int Ws, int Cs, int lds, const
   p.bwd = EpiBwd{};
   p.ksplit = 1;
   p.partial = nullptr;
+  p.pair = 0;
   CUtensorMap ta, tb;
   int rc;
   if ((rc = map_nhwc(&ta, S, B, Hs, Ws, Cs, lds, p.tw, p.th, p.nb))) return rc;
