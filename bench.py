@@ -32,6 +32,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly ONE JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) out of it
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 RECIPES = {
     # name: (trainer recipe, recon, sigmoid D, update_g)
