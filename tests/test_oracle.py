@@ -80,7 +80,7 @@ def test_wgan_step_matches_reference_modules(golden):
             assert ne < 1e-3, k
         for k, s in g["d_post"].items():
             ne, _ = summary_close(D[k], s, 0)
-            assert ne < ORACLE_TOL, k
+            assert ne < 1e-3, k  # post-step weights: one sign flip of a ~0 gradient element moves the norm by ~1e-4 (sign descent)
 
 
 def test_minimax_and_global_local_steps_match_reference_modules(golden):
