@@ -67,7 +67,7 @@ def flops_per_image(res: int, recipe: str) -> dict:
 class ClockSampler:
     """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md recipe)."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
@@ -77,35 +77,43 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
-    def stop(self) -> dict:
+    def stop(self, t0: float = None, t1: float = None) -> dict:
+        """Summary of the samples taken in the wall-clock window [t0, t1] (the timed region; nvidia-smi is started before the
+        warm-up so that its start-up cost stays outside).  Falls back to the last samples when none fell inside a short window."""
+        import datetime
+
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.p.terminate()
         self.p.wait()
         self.f.flush()
         rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
         os.unlink(self.f.name)
-        sm, mx, reasons, power = [], [], set(), []
+        samples = []
         for r in rows:
             try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                power.append(float(r[3]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.strip().lower() == "active":
-                        reasons.add(name)
+                ts = datetime.datetime.strptime(r[0].strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                reasons = {name for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[6:10])
+                           if v.strip().lower() == "active"}
+                samples.append((ts, float(r[2]), float(r[3]), float(r[4]), reasons))
             except (ValueError, IndexError):
                 continue
-        if not sm:
+        if not samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        load = sorted(sm[len(sm) // 4:]) or sorted(sm)
-        return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": max(mx), "power_w_max": max(power), "samples": len(sm), "reasons": sorted(reasons)}
+        inside = [x for x in samples if t0 is not None and t0 <= x[0] <= t1 + 0.06]
+        window = "timed region"
+        if not inside:
+            inside, window = samples[-3:], "last samples (none fell inside the timed region)"
+        sm = sorted(x[1] for x in inside)
+        reasons = set().union(*(x[4] for x in inside))
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(x[2] for x in inside), "power_w_max": max(x[3] for x in inside), "samples": len(inside),
+                "samples_total": len(samples), "window": window, "reasons": sorted(reasons)}
 
 
 def measured_peaks():
@@ -199,7 +207,7 @@ def run_b200(args):
     torch.manual_seed(0)
     G = networks.get_network("generator", "unet").to(dev).train()  # reference default: dropout ON
     D = networks.PatchGANDiscriminator(sigmoid=(kind != "wgan"), imagedim=R).to(dev).train()
-    tr = InpaintingTrainer(kind, G, D, recon=recon, distributed=world > 1, bucket_mb=args.bucket_mb)
+    tr = InpaintingTrainer(kind, G, D, recon=recon, distributed=world > 1, bucket_mb=args.bucket_mb, graph=not args.no_graph)
     ground_h, mask_h = synth.make_batch(B, R, seed=1234, rank=rank)
     ground_h, mask_h = ground_h.pin_memory(), mask_h.pin_memory()
     ground, mask = ground_h.to(dev), mask_h.to(dev)
@@ -246,14 +254,17 @@ def run_b200(args):
             out_h.copy_(tr.scalars, non_blocking=True)
             torch.cuda.current_stream().synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step_dev()
     sampler = ClockSampler(local)
-    l0 = _lib.value("b200_launch_count")
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    l0 = _lib.value("b200_launch_count")
+    sync_all()
+    w0 = time.time()
     ms = timed(step_dev, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
+    w1 = time.time()
+    clocks = sampler.stop(w0, w1) if rank == 0 else None
     launches = _lib.value("b200_launch_count") - l0
     # host-side enqueue cost of one step (Python + ctypes + allocator): must stay below the device time or the GPU starves
     torch.cuda.synchronize()
@@ -283,8 +294,10 @@ def run_b200(args):
     kernel_ms = {}
     if rank == 0:
         _lib.PROFILE = hook
+    tr.graph = False  # the instrumented step is enqueued kernel by kernel (events around every C-ABI call)
     step_dev()  # every rank takes part (the step contains the gradient all-reduces); only rank 0 is instrumented
     torch.cuda.synchronize()
+    tr.graph = not args.no_graph
     _lib.PROFILE = None
     if rank == 0:
         kernel_ms = {k: sum(a.elapsed_time(b) for a, b in v) for k, v in prof.items()}
@@ -329,7 +342,8 @@ def run_b200(args):
         "config": {"workload": f"{args.recipe}: U-Net generator + PatchGAN global D, full train step (D update + G update), {R}x{R}, batch {B} per GPU",
                    "recipe": args.recipe, "res": R, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                    "dropout": True, "l2": "no flush: one step streams ~6 GB of activations/gradients, far larger than the 126 MB L2",
-                   "bn": "per-replica batch statistics", "bucket_mb": args.bucket_mb},
+                   "bn": "per-replica batch statistics", "bucket_mb": args.bucket_mb,
+                   "launch": "eager (one ctypes call per kernel)" if args.no_graph else "whole step replayed as one CUDA graph"},
         "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": out_h.numel() * 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
@@ -355,6 +369,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=4, help="images per step of the bounded CPU sample")
     ap.add_argument("--bucket-mb", type=float, default=25.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying the captured step graph")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "b200" and args.gpus != world:

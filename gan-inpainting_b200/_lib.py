@@ -71,6 +71,8 @@ VALUE_FUNCS = {
     "b200_abi_version": (c_int, []),
     "b200_last_error": (c_char_p, []),
     "b200_launch_count": (c_longlong, []),
+    "b200_launch_count_add": (None, [c_longlong]),
+    "b200_set_seed_counter": (None, [c_void_p]),
     "b200_bn_stat_blocks": (c_int, [L, I]),
     "b200_igemm_stat_rows": (c_int, []),
     "b200_wgrad_c1_blocks": (c_int, []),

@@ -13,7 +13,14 @@ void b200_set_error(const char* msg) {
 static long long g_launches = 0;
 void b200_count_launch(void) { ++g_launches; }
 
+static const uint32_t* g_seed_counter = nullptr;
+const uint32_t* b200_seed_counter_ptr(void) { return g_seed_counter; }
+
 extern "C" {
+// device uint32 added (x odd constant) to the seed of every dropout mask drawn by kernels enqueued afterwards; NULL = off
+void b200_set_seed_counter(const unsigned* dev_counter) { g_seed_counter = dev_counter; }
+// replaying a captured graph launches kernels this library enqueued at capture time: account for them
+void b200_launch_count_add(long long n) { g_launches += n; }
 const char* b200_last_error(void) { return g_err; }
 // number of kernels this library has launched since load (bench.py's gpu_launches evidence)
 long long b200_launch_count(void) { return g_launches; }

@@ -23,6 +23,7 @@
 
 void b200_set_error(const char* msg);
 void b200_count_launch(void);
+const uint32_t* b200_seed_counter_ptr(void);  // device counter added to every dropout seed (null: none)
 
 namespace b200 {
 
@@ -260,6 +261,11 @@ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   x *= 0x846ca68bU;
   x ^= x >> 16;
   return x;
+}
+// seed of this launch's dropout masks: the host-passed seed, advanced by an optional device-side counter that is read when the
+// kernel RUNS (a captured CUDA graph of the train step draws fresh masks on every replay; b200_set_seed_counter)
+__device__ __forceinline__ uint32_t dropout_seed(uint32_t seed, const uint32_t* counter) {
+  return counter ? seed + __ldg(counter) * 0x9E3779B1U : seed;
 }
 __device__ __forceinline__ bool dropout_keep(uint32_t seed, uint64_t idx) {
   uint32_t h = mix32((uint32_t)idx ^ mix32(seed ^ (uint32_t)(idx >> 32) * 0x9E3779B9U));

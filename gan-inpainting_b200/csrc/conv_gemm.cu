@@ -41,6 +41,7 @@ struct EpiBwd {
   int ldg2, offg2;
   int dropout;             // Dropout(0.5) between BatchNorm and ReLU: keep-mask regenerated from (seed, element index)
   uint32_t seed;
+  const uint32_t* seed_ctr;  // optional device counter advancing the seed (b200_set_seed_counter)
   int col0;
   int Cy;                  // channels of y
   float* dz32;             // optional: dz is ALSO the input of a BatchNorm backward -> stored unrounded, fp32 [pixel][Cy] (then the
@@ -415,6 +416,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
     }
     uint8_t* wbuf = stat_tile + (warp - 2) * p.tile_bytes;
+    const uint32_t drop_seed = (E::BWD && p.bwd.dropout) ? dropout_seed(p.bwd.seed, p.bwd.seed_ctr) : 0u;
     int lt = 0;
     for (int t = tile0; t < p.num_tiles; t += tile_step, ++lt) {
       const TileCoord c = decode_tile<PAIR>(p, t, rank);
@@ -515,7 +517,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     g = z > 0.f ? (E::G2 ? g + (e ? gf.y : gf.x) : g) : 0.2f * g;
                   } else if (E::ACT == ACT_BWD_RELU) {
                     g = z > 0.f ? g : 0.f;
-                    if (p.bwd.dropout) g = dropout_keep(p.bwd.seed, (uint64_t)(pix * p.bwd.Cy + cb + jj)) ? 2.f * g : 0.f;
+                    if (p.bwd.dropout) g = dropout_keep(drop_seed, (uint64_t)(pix * p.bwd.Cy + cb + jj)) ? 2.f * g : 0.f;
                   }
                   v[jj] = __float_as_uint(g);
                 }
@@ -879,6 +881,7 @@ static int set_bwd(IGemmParams& p, const b200_epi_bwd* e, int Cout, const char* 
   p.bwd.offg2 = e->offg2;
   p.bwd.dropout = e->dropout;
   p.bwd.seed = e->seed;
+  p.bwd.seed_ctr = e->dropout ? b200_seed_counter_ptr() : nullptr;
   p.bwd.col0 = e->col0;
   p.bwd.Cy = e->Cy;
   p.bwd.dz32 = (float*)e->dz32;

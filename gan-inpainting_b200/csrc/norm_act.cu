@@ -170,11 +170,13 @@ struct ApplyParams {
   int ld2, off2;
   int dropout;  // 1 -> keep-mask from (seed, element index), kept values x2
   uint32_t seed;
+  const uint32_t* seed_ctr;  // optional device counter (b200_set_seed_counter)
 };
 
 __global__ void __launch_bounds__(256) bn_act_kernel(const ApplyParams p) {
   const unsigned total = (unsigned)p.P << p.cshift;
   const unsigned cmask = (1u << p.cshift) - 1u;
+  const uint32_t seed = p.dropout ? dropout_seed(p.seed, p.seed_ctr) : 0u;
   for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const size_t pix = idx >> p.cshift;
     const int c0 = (int)(idx & cmask) * 8;
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(256) bn_act_kernel(const ApplyParams p) {
     }
     if (p.dropout) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = dropout_keep(p.seed, (uint64_t)(pix * p.C + c0 + i)) ? 2.f * f[i] : 0.f;
+      for (int i = 0; i < 8; ++i) f[i] = dropout_keep(seed, (uint64_t)(pix * p.C + c0 + i)) ? 2.f * f[i] : 0.f;
     }
     if (p.act == ACT_LEAKY) {
 #pragma unroll
@@ -238,6 +240,7 @@ struct BwdParams {
   int ldg2, offg2;
   int dropout;
   uint32_t seed;
+  const uint32_t* seed_ctr;
   // reduce: partial[blk][2][C] = sum dz, sum dz*y
   float* partial;
   // apply: dy = kdz*dz + ky*y + k0   (coef[3][C]; null: dy = dz)
@@ -286,8 +289,9 @@ __device__ __forceinline__ void compute_dz(const BwdParams& p, size_t pix, int c
 #pragma unroll
     for (int i = 0; i < 8; ++i) dz[i] = z[i] > 0.f ? g1[i] : 0.f;
     if (p.dropout) {
+      const uint32_t seed = dropout_seed(p.seed, p.seed_ctr);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) dz[i] = dropout_keep(p.seed, (uint64_t)(pix * p.C + c0 + i)) ? 2.f * dz[i] : 0.f;
+      for (int i = 0; i < 8; ++i) dz[i] = dropout_keep(seed, (uint64_t)(pix * p.C + c0 + i)) ? 2.f * dz[i] : 0.f;
     }
   } else {
 #pragma unroll
@@ -482,7 +486,7 @@ int b200_bn_act(const void* y, long long P, int C, const float* scale, const flo
     b200_set_error("bn_act: C must be a power of two >= 8; strides / offsets multiples of 8");
     return B200_ERR_ARG;
   }
-  ApplyParams p{(const __nv_bfloat16*)y, (int)P, C, cs, scale, shift, act, (__nv_bfloat16*)out1, ld1, off1, (__nv_bfloat16*)out2, ld2, off2, dropout, seed};
+  ApplyParams p{(const __nv_bfloat16*)y, (int)P, C, cs, scale, shift, act, (__nv_bfloat16*)out1, ld1, off1, (__nv_bfloat16*)out2, ld2, off2, dropout, seed, b200_seed_counter_ptr()};
   bn_act_kernel<<<grid_for(P * (C >> 3), 256), 256, 0, stream>>>(p);
   B200_CHECK_LAUNCH();
   return B200_OK;
@@ -515,6 +519,7 @@ int b200_bn_act_bwd(const void* y, long long P, int C, const float* stats /*[4][
   p.offg2 = offg2;
   p.dropout = dropout;
   p.seed = seed;
+  p.seed_ctr = b200_seed_counter_ptr();
   p.partial = (float*)partial;
   p.coef = nullptr;
   p.dy = (__nv_bfloat16*)dy;

@@ -7,8 +7,9 @@ kernels) and the bookkeeping around it is written once:
 * ``state`` keys read: ``numepoch, batchsize, imagedim, saveevery, evalevery, updatediscevery, generator`` (train.py:22-36);
   optional extras with defaults so reference-style callers keep working: ``experiment_dir`` (the reference hard-codes a
   home directory, wgan_l1.py:27), ``log_dir`` ('log'), ``distributed`` (False), ``bucket_mb`` (25), ``evaluate_fn``
-  (callable(net_G, loader, mode) -> dict; the reference's evaluate.calculate_metric is out of scope),
-  ``max_batches`` (None; smoke runs).
+  (callable(net_G, loader, mode) -> dict; default: ``lib.models.evaluate.calculate_metric`` like wgan_l1.py:251-259, with
+  ``state['train_fid'] / ['test_fid'] / ['inception_model']`` passed through when present), ``graph`` (True: replay the step as a
+  CUDA graph), ``max_batches`` (None; smoke runs).
 * per-epoch history dicts with the reference's keys (``g``/``d``/``gradients``; -7777 sentinel when G never updated,
   wgan_l1.py:214-249), pickled to ``training_epoch_history.obj`` / ``eval_history.obj`` (:262-267), and
   ``epoch{N}_G.pt`` checkpoints of ``net_G.state_dict()`` (:269-271) in the reference's key layout.
@@ -26,7 +27,7 @@ from typing import Callable, Dict, Optional
 import torch
 
 from ..data import DevicePrefetcher
-from ..lib.models import networks
+from ..lib.models import evaluate, networks
 from ..trainer import InpaintingTrainer
 
 SENTINEL = -7777  # wgan_l1.py:224-233
@@ -80,10 +81,13 @@ def run(state: dict, loaders: dict, title: str, recipe: str, recon: str, schedul
     net_D = networks.PatchGANDiscriminator(sigmoid=sigmoid, imagedim=R).to(device)
     net_Dl = networks.PatchGANDiscriminator(sigmoid=sigmoid, imagedim=R).to(device) if local_d else None
     tr = InpaintingTrainer(recipe, net_G, net_D, net_Dl, recon=recon, lambdas=lambdas, distributed=distributed,
-                           bucket_mb=float(state.get("bucket_mb", 25.0)), log_grad_means=True)
+                           bucket_mb=float(state.get("bucket_mb", 25.0)), log_grad_means=True, graph=bool(state.get("graph", True)))
     g_names = [n for n, _ in net_G.named_parameters() if "bias" not in n]
     d_names = [n for n, _ in net_D.named_parameters() if "bias" not in n]
     evaluate_fn: Optional[Callable] = state.get("evaluate_fn")
+    if evaluate_fn is None:  # wgan_l1.py:251-252
+        def evaluate_fn(net, loader, mode):
+            return evaluate.calculate_metric(device, loader, net, state.get(mode + "_fid", (-1, -1)), mode=mode, inception_model=state.get("inception_model"))
     max_batches = state.get("max_batches")
 
     training_epoch_hist, eval_hist = [], []
@@ -137,10 +141,9 @@ def run(state: dict, loaders: dict, title: str, recipe: str, recon: str, schedul
         training_epoch_hist.append({"g": eg, "d": ed, "gradients": gh})
 
         if epoch % evaluate_every == 0 and epoch > 0:
-            if evaluate_fn is not None:
-                entry = {"train": evaluate_fn(net_G, train_loader, "train"), "test": evaluate_fn(net_G, test_loader, "test") if test_loader is not None else None}
-                eval_hist.append(entry)
-                logger.info("VALIDATION: train - {}, test - {}".format(str(entry["train"]), str(entry["test"])))
+            entry = {"train": evaluate_fn(net_G, train_loader, "train"), "test": evaluate_fn(net_G, test_loader, "test") if test_loader is not None else None}
+            eval_hist.append(entry)
+            logger.info("VALIDATION: train - {}, test - {}".format(str(entry["train"]), str(entry["test"])))
             with open(os.path.join(experiment_dir, "training_epoch_history.obj"), "wb") as handle:
                 pickle.dump(training_epoch_hist, handle, protocol=pickle.HIGHEST_PROTOCOL)
             with open(os.path.join(experiment_dir, "eval_history.obj"), "wb") as handle:

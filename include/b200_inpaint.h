@@ -48,6 +48,11 @@ typedef struct CUstream_st* b200_stream_t; /* == cudaStream_t */
 int b200_abi_version(void);
 const char* b200_last_error(void); /* thread-local, host string */
 long long b200_launch_count(void);  /* kernels launched by this library since load */
+void b200_launch_count_add(long long n); /* a replayed CUDA graph re-launches n kernels this library enqueued at capture time */
+/* Dropout(0.5) masks (networks.py:312-314) are a stateless hash of (seed, element index).  With a device counter installed the
+ * effective seed of every kernel enqueued afterwards is seed + *dev_counter * odd constant, read when the kernel RUNS: a captured
+ * CUDA graph of the whole train step then draws fresh masks on every replay (bump the counter with b200_step_inc).  NULL = off. */
+void b200_set_seed_counter(const unsigned* dev_counter);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * tcgen05 implicit-GEMM convolutions (csrc/conv_gemm.cu).  4x4 kernel, stride 2, padding 1; TMA-staged NHWC bf16

@@ -92,6 +92,29 @@ def inference(G: Params, ground, mask, train_mode: bool = False):
         return composite(masked, nets.unet_forward(G, masked, train=train_mode), mask)
 
 
+def calculate_metric(G: Params, batches, is_flip_mask: bool = False, train_mode: bool = True, eps: float = 1e-16):
+    """The reconstruction part of evaluate.py:87-177 (``calculate_metric``; the file itself is a TabError, SURVEY.md D7, so this
+    follows its statements): per batch ``mask = ceil(mask)`` [``1 - mask``] (:129-132), ``masked = input*(1-m)``,
+    ``out = net(masked)*m + masked`` (:133-136), RMSELoss / L1Loss globally (:139-140) and LocalLoss(L1) / the intended
+    LocalLoss(RMSELoss) = sqrt(masked-MSE micro-average + eps) (:142-143, loss.py:30-31,44-45); means over batches (:166-170).
+    ``train_mode`` mirrors the reference never calling ``net.eval()``."""
+    acc = dict(recon_rmse_global=0.0, recon_l1_global=0.0, recon_rmse_local=0.0, recon_l1_local=0.0)
+    n = 0
+    with torch.no_grad():
+        for ground, mask, *_ in batches:
+            m = torch.ceil(mask)
+            if is_flip_mask:
+                m = 1 - m
+            masked = ground * (1 - m)
+            out = nets.unet_forward(G, masked, train=train_mode) * m + masked
+            acc["recon_rmse_global"] += float(losses.rmse(ground, out, eps))
+            acc["recon_l1_global"] += float((ground - out).abs().mean())
+            acc["recon_rmse_local"] += float(torch.sqrt(losses.local_loss(ground, out, m, "mse") + eps))
+            acc["recon_l1_local"] += float(losses.local_loss(ground, out, m, "l1"))
+            n += 1
+    return {k: v / n for k, v in acc.items()}
+
+
 def wgan_step(
     G: Params,
     D: Params,

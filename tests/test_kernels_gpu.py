@@ -338,6 +338,32 @@ def test_dropout_rate_and_determinism(dev):
     assert set(a.float().unique().tolist()) == {0.0, 2.0}  # Dropout(0.5) scales kept values by 2
 
 
+def test_dropout_device_seed_counter(dev):
+    """b200_set_seed_counter: the dropout seed is advanced by a device counter read when the kernel runs (what lets a captured CUDA
+    graph of the step draw fresh masks per replay); counter == 0 is the plain seed; forward and backward stay consistent."""
+    eng, lib = _eng(), _lib()
+    P, C = 2048, 256
+    y = bf(torch.ones(P, C, device=dev))
+    ctr = torch.zeros(1, dtype=torch.int32, device=dev)
+    base, a0, a1, a1b = (torch.empty_like(y) for _ in range(4))
+    eng.bn_act(y, C, None, eng.ACT_RELU, base, C, 0, dropout=True, seed=7)
+    lib.value("b200_set_seed_counter", lib.ptr(ctr))
+    try:
+        eng.bn_act(y, C, None, eng.ACT_RELU, a0, C, 0, dropout=True, seed=7)
+        lib.call("b200_step_inc", lib.ptr(ctr), lib.stream())
+        eng.bn_act(y, C, None, eng.ACT_RELU, a1, C, 0, dropout=True, seed=7)
+        eng.bn_act(y, C, None, eng.ACT_RELU, a1b, C, 0, dropout=True, seed=7)
+        # backward under the same counter regenerates the same mask: dz = keep ? 2 g : 0 with g == 1 equals the forward's output
+        sc = eng.Scratch.get(dev)
+        g = bf(torch.ones(P, C, device=dev))
+        dz = eng.bn_act_bwd(y, C, None, None, eng.ACT_RELU, g, C, 0, None, 0, 0, True, 7, None, None, False, sc)
+    finally:
+        lib.value("b200_set_seed_counter", None)
+    assert torch.equal(base, a0) and torch.equal(a1, a1b) and not torch.equal(a0, a1)
+    assert abs((a1.float() != 0).float().mean().item() - 0.5) < 0.01
+    assert torch.equal(dz, a1)
+
+
 # ------------------------------------------------------------------------------------------------ 1-channel-side convs
 @pytest.mark.parametrize("B,R,C,act,mul", [(2, 64, 64, 1, False), (3, 32, 128, 0, False), (2, 128, 64, 1, True)])
 def test_conv_c1_fwd(dev, B, R, C, act, mul):

@@ -348,6 +348,8 @@ def test_begin_call_surface(dev, tmp_path):
     assert not any("bias" in n for n in h[0]["gradients"]["avg_d"])
     sd = torch.load(tmp_path / "model" / "epoch1_G.pt")
     assert set(sd) == set(nets.init_unet(0))
+    ev = out["eval_history"]  # evaluate.calculate_metric on both loaders after epoch 1 (wgan_l1.py:251-259)
+    assert len(ev) == 1 and set(ev[0]) == {"train", "test"} and ev[0]["test"]["recon_l1_local"] > 0 and ev[0]["test"]["fid"] == -1
     out = minimaxgan_rmse.begin(dict(state, numepoch=0), {"train": batches, "test": batches, "extra": batches})
     h = out["history"]
     assert out["g_iter"] == 3 and h[0]["g"]["update_count"] == 3 and h[0]["g"]["total"] > 0
@@ -368,3 +370,84 @@ def test_device_prefetcher_feeds_identical_batches(dev):
     assert [t for _, _, t in seen] == list(range(5))
     for (g, m, _), (hg, hm, _) in zip(seen, batches):
         assert torch.equal(g.cpu(), hg) and torch.equal(m.cpu(), hm)
+
+
+@pytest.mark.parametrize("recipe", ["wgan", "minimax"])
+def test_graph_replayed_step_equals_eager_step(dev, recipe):
+    """InpaintingTrainer(graph=True): the first batch runs eagerly, the step is captured into a CUDA graph, later batches replay
+    it.  The kernels are deterministic, so with dropout off four steps (one eager + three replays, fresh inputs copied into the
+    static buffers, WGAN: alternating D-only / full steps = two graphs) leave bit-identical weights, statistics and scalars."""
+    trainer, nets, steps, synth = _imports()
+    R, B = 128, 4
+    gp, dp = nets.init_unet(0), nets.init_patchgan(1, res=R)
+    sig = recipe != "wgan"
+    batches = [tuple(t.to(dev) for t in synth.make_batch(B, R, seed=70 + i)) for i in range(6)]
+    sched = [True, True, False, True, False, True] if recipe == "wgan" else [True] * 6
+    nets_out, scal, launches = [], [], []
+    from gan_inpainting_b200 import _lib
+    for graph in (False, True):
+        G, D = make_G(dev, gp).train(), make_D(dev, dp, R, sig).train()
+        tr = trainer.InpaintingTrainer(recipe, G, D, recon="l1", graph=graph)
+        per_step = []
+        for (g, m), upd in zip(batches, sched):
+            n0 = _lib.value("b200_launch_count")
+            tr.step(g, m, update_g=upd)
+            launches.append(_lib.value("b200_launch_count") - n0)
+            per_step.append(tr.scalars.clone())
+        torch.cuda.synchronize()
+        nets_out.append((G.state_dict(), D.state_dict()))
+        scal.append(per_step)
+        if graph:
+            assert len(tr._graphs) == (2 if recipe == "wgan" else 1)
+            assert torch.equal(tr.last["inpainted"], last_inp)
+        else:
+            last_inp = tr.last["inpainted"].clone()
+    n = len(sched)
+    # a replayed graph accounts for the kernels it re-launches (bench.py's gpu_launches): the eager count +1 (seed counter) and
+    # +-2 for the weight re-packs that depend on what ran before
+    assert all(abs(a - b) <= 4 for a, b in zip(launches[:n], launches[n:])), launches
+    for a, b in zip(scal[0], scal[1]):
+        assert torch.equal(a, b)
+    for sd_a, sd_b in zip(nets_out[0], nets_out[1]):
+        for k in sd_a:
+            assert torch.equal(sd_a[k], sd_b[k]), k
+
+
+def test_graph_replay_draws_fresh_dropout_masks(dev):
+    """With dropout on (the reference default) every replay must use a new mask: the device seed counter the
+    graph increments.  Same weights (lr = 0 is not available, so compare the dropout layer's zero pattern) on the same batch."""
+    trainer, nets, steps, synth = _imports()
+    R, B = 128, 2
+    G = make_G(dev, nets.init_unet(0), dropout=True).train()
+    D = make_D(dev, nets.init_patchgan(1, res=R), R, False).train()
+    tr = trainer.InpaintingTrainer("wgan", G, D, graph=True)
+    g, m = (t.to(dev) for t in synth.make_batch(B, R, seed=80))
+    w = G._cfg["widths"]
+    pats = []
+    for i in range(4):
+        tr.step(g, m)
+        cat = tr.last["ctx"]["G"].cat[5]  # up half = relu(dropout(bn(yu6))): zero where dropped (or negative)
+        pats.append((cat[..., w[4]:] == 0).clone())
+    assert len(tr._graphs) == 1
+    for i in range(1, 4):
+        for j in range(i):
+            differ = (pats[i] != pats[j]).float().mean().item()
+            assert differ > 0.2, (i, j, differ)
+
+
+@pytest.mark.parametrize("flip", [False, True])
+def test_calculate_metric_matches_oracle(dev, flip):
+    """lib.models.evaluate.calculate_metric (the train-time evaluation pass, evaluate.py:87-177 / wgan_l1.py:251-259): global and
+    masked L1 / RMSE over a loader of (ground, mask, segment) host batches, against the oracle's restatement."""
+    from gan_inpainting_b200.lib.models import evaluate
+    trainer, nets, steps, synth = _imports()
+    gp = nets.init_unet(0)
+    G = make_G(dev, gp).train()
+    batches = [synth.make_batch(3, 128, seed=90 + i, soft_edge=(i == 1)) + (None,) for i in range(3)]
+    got = evaluate.calculate_metric(dev, batches, G, fid_stats=(-1, -1), mode="test", inception_model=None, epoch=7, is_flip_mask=flip)
+    ref = steps.calculate_metric({k: v.clone() for k, v in gp.items()}, batches, is_flip_mask=flip, train_mode=True)
+    for k, v in ref.items():
+        assert close(got[k], v, TOL), (k, got[k], v)
+    assert got["fid"] == -1 and got["epoch"] == 7
+    with pytest.raises(ValueError):
+        evaluate.calculate_metric(dev, [], G)
