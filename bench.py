@@ -304,9 +304,20 @@ def run_b200(args):
     if dist:
         dist.barrier()
 
-    if rank != 0:
+    def teardown():
+        # captured NCCL collectives pin the communicator: drop the step graphs first; a watchdog guarantees that a teardown problem
+        # can never hang the job after the result line has been printed
+        t = threading.Timer(30.0, lambda: os._exit(0))
+        t.daemon = True
+        t.start()
+        tr.release_graphs()
         if dist:
+            dist.barrier()
             dist.destroy_process_group()
+        t.cancel()
+
+    if rank != 0:
+        teardown()
         return
     peaks = measured_peaks()
     fl = flops_per_image(R, args.recipe)
@@ -353,8 +364,7 @@ def run_b200(args):
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
-    if dist:
-        dist.destroy_process_group()
+    teardown()
 
 
 def main():

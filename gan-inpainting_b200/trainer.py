@@ -242,6 +242,20 @@ class InpaintingTrainer:
         self.last = cs.last
         return self.scalars
 
+    def release_graphs(self):
+        """Destroy the captured step graphs.  MUST run before ``torch.distributed.destroy_process_group()``: NCCL keeps a
+        communicator alive (and its destruction waits) while CUDA graphs holding captured collectives exist."""
+        import gc
+
+        torch.cuda.synchronize(self.device)
+        for cs in self._graphs.values():
+            cs.graph = None
+            cs.last = None
+        self._graphs.clear()
+        self.last = None
+        gc.collect()
+        torch.cuda.synchronize(self.device)
+
     def _step_gan(self, ground, mask, update_g, seed):
         G, D, eG, eD, dev = self.G, self.D, self.eG, self.eD, self.device
         n = ground.numel()

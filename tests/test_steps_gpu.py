@@ -451,3 +451,19 @@ def test_calculate_metric_matches_oracle(dev, flip):
     assert got["fid"] == -1 and got["epoch"] == 7
     with pytest.raises(ValueError):
         evaluate.calculate_metric(dev, [], G)
+
+
+def test_two_rank_data_parallel_graph_step(dev):
+    """N > 1 on real GPUs (skipped on 1-GPU boxes; the CPU suite covers the bucketing with gloo): tools/ddp_check.py under torchrun —
+    replicas stay identical, the CUDA-graph replay (NCCL all-reduces captured) equals the eager step, the all-reduced gradient is the
+    mean of the per-shard gradients."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29611",
+           os.path.join(root, "tools", "ddp_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "DDP_CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
