@@ -1,6 +1,7 @@
 // Error reporting and library identity for the C-ABI (see include/b200_inpaint.h).
 #include "common.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 static thread_local char g_err[512] = "";
@@ -12,6 +13,14 @@ void b200_set_error(const char* msg) {
 
 static long long g_launches = 0;
 void b200_count_launch(void) { ++g_launches; }
+
+bool b200_pdl_enabled(void) {
+  static const bool on = [] {
+    const char* e = getenv("B200_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 
 static const uint32_t* g_seed_counter = nullptr;
 const uint32_t* b200_seed_counter_ptr(void) { return g_seed_counter; }

@@ -23,9 +23,39 @@
 
 void b200_set_error(const char* msg);
 void b200_count_launch(void);
+bool b200_pdl_enabled(void);  // programmatic dependent launch for every kernel of this library (env B200_PDL=0 turns it off)
 const uint32_t* b200_seed_counter_ptr(void);  // device counter added to every dropout seed (null: none)
 
 namespace b200 {
+
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of this library is launched with cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs may be scheduled while
+// the previous kernel in the stream is still draining (launch latency, block scheduling and the prologue overlap the predecessor's
+// tail), and `griddepcontrol.wait` holds them until the predecessor has completed and its writes are visible.  The rule that keeps
+// this safe: NO global memory access before pdl_wait().  The trigger directly follows the wait, so a kernel can never run ahead of
+// its grand-predecessor.  One step is ~210 dependent kernels of 5-250 us: the hand-over time is a few percent of the step.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+  pdl_wait();
+  pdl_trigger();
+}
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = b200_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define B200_LAUNCH(kernel, grid, block, smem, stream, ...) b200::launch_pdl(kernel, dim3(grid), dim3(block), (size_t)(smem), stream, ##__VA_ARGS__)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -34,6 +34,7 @@ template <int C>
 __global__ void __launch_bounds__(256, 3) conv_c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ xmul, int B, int H, int W, int tow_shift,
                                                              const float* __restrict__ w, int act, __nv_bfloat16* __restrict__ y,
                                                              __nv_bfloat16* __restrict__ y2, int ld2, int off2) {
+  b200::pdl_enter();
   constexpr int NT = C / 8;   // n-tiles
   constexpr int CPL = C / 4;  // consecutive channels per lane
   __shared__ __align__(16) float xs[2][kXsFloats];
@@ -174,6 +175,7 @@ template <int C>
 __global__ void __launch_bounds__(256, 2) convt_c1_fwd_kernel(const __nv_bfloat16* __restrict__ z, int B, int H, int W, int ldz, const float* __restrict__ w,
                                                            const float* __restrict__ bias, int act, const float* __restrict__ base,
                                                            const float* __restrict__ mul, float* __restrict__ y, float* __restrict__ comp) {
+  b200::pdl_enter();
   constexpr int NG = C / 32;  // 32-channel groups
   __shared__ float T[kTH * kTH][17];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -303,6 +305,7 @@ constexpr int kWgTH = 4, kWgTW = 32, kWgStride = 2 * kWgTW + 4, kWgRows = 2 * kW
 template <int C>
 __global__ void __launch_bounds__(256) wgrad_c1_kernel(const __nv_bfloat16* __restrict__ z, int B, int H, int W, int ldz, const float* __restrict__ g,
                                                        const float* __restrict__ gmul, float* __restrict__ partial) {
+  b200::pdl_enter();
   constexpr int NT = C / 8;
   constexpr int ROWB = (C + 8) * 2;              // padded shared-memory row (bytes): conflict-free ldmatrix
   constexpr int ZBYTES = kWgTH * kWgTW * ROWB;   // one stage of z
@@ -411,6 +414,7 @@ __global__ void __launch_bounds__(256) wgrad_c1_kernel(const __nv_bfloat16* __re
 
 // out[k] (+)= sum_b partial[b][k]: block = 32 outputs, warp w sums rows w, w+8, ... (fp64), fixed-order combine (deterministic)
 __global__ void __launch_bounds__(256) partial_sum_kernel(const float* __restrict__ partial, int nblk, int n, float* __restrict__ out, int accumulate) {
+  b200::pdl_enter();
   __shared__ double red[8][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = blockIdx.x * 32 + lane;
@@ -432,6 +436,7 @@ __global__ void __launch_bounds__(256) partial_sum_kernel(const float* __restric
 // ------------------------------------------------------------------------------------------------
 // E[h][w][c] = sum_{kh,kw} W5[c][kh][kw] * Wl[(h-kh)*n + (w-kw)],  n = S-3
 __global__ void head_weight_kernel(const float* __restrict__ w5, const float* __restrict__ wl, int S, int C, float* __restrict__ E) {
+  b200::pdl_enter();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= S * S * C) return;
   const int c = idx % C, wq = (idx / C) % S, h = idx / (C * S);
@@ -453,6 +458,7 @@ __global__ void head_weight_kernel(const float* __restrict__ w5, const float* __
 
 // partial[b][blockIdx.x] = sum over this block's slice of a[b,:] * E[:]
 __global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __restrict__ a, const float* __restrict__ E, int n, float* __restrict__ partial) {
+  b200::pdl_enter();
   const int b = blockIdx.y;
   const __nv_bfloat16* ab = a + (size_t)b * n;
   float s = 0.f;
@@ -475,6 +481,7 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const __nv_bfloat16* __re
 
 __global__ void head_finalize_kernel(const float* __restrict__ partial, int nsplit, int B, const float* __restrict__ bias, int sigmoid,
                                      float* __restrict__ lin, float* __restrict__ pred) {
+  b200::pdl_enter();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   float s = 0.f;
@@ -486,6 +493,7 @@ __global__ void head_finalize_kernel(const float* __restrict__ partial, int nspl
 
 // dlin[b] = dpred[b] * (sigmoid ? p(1-p) : 1)
 __global__ void head_dlin_kernel(const float* __restrict__ dpred, const float* __restrict__ pred, int sigmoid, int B, float* __restrict__ dlin) {
+  b200::pdl_enter();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const float p = pred[b];
@@ -495,6 +503,7 @@ __global__ void head_dlin_kernel(const float* __restrict__ dpred, const float* _
 // da[b][k] = dlin[b] * E[k]
 __global__ void __launch_bounds__(256) head_bwd_input_kernel(const float* __restrict__ dlin, const float* __restrict__ E, int n, int B,
                                                              __nv_bfloat16* __restrict__ da) {
+  b200::pdl_enter();
   const long long total = (long long)B * (n >> 3);
   for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
     const int b = (int)(idx / (n >> 3));
@@ -509,6 +518,7 @@ __global__ void __launch_bounds__(256) head_bwd_input_kernel(const float* __rest
 // dE[k] = sum_b dlin[b] * a[b][k]
 __global__ void __launch_bounds__(256) head_bwd_dE_kernel(const float* __restrict__ dlin, const __nv_bfloat16* __restrict__ a, int n, int B,
                                                           float* __restrict__ dE) {
+  b200::pdl_enter();
   const int k = (blockIdx.x * 256 + threadIdx.x) * 8;
   if (k >= n) return;
   float s[8];
@@ -535,6 +545,7 @@ __global__ void __launch_bounds__(256) head_bwd_dE_kernel(const float* __restric
 // block = (tap, 32 channels); warp w walks output rows w, w+8, ...; lane = channel (coalesced 128-byte reads of dE)
 __global__ void __launch_bounds__(256) head_bwd_w5_kernel(const float* __restrict__ dE, const float* __restrict__ wl, int S, int C, float* __restrict__ dw5,
                                                           int accumulate) {
+  b200::pdl_enter();
   __shared__ float red[8][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane, tap = blockIdx.y;
@@ -560,6 +571,7 @@ __global__ void __launch_bounds__(256) head_bwd_w5_kernel(const float* __restric
 // blockIdx.x == n*n computes dbias = sum_b dlin[b].
 __global__ void __launch_bounds__(256) head_bwd_wl_kernel(const float* __restrict__ dE, const float* __restrict__ w5, const float* __restrict__ dlin, int B,
                                                           int S, int C, float* __restrict__ dwl, float* __restrict__ dbias, int accumulate) {
+  b200::pdl_enter();
   const int n = S - 3;
   __shared__ float red[8];
   float s = 0.f;
@@ -602,9 +614,9 @@ int b200_conv_c1_fwd(const float* x, const float* xmul, int B, int H, int W, con
   const int ntiles = B * (Ho / TOH) * (Wo / TOW);
   const int grid = ntiles < 148 * 3 ? ntiles : 148 * 3;  // persistent: three resident blocks per SM
   if (C == 64)
-    conv_c1_fwd_kernel<64><<<grid, 256, 0, stream>>>(x, xmul, B, H, W, tow_shift, w, act, (__nv_bfloat16*)y, (__nv_bfloat16*)y2, ld2, off2);
+    B200_LAUNCH((conv_c1_fwd_kernel<64>), grid, 256, 0, stream, x, xmul, B, H, W, tow_shift, w, act, (__nv_bfloat16*)y, (__nv_bfloat16*)y2, ld2, off2);
   else
-    conv_c1_fwd_kernel<128><<<grid, 256, 0, stream>>>(x, xmul, B, H, W, tow_shift, w, act, (__nv_bfloat16*)y, (__nv_bfloat16*)y2, ld2, off2);
+    B200_LAUNCH((conv_c1_fwd_kernel<128>), grid, 256, 0, stream, x, xmul, B, H, W, tow_shift, w, act, (__nv_bfloat16*)y, (__nv_bfloat16*)y2, ld2, off2);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -617,9 +629,9 @@ int b200_convt_c1_fwd(const void* z, int B, int H, int W, int C, int ldz, const 
   }
   const int grid = B * (H / kTT) * (W / kTT);
   if (C == 64)
-    convt_c1_fwd_kernel<64><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)z, B, H, W, ldz, w, bias, act, base, mul, y, comp);
+    B200_LAUNCH((convt_c1_fwd_kernel<64>), grid, 256, 0, stream, (const __nv_bfloat16*)z, B, H, W, ldz, w, bias, act, base, mul, y, comp);
   else
-    convt_c1_fwd_kernel<128><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)z, B, H, W, ldz, w, bias, act, base, mul, y, comp);
+    B200_LAUNCH((convt_c1_fwd_kernel<128>), grid, 256, 0, stream, (const __nv_bfloat16*)z, B, H, W, ldz, w, bias, act, base, mul, y, comp);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -641,11 +653,11 @@ int b200_wgrad_c1(const void* z, int B, int H, int W, int C, int ldz, const floa
     cudaFuncSetAttribute(wgrad_c1_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   });
   if (C == 64)
-    wgrad_c1_kernel<64><<<nblk, 256, smem, stream>>>((const __nv_bfloat16*)z, B, H, W, ldz, g, gmul, partial);
+    B200_LAUNCH((wgrad_c1_kernel<64>), nblk, 256, smem, stream, (const __nv_bfloat16*)z, B, H, W, ldz, g, gmul, partial);
   else
-    wgrad_c1_kernel<128><<<nblk, 256, smem, stream>>>((const __nv_bfloat16*)z, B, H, W, ldz, g, gmul, partial);
+    B200_LAUNCH((wgrad_c1_kernel<128>), nblk, 256, smem, stream, (const __nv_bfloat16*)z, B, H, W, ldz, g, gmul, partial);
   B200_CHECK_LAUNCH();
-  partial_sum_kernel<<<(C * 16 + 31) / 32, 256, 0, stream>>>(partial, nblk, C * 16, dw, accumulate);
+  B200_LAUNCH((partial_sum_kernel), (C * 16 + 31) / 32, 256, 0, stream, partial, nblk, C * 16, dw, accumulate);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -655,7 +667,7 @@ int b200_head_weight(const float* w5, const float* wl, int S, int C, float* E, c
     b200_set_error("head_weight: feature map smaller than the 4x4 kernel");
     return B200_ERR_ARG;
   }
-  head_weight_kernel<<<(S * S * C + 255) / 256, 256, 0, stream>>>(w5, wl, S, C, E);
+  B200_LAUNCH((head_weight_kernel), (S * S * C + 255) / 256, 256, 0, stream, w5, wl, S, C, E);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -667,15 +679,15 @@ int b200_head_fwd(const void* a, const float* E, int B, int n, const float* bias
     b200_set_error("head_fwd: n must be a multiple of 8");
     return B200_ERR_ARG;
   }
-  head_fwd_kernel<<<dim3(B200_HEAD_SPLIT, B), 256, 0, stream>>>((const __nv_bfloat16*)a, E, n, scratch);
+  B200_LAUNCH((head_fwd_kernel), dim3(B200_HEAD_SPLIT, B), 256, 0, stream, (const __nv_bfloat16*)a, E, n, scratch);
   B200_CHECK_LAUNCH();
-  head_finalize_kernel<<<(B + 127) / 128, 128, 0, stream>>>(scratch, B200_HEAD_SPLIT, B, bias, sigmoid, lin, pred);
+  B200_LAUNCH((head_finalize_kernel), (B + 127) / 128, 128, 0, stream, scratch, B200_HEAD_SPLIT, B, bias, sigmoid, lin, pred);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
 
 int b200_head_dlin(const float* dpred, const float* pred, int sigmoid, int B, float* dlin, cudaStream_t stream) {
-  head_dlin_kernel<<<(B + 127) / 128, 128, 0, stream>>>(dpred, pred, sigmoid, B, dlin);
+  B200_LAUNCH((head_dlin_kernel), (B + 127) / 128, 128, 0, stream, dpred, pred, sigmoid, B, dlin);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -683,7 +695,7 @@ int b200_head_dlin(const float* dpred, const float* pred, int sigmoid, int B, fl
 int b200_head_bwd_input(const float* dlin, const float* E, int B, int n, void* da, cudaStream_t stream) {
   long long blocks = ((long long)B * (n / 8) + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  head_bwd_input_kernel<<<(int)blocks, 256, 0, stream>>>(dlin, E, n, B, (__nv_bfloat16*)da);
+  B200_LAUNCH((head_bwd_input_kernel), (int)blocks, 256, 0, stream, dlin, E, n, B, (__nv_bfloat16*)da);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -692,12 +704,12 @@ int b200_head_bwd_input(const float* dlin, const float* E, int B, int n, void* d
 int b200_head_bwd_params(const float* dlin, const void* a, int B, int S, int C, const float* w5, const float* wl, float* dE, float* dw5, float* dwl,
                          float* dbias, int accumulate, cudaStream_t stream) {
   const int n = S * S * C;
-  head_bwd_dE_kernel<<<(n / 8 + 255) / 256, 256, 0, stream>>>(dlin, (const __nv_bfloat16*)a, n, B, dE);
+  B200_LAUNCH((head_bwd_dE_kernel), (n / 8 + 255) / 256, 256, 0, stream, dlin, (const __nv_bfloat16*)a, n, B, dE);
   B200_CHECK_LAUNCH();
-  head_bwd_w5_kernel<<<dim3((C + 31) / 32, 16), 256, 0, stream>>>(dE, wl, S, C, dw5, accumulate);
+  B200_LAUNCH((head_bwd_w5_kernel), dim3((C + 31) / 32, 16), 256, 0, stream, dE, wl, S, C, dw5, accumulate);
   B200_CHECK_LAUNCH();
   const int nn = (S - 3) * (S - 3);
-  head_bwd_wl_kernel<<<nn + 1, 256, 0, stream>>>(dE, w5, dlin, B, S, C, dwl, dbias, accumulate);
+  B200_LAUNCH((head_bwd_wl_kernel), nn + 1, 256, 0, stream, dE, w5, dlin, B, S, C, dwl, dbias, accumulate);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

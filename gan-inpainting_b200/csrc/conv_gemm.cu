@@ -294,6 +294,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) touched no global memory
+  // and may overlap the previous kernel's tail; from here on its results are needed
+  pdl_enter();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -615,6 +618,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 // out[pix][c] (bf16, pixel stride ldy) = sum_ks partial[ks][pix][c]
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int ksplit, long long P, int C, __nv_bfloat16* __restrict__ out,
                                                             int ldy) {
+  b200::pdl_enter();
   const long long chunks = P * (C >> 3);
   const long long stride = (long long)P * C;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < chunks; idx += (long long)gridDim.x * blockDim.x) {
@@ -633,6 +637,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 // Debug aid: load one TMA box into shared memory and copy the raw (swizzled) bytes out.
 __global__ void tma_probe_kernel(const __grid_constant__ CUtensorMap tm, int rank, int c0, int c1, int c2, int c3, int c4, int bytes,
                                  uint8_t* out) {
+  b200::pdl_enter();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar;
@@ -735,19 +740,21 @@ static void launch_variant(const CUtensorMap& a, const CUtensorMap& b, const IGe
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = b200_pdl_enabled() ? 2 : 1;
     cudaLaunchKernelEx(&cfg, igemm_kernel<E, true>, a, b, p);
     return;
   }
   static std::once_flag once;
   std::call_once(once, [] { cudaFuncSetAttribute(igemm_kernel<E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
-  igemm_kernel<E, false><<<grid, kThreads, smem, stream>>>(a, b, p);
+  B200_LAUNCH((igemm_kernel<E, false>), grid, kThreads, smem, stream, a, b, p);
 }
 
 // CTA pairs pay when the single-CTA tiles are bound by operand traffic: fprop / dgrad with enough pixel tiles to give every
@@ -1057,7 +1064,7 @@ int b200_splitk_reduce(const float* partial, int ksplit, long long P, int C, voi
   }
   long long blocks = (P * (C >> 3) + 255) / 256;
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  splitk_reduce_kernel<<<(int)blocks, 256, 0, stream>>>(partial, ksplit, P, C, (__nv_bfloat16*)out, ldy);
+  B200_LAUNCH((splitk_reduce_kernel), (int)blocks, 256, 0, stream, partial, ksplit, P, C, (__nv_bfloat16*)out, ldy);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -1074,7 +1081,7 @@ int b200_debug_tma_probe(const void* x, int B, int H, int W, int C, int kind, in
   }
   const int bytes = 128 * tw * th * nb;
   cudaFuncSetAttribute(tma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  tma_probe_kernel<<<1, 128, bytes + 1024, stream>>>(tm, kind == 0 ? 5 : 4, c0, c1, c2, c3, c4, bytes, (uint8_t*)out);
+  B200_LAUNCH((tma_probe_kernel), 1, 128, bytes + 1024, stream, tm, kind == 0 ? 5 : 4, c0, c1, c2, c3, c4, bytes, (uint8_t*)out);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

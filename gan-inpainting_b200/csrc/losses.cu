@@ -20,6 +20,7 @@ __device__ __forceinline__ float4 ld4(const float* p, long long i) { return __ld
 // mask_out = ceil ? ceil(mask) : mask ;  masked = ground * (1 - mask_out)
 __global__ void __launch_bounds__(256) mask_prepare_kernel(const float* __restrict__ ground, const float* __restrict__ mask, long long n4, int do_ceil,
                                                            float* __restrict__ mask_out, float* __restrict__ masked) {
+  b200::pdl_enter();
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
     float4 m = ld4(mask, i);
     const float4 g = ld4(ground, i);
@@ -37,6 +38,7 @@ __global__ void __launch_bounds__(256) mask_prepare_kernel(const float* __restri
 // out = base + g * mask
 __global__ void __launch_bounds__(256) composite_kernel(const float* __restrict__ base, const float* __restrict__ g, const float* __restrict__ mask,
                                                         long long n4, float* __restrict__ out) {
+  b200::pdl_enter();
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
     const float4 b = ld4(base, i), v = ld4(g, i), m = ld4(mask, i);
     reinterpret_cast<float4*>(out)[i] = make_float4(fmaf(v.x, m.x, b.x), fmaf(v.y, m.y, b.y), fmaf(v.z, m.z, b.z), fmaf(v.w, m.w, b.w));
@@ -45,6 +47,7 @@ __global__ void __launch_bounds__(256) composite_kernel(const float* __restrict_
 
 // out = a * b
 __global__ void __launch_bounds__(256) mul_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n4, float* __restrict__ out) {
+  b200::pdl_enter();
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
     const float4 x = ld4(a, i), y = ld4(b, i);
     reinterpret_cast<float4*>(out)[i] = make_float4(x.x * y.x, x.y * y.y, x.z * y.z, x.w * y.w);
@@ -73,6 +76,7 @@ __device__ __forceinline__ void recon_term(int kind, float y, float yh, float m,
 // partial[blk][2] = (sum, count)
 __global__ void __launch_bounds__(256) recon_reduce_kernel(int kind, const float* __restrict__ y, const float* __restrict__ yh, const float* __restrict__ mask,
                                                            long long n4, float* __restrict__ partial) {
+  b200::pdl_enter();
   float s = 0.f, c = 0.f;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
     const float4 a = ld4(y, i), b = ld4(yh, i);
@@ -104,6 +108,7 @@ __global__ void __launch_bounds__(256) recon_reduce_kernel(int kind, const float
 
 // out[0] = loss, out[1] = denominator as float, out[2..3] = exact (mask != 0) pixel count (LocalLoss) or N as two int words
 __global__ void recon_finalize_kernel(int kind, const float* __restrict__ partial, int nblk, double n, float eps, float* __restrict__ out) {
+  b200::pdl_enter();
   // one warp: lane-strided fp64 partial sums in a fixed order, then a fixed shuffle tree (deterministic)
   double s = 0.0, c = 0.0;
   for (int b = threadIdx.x; b < nblk; b += 32) {
@@ -180,6 +185,7 @@ __device__ __forceinline__ float recon_grad(int kind, float y, float yh, float m
 }
 
 __global__ void __launch_bounds__(256) gstep_seed_kernel(const SeedParams p, float inv_n) {
+  b200::pdl_enter();
   float bsum = 0.f;
   float l1 = 1.f, c1 = 1.f, l2 = 1.f, c2 = 1.f;
   if (p.kind1 >= 0) {
@@ -248,6 +254,7 @@ __global__ void __launch_bounds__(256) gstep_seed_kernel(const SeedParams p, flo
 }
 
 __global__ void scalar_sum_kernel(const float* __restrict__ partial, int nblk, float* __restrict__ out, int accumulate) {
+  b200::pdl_enter();
   double s = 0.0;
   for (int b = threadIdx.x; b < nblk; b += 32) s += (double)partial[b];
   s = warp_sum_d(s);
@@ -258,6 +265,7 @@ __global__ void scalar_sum_kernel(const float* __restrict__ partial, int nblk, f
 // adversarial heads on pred[B]:  loss_out[0] = loss;  dpred[b] = scale * d loss / d pred[b]
 __global__ void __launch_bounds__(256) adv_loss_kernel(const float* __restrict__ pred, int B, int mode, float target, float scale, float* __restrict__ loss_out,
                                                        float* __restrict__ dpred) {
+  b200::pdl_enter();
   float s = 0.f;
   const float invB = 1.f / (float)B;
   for (int b = threadIdx.x; b < B; b += 256) {
@@ -311,21 +319,21 @@ int b200_recon_scratch_floats(void) { return 2 * kRedBlocks; }
 
 int b200_mask_prepare(const float* ground, const float* mask, long long n, int do_ceil, float* mask_out, float* masked, cudaStream_t stream) {
   B200_REQUIRE_N4(n);
-  mask_prepare_kernel<<<ew_grid(n / 4), 256, 0, stream>>>(ground, mask, n / 4, do_ceil, mask_out, masked);
+  B200_LAUNCH((mask_prepare_kernel), ew_grid(n / 4), 256, 0, stream, ground, mask, n / 4, do_ceil, mask_out, masked);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
 
 int b200_composite(const float* base, const float* g, const float* mask, long long n, float* out, cudaStream_t stream) {
   B200_REQUIRE_N4(n);
-  composite_kernel<<<ew_grid(n / 4), 256, 0, stream>>>(base, g, mask, n / 4, out);
+  B200_LAUNCH((composite_kernel), ew_grid(n / 4), 256, 0, stream, base, g, mask, n / 4, out);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
 
 int b200_mul(const float* a, const float* b, long long n, float* out, cudaStream_t stream) {
   B200_REQUIRE_N4(n);
-  mul_kernel<<<ew_grid(n / 4), 256, 0, stream>>>(a, b, n / 4, out);
+  B200_LAUNCH((mul_kernel), ew_grid(n / 4), 256, 0, stream, a, b, n / 4, out);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -339,9 +347,9 @@ int b200_recon_loss(int kind, const float* y, const float* yhat, const float* ma
   }
   int nblk = ew_grid(n / 4);
   if (nblk > kRedBlocks) nblk = kRedBlocks;
-  recon_reduce_kernel<<<nblk, 256, 0, stream>>>(kind, y, yhat, mask, n / 4, scratch);
+  B200_LAUNCH((recon_reduce_kernel), nblk, 256, 0, stream, kind, y, yhat, mask, n / 4, scratch);
   B200_CHECK_LAUNCH();
-  recon_finalize_kernel<<<1, 32, 0, stream>>>(kind, scratch, nblk, (double)n, eps, out);
+  B200_LAUNCH((recon_finalize_kernel), 1, 32, 0, stream, kind, scratch, nblk, (double)n, eps, out);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -357,17 +365,17 @@ int b200_gstep_seed(const float* ground, const float* inp, const float* g, const
   SeedParams p{ground, inp, g, mask, dadv1, dadv2, kind1, kind2, lambda1, lambda2, loss1, loss2, gscale, composite, n / 4, dpre, dinp, dbias ? scratch : nullptr};
   int nblk = ew_grid(n / 4);
   if (nblk > kRedBlocks) nblk = kRedBlocks;
-  gstep_seed_kernel<<<nblk, 256, 0, stream>>>(p, (float)(1.0 / (double)n));
+  B200_LAUNCH((gstep_seed_kernel), nblk, 256, 0, stream, p, (float)(1.0 / (double)n));
   B200_CHECK_LAUNCH();
   if (dbias) {
-    scalar_sum_kernel<<<1, 32, 0, stream>>>(scratch, nblk, dbias, accumulate);
+    B200_LAUNCH((scalar_sum_kernel), 1, 32, 0, stream, scratch, nblk, dbias, accumulate);
     B200_CHECK_LAUNCH();
   }
   return B200_OK;
 }
 
 int b200_adv_loss(const float* pred, int B, int mode, float target, float scale, float* loss_out, float* dpred, cudaStream_t stream) {
-  adv_loss_kernel<<<1, 256, 0, stream>>>(pred, B, mode, target, scale, loss_out, dpred);
+  B200_LAUNCH((adv_loss_kernel), 1, 256, 0, stream, pred, B, mode, target, scale, loss_out, dpred);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

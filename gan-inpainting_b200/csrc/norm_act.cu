@@ -18,6 +18,7 @@ constexpr int kStatThreads = 256;
 // ---------------------------------------------------------------- statistics: sum, sum of squares per channel
 // partial[blk][2][C].  C is a power of two (chunk index by mask / shift, no integer division in the loop).
 __global__ void __launch_bounds__(kStatThreads) bn_stats_kernel(const __nv_bfloat16* __restrict__ y, int P, int C, int cshift, float* __restrict__ partial) {
+  b200::pdl_enter();
   const int chunks = C >> 3;                // 8-channel chunks per pixel
   const int lanes = kStatThreads >> cshift;  // pixel lanes per block
   const int chunk = threadIdx.x & (chunks - 1);
@@ -120,6 +121,7 @@ __global__ void __launch_bounds__(kFinThreads) bn_finalize_kernel(const float* _
                                                                   float* __restrict__ running_mean, float* __restrict__ running_var,
                                                                   long long* __restrict__ num_batches_tracked, float momentum, float eps,
                                                                   float* __restrict__ stats_out) {
+  b200::pdl_enter();
   double s, q;
   reduce_partials(partial, nblk, C, blockIdx.x * 32 + (threadIdx.x & 31), s, q);
   const int c = blockIdx.x * 32 + (threadIdx.x >> 3);
@@ -145,6 +147,7 @@ __global__ void __launch_bounds__(kFinThreads) bn_finalize_kernel(const float* _
 // eval-mode: scale/shift from the running statistics.
 __global__ void bn_eval_coeffs_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ running_mean,
                                       const float* __restrict__ running_var, float eps, float* __restrict__ stats_out) {
+  b200::pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float rstd = 1.f / sqrtf(running_var[c] + eps);
@@ -174,6 +177,7 @@ struct ApplyParams {
 };
 
 __global__ void __launch_bounds__(256) bn_act_kernel(const ApplyParams p) {
+  b200::pdl_enter();
   const unsigned total = (unsigned)p.P << p.cshift;
   const unsigned cmask = (1u << p.cshift) - 1u;
   const uint32_t seed = p.dropout ? dropout_seed(p.seed, p.seed_ctr) : 0u;
@@ -300,6 +304,7 @@ __device__ __forceinline__ void compute_dz(const BwdParams& p, size_t pix, int c
 }
 
 __global__ void __launch_bounds__(kStatThreads) bn_bwd_reduce_kernel(const BwdParams p) {
+  b200::pdl_enter();
   const int chunks = p.C >> 3;
   const int lanes = kStatThreads >> p.cshift;
   const int chunk = threadIdx.x & (chunks - 1);
@@ -340,6 +345,7 @@ __global__ void __launch_bounds__(kFinThreads) bn_bwd_finalize_kernel(const floa
                                                                       const float* __restrict__ stats, const float* __restrict__ gamma,
                                                                       float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate,
                                                                       float* __restrict__ coef, int row_stride, int k_stride) {
+  b200::pdl_enter();
   double sdz, sdzy;
   reduce_partials(partial, nblk, C, blockIdx.x * 32 + (threadIdx.x & 31), sdz, sdzy, row_stride, k_stride);
   const int c = blockIdx.x * 32 + (threadIdx.x >> 3);
@@ -365,6 +371,7 @@ __global__ void __launch_bounds__(kFinThreads) bn_bwd_finalize_kernel(const floa
 // dy = kdz*dz + ky*y + k0 with dz read as fp32 (the unrounded output of a fused GEMM epilogue)
 __global__ void __launch_bounds__(256) bn_bwd_apply_f32_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ dz, int lddz, int offdz, int P,
                                                                int C, int cshift, const float* __restrict__ coef, __nv_bfloat16* __restrict__ dy) {
+  b200::pdl_enter();
   const unsigned total = (unsigned)P << cshift;
   const unsigned cmask = (1u << cshift) - 1u;
   for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -389,6 +396,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_f32_kernel(const __nv_bfloat
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdParams p) {
+  b200::pdl_enter();
   const unsigned total = (unsigned)p.P << p.cshift;
   const unsigned cmask = (1u << p.cshift) - 1u;
   for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -451,9 +459,9 @@ int b200_bn_stats(const void* y, long long P, int C, void* partial, const float*
     return B200_ERR_ARG;
   }
   const int nblk = b200_bn_stat_blocks(P, C);
-  bn_stats_kernel<<<nblk, kStatThreads, 0, stream>>>((const __nv_bfloat16*)y, (int)P, C, cs, (float*)partial);
+  B200_LAUNCH((bn_stats_kernel), nblk, kStatThreads, 0, stream, (const __nv_bfloat16*)y, (int)P, C, cs, (float*)partial);
   B200_CHECK_LAUNCH();
-  bn_finalize_kernel<<<(C + 31) / 32, kFinThreads, 0, stream>>>((const float*)partial, nblk, C, (double)P, gamma, beta, running_mean, running_var,
+  B200_LAUNCH((bn_finalize_kernel), (C + 31) / 32, kFinThreads, 0, stream, (const float*)partial, nblk, C, (double)P, gamma, beta, running_mean, running_var,
                                                                 num_batches_tracked, momentum, eps, stats_out);
   B200_CHECK_LAUNCH();
   return B200_OK;
@@ -466,7 +474,7 @@ int b200_bn_finalize(const float* partial, int rows, long long P, int C, const f
     b200_set_error("bn_finalize: bad sizes");
     return B200_ERR_ARG;
   }
-  bn_finalize_kernel<<<(C + 31) / 32, kFinThreads, 0, stream>>>(partial, rows, C, (double)P, gamma, beta, running_mean, running_var, num_batches_tracked, momentum,
+  B200_LAUNCH((bn_finalize_kernel), (C + 31) / 32, kFinThreads, 0, stream, partial, rows, C, (double)P, gamma, beta, running_mean, running_var, num_batches_tracked, momentum,
                                                                 eps, stats_out);
   B200_CHECK_LAUNCH();
   return B200_OK;
@@ -474,7 +482,7 @@ int b200_bn_finalize(const float* partial, int rows, long long P, int C, const f
 
 int b200_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps, float* stats_out,
                         cudaStream_t stream) {
-  bn_eval_coeffs_kernel<<<(C + 127) / 128, 128, 0, stream>>>(C, gamma, beta, running_mean, running_var, eps, stats_out);
+  B200_LAUNCH((bn_eval_coeffs_kernel), (C + 127) / 128, 128, 0, stream, C, gamma, beta, running_mean, running_var, eps, stats_out);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -487,7 +495,7 @@ int b200_bn_act(const void* y, long long P, int C, const float* scale, const flo
     return B200_ERR_ARG;
   }
   ApplyParams p{(const __nv_bfloat16*)y, (int)P, C, cs, scale, shift, act, (__nv_bfloat16*)out1, ld1, off1, (__nv_bfloat16*)out2, ld2, off2, dropout, seed, b200_seed_counter_ptr()};
-  bn_act_kernel<<<grid_for(P * (C >> 3), 256), 256, 0, stream>>>(p);
+  B200_LAUNCH((bn_act_kernel), grid_for(P * (C >> 3), 256), 256, 0, stream, p);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -525,13 +533,13 @@ int b200_bn_act_bwd(const void* y, long long P, int C, const float* stats /*[4][
   p.dy = (__nv_bfloat16*)dy;
   if (stats) {
     const int nblk = b200_bn_stat_blocks(P, C);
-    bn_bwd_reduce_kernel<<<nblk, kStatThreads, 0, stream>>>(p);
+    B200_LAUNCH((bn_bwd_reduce_kernel), nblk, kStatThreads, 0, stream, p);
     B200_CHECK_LAUNCH();
-    bn_bwd_finalize_kernel<<<(C + 31) / 32, kFinThreads, 0, stream>>>((const float*)partial, nblk, C, (double)P, stats, gamma, dgamma, dbeta, accumulate, coef, 0, 0);
+    B200_LAUNCH((bn_bwd_finalize_kernel), (C + 31) / 32, kFinThreads, 0, stream, (const float*)partial, nblk, C, (double)P, stats, gamma, dgamma, dbeta, accumulate, coef, 0, 0);
     B200_CHECK_LAUNCH();
     p.coef = coef;
   }
-  bn_bwd_apply_kernel<<<grid_for(P * (C >> 3), 256), 256, 0, stream>>>(p);
+  B200_LAUNCH((bn_bwd_apply_kernel), grid_for(P * (C >> 3), 256), 256, 0, stream, p);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -547,11 +555,11 @@ int b200_bn_bwd_fused(const void* y, long long P, int C, const float* stats, con
     b200_set_error("bn_bwd_fused: C must be a power of two in [8, 2048]; strides / offsets multiples of 8");
     return B200_ERR_ARG;
   }
-  bn_bwd_finalize_kernel<<<(C + 31) / 32, kFinThreads, 0, stream>>>(partial, rows, C, (double)P, stats, gamma, dgamma, dbeta, accumulate, coef, row_stride,
+  B200_LAUNCH((bn_bwd_finalize_kernel), (C + 31) / 32, kFinThreads, 0, stream, partial, rows, C, (double)P, stats, gamma, dgamma, dbeta, accumulate, coef, row_stride,
                                                                     k_stride);
   B200_CHECK_LAUNCH();
   if (dz_is_f32) {
-    bn_bwd_apply_f32_kernel<<<grid_for(P * (C >> 3), 256), 256, 0, stream>>>((const __nv_bfloat16*)y, (const float*)dz, lddz, offdz, (int)P, C, cs, coef,
+    B200_LAUNCH((bn_bwd_apply_f32_kernel), grid_for(P * (C >> 3), 256), 256, 0, stream, (const __nv_bfloat16*)y, (const float*)dz, lddz, offdz, (int)P, C, cs, coef,
                                                                               (__nv_bfloat16*)dy);
     B200_CHECK_LAUNCH();
     return B200_OK;
@@ -567,7 +575,7 @@ int b200_bn_bwd_fused(const void* y, long long P, int C, const float* stats, con
   p.offg1 = offdz;
   p.coef = coef;
   p.dy = (__nv_bfloat16*)dy;
-  bn_bwd_apply_kernel<<<grid_for(P * (C >> 3), 256), 256, 0, stream>>>(p);
+  B200_LAUNCH((bn_bwd_apply_kernel), grid_for(P * (C >> 3), 256), 256, 0, stream, p);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

@@ -11,6 +11,7 @@ namespace b200 {
 
 __global__ void __launch_bounds__(256) rmsprop_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ sq, long long n, float lr,
                                                       float alpha, float eps, int clamp, float lo, float hi) {
+  b200::pdl_enter();
   const long long n4 = n >> 2;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
     float4 w = reinterpret_cast<float4*>(p)[i];
@@ -45,7 +46,10 @@ __global__ void __launch_bounds__(256) rmsprop_kernel(float* __restrict__ p, con
 }
 
 // step_count: device int, incremented by the single-thread prologue kernel so the whole step is graph-capturable
-__global__ void step_inc_kernel(int* step_count) { *step_count += 1; }
+__global__ void step_inc_kernel(int* step_count) {
+  b200::pdl_enter();
+  *step_count += 1;
+}
 
 __device__ __forceinline__ float adam_one(float w, float d, float& m, float& v, float b1, float b2, float step_size, float inv_bc2_sqrt, float eps) {
   m = b1 * m + (1.f - b1) * d;
@@ -56,6 +60,7 @@ __device__ __forceinline__ float adam_one(float w, float d, float& m, float& v, 
 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                                    long long n, float lr, float b1, float b2, float eps, const int* __restrict__ step_count) {
+  b200::pdl_enter();
   const float t = (float)(*step_count);
   const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
   const float step_size = lr / bc1, inv_bc2_sqrt = 1.f / sqrtf(bc2);
@@ -81,11 +86,13 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 }
 
 __global__ void __launch_bounds__(256) clamp_kernel(float* __restrict__ p, long long n, float lo, float hi) {
+  b200::pdl_enter();
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) p[i] = fminf(fmaxf(p[i], lo), hi);
 }
 
 // out[t] = mean |g[off[t] .. off[t+1])|  — one block per tensor (deterministic)
 __global__ void __launch_bounds__(256) absmean_kernel(const float* __restrict__ g, const long long* __restrict__ off, float* __restrict__ out) {
+  b200::pdl_enter();
   const long long a = off[blockIdx.x], b = off[blockIdx.x + 1];
   float s = 0.f;
   for (long long i = a + threadIdx.x; i < b; i += 256) s += fabsf(g[i]);
@@ -118,13 +125,13 @@ int b200_rmsprop_step(float* p, const float* g, float* sq, long long n, float lr
     b200_set_error("rmsprop_step: buffers must be 16-byte aligned");
     return B200_ERR_ARG;
   }
-  rmsprop_kernel<<<opt_grid(n), 256, 0, stream>>>(p, g, sq, n, lr, alpha, eps, clamp, lo, hi);
+  B200_LAUNCH((rmsprop_kernel), opt_grid(n), 256, 0, stream, p, g, sq, n, lr, alpha, eps, clamp, lo, hi);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
 
 int b200_step_inc(int* step_count, cudaStream_t stream) {
-  step_inc_kernel<<<1, 1, 0, stream>>>(step_count);
+  B200_LAUNCH((step_inc_kernel), 1, 1, 0, stream, step_count);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -135,20 +142,20 @@ int b200_adam_step(float* p, const float* g, float* m, float* v, long long n, fl
     b200_set_error("adam_step: buffers must be 16-byte aligned");
     return B200_ERR_ARG;
   }
-  adam_kernel<<<opt_grid(n), 256, 0, stream>>>(p, g, m, v, n, lr, b1, b2, eps, step_count);
+  B200_LAUNCH((adam_kernel), opt_grid(n), 256, 0, stream, p, g, m, v, n, lr, b1, b2, eps, step_count);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
 
 int b200_clamp(float* p, long long n, float lo, float hi, cudaStream_t stream) {
-  clamp_kernel<<<opt_grid(n * 4), 256, 0, stream>>>(p, n, lo, hi);
+  B200_LAUNCH((clamp_kernel), opt_grid(n * 4), 256, 0, stream, p, n, lo, hi);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
 
 int b200_absmean(const float* g, const long long* offsets, int ntensors, float* out, cudaStream_t stream) {
   if (ntensors < 1) return B200_OK;
-  absmean_kernel<<<ntensors, 256, 0, stream>>>(g, offsets, out);
+  B200_LAUNCH((absmean_kernel), ntensors, 256, 0, stream, g, offsets, out);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

@@ -8,6 +8,7 @@ namespace b200 {
 // src fp32 [D0][D1][16]  ->  dst bf16 [D0][16*D1],  dst[n][t*D1 + k] = src[n][k][t]
 // (Conv2d forward operand; ConvTranspose2d data-gradient operand)
 __global__ void __launch_bounds__(256) pack_gather_kernel(const float* __restrict__ src, int D0, int D1, __nv_bfloat16* __restrict__ dst) {
+  b200::pdl_enter();
   // one block per (n, 64-wide k slab): stage 64 x 16 floats through smem so both sides are coalesced
   __shared__ float tile[64][17];
   const int n = blockIdx.y, k0 = blockIdx.x * 64;
@@ -27,6 +28,7 @@ __global__ void __launch_bounds__(256) pack_gather_kernel(const float* __restric
 //   dst[p*2+q][n][(a*2+b)*D0 + k] = src[k][n][3-p-2a][3-q-2b]
 // (ConvTranspose2d forward operand; Conv2d data-gradient operand)
 __global__ void __launch_bounds__(256) pack_phase_kernel(const float* __restrict__ src, int D0, int D1, __nv_bfloat16* __restrict__ dst) {
+  b200::pdl_enter();
   // block: 16 k x 16 n; src reads contiguous over (n, tap), dst writes contiguous over k
   __shared__ float tile[16][16 * 16 + 1];
   const int k0 = blockIdx.x * 16, n0 = blockIdx.y * 16;
@@ -54,6 +56,7 @@ struct PackEntry {
 };
 
 __global__ void __launch_bounds__(256) pack_all_kernel(const PackEntry* __restrict__ table, int nlayers) {
+  b200::pdl_enter();
   constexpr int TS = 33, RS = 16 * TS + 1;  // tile[d0][tap][d1] with padded strides (shared-memory banks)
   __shared__ float tile[16 * RS];
   int l = 0;
@@ -91,6 +94,7 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const PackEntry* __restri
 // partial fp32 [splits][Cs][16*Cl] (column = t*Cl + cl)  ->  grad fp32 [Cs][Cl][16]
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int Cs, int Cl, float* __restrict__ grad,
                                                            int accumulate) {
+  b200::pdl_enter();
   // block: one cs, 64 cl: thread (tap, cl quad) sums the splits with 128-bit loads (256-byte runs per tap), the 64 x 16 tile is
   // transposed through shared memory and written as 4 KB of contiguous floats
   __shared__ float tile[64][17];
@@ -123,7 +127,7 @@ using namespace b200;
 extern "C" {
 
 int b200_pack_gather(const float* w, int D0, int D1, void* out, cudaStream_t stream) {
-  pack_gather_kernel<<<dim3((D1 + 63) / 64, D0), 256, 0, stream>>>(w, D0, D1, (__nv_bfloat16*)out);
+  B200_LAUNCH((pack_gather_kernel), dim3((D1 + 63) / 64, D0), 256, 0, stream, w, D0, D1, (__nv_bfloat16*)out);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -133,7 +137,7 @@ int b200_pack_phase(const float* w, int D0, int D1, void* out, cudaStream_t stre
     b200_set_error("pack_phase: both channel counts must be multiples of 16");
     return B200_ERR_ARG;
   }
-  pack_phase_kernel<<<dim3(D0 / 16, D1 / 16), 256, 0, stream>>>(w, D0, D1, (__nv_bfloat16*)out);
+  B200_LAUNCH((pack_phase_kernel), dim3(D0 / 16, D1 / 16), 256, 0, stream, w, D0, D1, (__nv_bfloat16*)out);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -145,7 +149,7 @@ int b200_pack_all(const void* table, int nlayers, int total_tiles, cudaStream_t 
     b200_set_error("pack_all: empty table");
     return B200_ERR_ARG;
   }
-  pack_all_kernel<<<total_tiles, 256, 0, stream>>>((const PackEntry*)table, nlayers);
+  B200_LAUNCH((pack_all_kernel), total_tiles, 256, 0, stream, (const PackEntry*)table, nlayers);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
@@ -155,7 +159,7 @@ int b200_wgrad_reduce(const float* partial, int splits, int Cs, int Cl, float* g
     b200_set_error("wgrad_reduce: Cl must be a multiple of 64");
     return B200_ERR_ARG;
   }
-  wgrad_reduce_kernel<<<dim3(Cl / 64, Cs), 256, 0, stream>>>(partial, splits, Cs, Cl, grad, accumulate);
+  B200_LAUNCH((wgrad_reduce_kernel), dim3(Cl / 64, Cs), 256, 0, stream, partial, splits, Cs, Cl, grad, accumulate);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }
