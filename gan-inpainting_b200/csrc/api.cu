@@ -16,8 +16,10 @@ void b200_count_launch(void) { ++g_launches; }
 
 bool b200_pdl_enabled(void) {
   static const bool on = [] {
+    // measured on B200 (bench.py, step replayed as a CUDA graph): 7.44 ms/step with programmatic edges vs 7.32 ms without — the
+    // graph already hides the launch latency and early-resident dependents only add contention, so it is opt-in (B200_PDL=1)
     const char* e = getenv("B200_PDL");
-    return !(e && e[0] == '0');
+    return e && e[0] == '1';
   }();
   return on;
 }
