@@ -65,6 +65,8 @@ SIGNATURES = {
     "b200_adam_step": [P, P, P, P, L, F, F, F, F, P, S],
     "b200_clamp": [P, L, F, F, S],
     "b200_absmean": [P, P, I, P, S],
+    # ---- SSIM metric (csrc/ssim.cu)
+    "b200_ssim": [P, P, I, I, I, I, POINTER(c_float), I, P, P, S],
 }
 # helpers that return a plain value instead of a status
 VALUE_FUNCS = {
@@ -77,6 +79,7 @@ VALUE_FUNCS = {
     "b200_igemm_stat_rows": (c_int, []),
     "b200_wgrad_c1_blocks": (c_int, []),
     "b200_recon_scratch_floats": (c_int, []),
+    "b200_ssim_partials": (c_longlong, [I, I, I, I]),
 }
 
 

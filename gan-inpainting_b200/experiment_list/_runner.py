@@ -27,6 +27,7 @@ from typing import Callable, Dict, Optional
 import torch
 
 from ..data import DevicePrefetcher
+from ..lib import pytorch_ssim
 from ..lib.models import evaluate, networks
 from ..trainer import InpaintingTrainer
 
@@ -97,6 +98,7 @@ def run(state: dict, loaders: dict, title: str, recipe: str, recon: str, schedul
         eg = {"total": 0.0, "recon": 0.0, "adv": 0.0, "update_count": 0}
         ed = {"total": 0.0, "adv_real": 0.0, "adv_fake": 0.0, "update_count": 0}
         gh = {"avg_g": {n: 0.0 for n in g_names}, "avg_d": {n: 0.0 for n in d_names}}
+        ssim_acc, n_images = torch.zeros((), dtype=torch.float32, device=device), 0  # experiment1_global_local_D.py:135,209
         net_G.train()
         # the next batch's host -> device copy overlaps this batch's kernels (the reference blocks on .to(device), wgan_l1.py:113-114)
         for batch_idx, (ground, mask, _) in enumerate(DevicePrefetcher(train_loader, device)):
@@ -106,6 +108,9 @@ def run(state: dict, loaders: dict, title: str, recipe: str, recon: str, schedul
             tr.step(ground, mask, update_g=upd)
             s = tr.read_scalars()
             d_iter += 1
+            if local_d:  # SSIM of the inpainted batch against the ground truth, logged per epoch (experiment1_global_local_D.py:209,216)
+                ssim_acc += pytorch_ssim.ssim(ground, tr.last["inpainted"]) * ground.shape[0]
+                n_images += ground.shape[0]
             if upd:
                 g_iter += 1
                 eg["total"] += s["g_loss"]
@@ -138,6 +143,8 @@ def run(state: dict, loaders: dict, title: str, recipe: str, recon: str, schedul
                 ed[k] /= ed["update_count"]
             for n in d_names:
                 gh["avg_d"][n] /= ed["update_count"]
+        if local_d and n_images:
+            eg["ssim"] = float(ssim_acc) / n_images
         training_epoch_hist.append({"g": eg, "d": ed, "gradients": gh})
 
         if epoch % evaluate_every == 0 and epoch > 0:

@@ -214,6 +214,16 @@ int b200_clamp(float* p, long long n, float lo, float hi, b200_stream_t stream);
 /* out[t] = mean |g[offsets[t] .. offsets[t+1])|, t < ntensors (offsets: int64[ntensors+1]) */
 int b200_absmean(const float* g, const long long* offsets, int ntensors, float* out, b200_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * SSIM metric (csrc/ssim.cu) — lib/pytorch_ssim/__init__.py:20-40 (`_ssim`), logged per batch at
+ * experiment1_global_local_D.py:209.  img1, img2: fp32 [N,C,H,W]; window11: HOST pointer to the 11 taps of the normalised 1-D
+ * Gaussian (pytorch_ssim gaussian(11, 1.5)); zero padding 5; C1 = 0.01^2, C2 = 0.03^2.  partial: b200_ssim_partials() floats of
+ * scratch; out: 1 float (size_average: mean over everything) or N floats (mean over C,H,W per image).
+ * ------------------------------------------------------------------------------------------------------------------ */
+long long b200_ssim_partials(int N, int C, int H, int W);
+int b200_ssim(const float* img1, const float* img2, int N, int C, int H, int W, const float* window11, int size_average, float* partial, float* out,
+              b200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,40 @@ def test_module_layout_is_the_reference_checkpoint_layout():
     assert not any(p["dropout"] for p in g2._levels())
 
 
+@pytest.mark.skipif(not os.path.exists("/root/reference/lib/models/networks.py"), reason="reference tree not mounted (GPU box)")
+def test_checkpoint_interchange_with_the_reference_modules(tmp_path):
+    """an ``epochN_G.pt`` written by either side (``torch.save(net_G.state_dict())``, wgan_l1.py:269-271)
+    loads strictly into the other side's module (eval.py:77-79), for the generator and the discriminator."""
+    from gan_inpainting_b200.lib.models import networks
+
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, "/root/reference")
+    try:
+        for k in [k for k in sys.modules if k == "lib" or k.startswith("lib.")]:
+            del sys.modules[k]
+        from lib.models import networks as ref_networks
+    finally:
+        sys.path.pop(0)
+        for k in [k for k in sys.modules if k == "lib" or k.startswith("lib.")]:
+            del sys.modules[k]
+    torch.manual_seed(3)
+    ours_g, ref_g = networks.get_network("generator", "unet"), ref_networks.get_network("generator", "unet")
+    ours_d, ref_d = networks.get_network("discriminator", "patchgan"), ref_networks.get_network("discriminator", "patchgan")
+    for ours, ref, name in ((ours_g, ref_g, "G"), (ours_d, ref_d, "D")):
+        path = tmp_path / f"epoch1_{name}.pt"
+        torch.save(ours.state_dict(), path)  # ours -> reference
+        ref.load_state_dict(torch.load(path), strict=True)
+        for (k, a), (k2, b) in zip(ours.state_dict().items(), ref.state_dict().items()):
+            assert k == k2 and torch.equal(a, b), k
+        with torch.no_grad():
+            for p_ in ref.parameters():
+                p_.mul_(0.5).add_(0.01)
+        torch.save(ref.state_dict(), path)  # reference -> ours
+        ours.load_state_dict(torch.load(path), strict=True)
+        assert all(torch.equal(a, b) for a, b in zip(ours.state_dict().values(), ref.state_dict().values()))
+        assert [n for n, _ in ours.named_parameters()] == [n for n, _ in ref.named_parameters()]
+
+
 def test_default_initialisation_is_pytorch_default():
     from gan_inpainting_b200.lib.models import networks
 

@@ -579,3 +579,27 @@ def test_absmean(dev):
     lib.call("b200_absmean", lib.ptr(g), lib.ptr(offs), 3, lib.ptr(out), lib.stream())
     assert abs(float(out[0]) - float(g[:100].abs().mean())) < 1e-6
     assert abs(float(out[2]) - float(g[100:].abs().mean())) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ SSIM metric
+def test_ssim_matches_oracle_and_reference_golden(dev):
+    """lib.pytorch_ssim.ssim / SSIM (fused separable-Gaussian kernel) against the oracle and the values recorded from the
+    reference's lib/pytorch_ssim (tests/golden/reference_ssim.pt): 1 and 3 channels, sizes that are not tile multiples, images
+    smaller than the window, identical images (== 1)."""
+    import os
+    from gan_inpainting_b200.lib import pytorch_ssim
+    from oracle import pin_ssim_against_reference as pin
+    from oracle import ssim as ossim
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_ssim.pt"))
+    for name, (a, b) in pin.cases().items():
+        got = pytorch_ssim.ssim(a.to(dev), b.to(dev))
+        per = pytorch_ssim.ssim(a.to(dev), b.to(dev), size_average=False)
+        mod = pytorch_ssim.SSIM()(a.to(dev), b.to(dev))
+        assert got.dim() == 0 and per.shape == (a.shape[0],)
+        assert abs(float(got) - gold[name]["mean"]) < 1e-5, (name, float(got), gold[name]["mean"])
+        assert float((per.cpu() - gold[name]["per_image"]).abs().max()) < 1e-5, name
+        assert abs(float(got) - float(ossim.ssim(a, b))) < 1e-5 and float(mod) == float(got)
+    with pytest.raises(NotImplementedError):
+        pytorch_ssim.ssim(a.to(dev), b.to(dev), window_size=7)
+    with pytest.raises(Exception):
+        pytorch_ssim.ssim(a, b)  # CPU tensors: no fallback

@@ -128,3 +128,15 @@ def test_flop_counts_match_survey():
     assert abs(nets.conv_flops_unet(128) / 1e9 - 2.961) < 0.01
     assert abs(nets.conv_flops_patchgan(256) / 1e9 - 3.258) < 0.01
     assert abs(nets.conv_flops_patchgan(128) / 1e9 - 0.814) < 0.01
+
+
+def test_ssim_oracle_matches_reference_golden():
+    """oracle.ssim against the values the REFERENCE's lib/pytorch_ssim produced (oracle/pin_ssim_against_reference.py)."""
+    import os
+    from oracle import pin_ssim_against_reference as pin
+    from oracle import ssim as ossim
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_ssim.pt"))
+    for name, (a, b) in pin.cases().items():
+        assert abs(float(ossim.ssim(a, b)) - gold[name]["mean"]) < 2e-6, name
+        assert float((ossim.ssim(a, b, size_average=False) - gold[name]["per_image"]).abs().max()) < 2e-6, name
+    assert abs(gold["b1_c1_256_same"]["mean"] - 1.0) < 1e-6  # identical images

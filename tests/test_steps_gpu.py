@@ -354,6 +354,9 @@ def test_begin_call_surface(dev, tmp_path):
     h = out["history"]
     assert out["g_iter"] == 3 and h[0]["g"]["update_count"] == 3 and h[0]["g"]["total"] > 0
     assert all(v > 0 for v in h[0]["gradients"]["avg_g"].values())
+    from gan_inpainting_b200.experiment_list import experiment1_global_local_D
+    out = experiment1_global_local_D.begin(dict(state, numepoch=0), {"train": batches, "test": batches, "extra": batches})
+    assert 0.0 < out["history"][0]["g"]["ssim"] <= 1.0  # lib.pytorch_ssim per batch (experiment1_global_local_D.py:209)
 
 
 def test_device_prefetcher_feeds_identical_batches(dev):
