@@ -65,7 +65,8 @@ def test_conv_s2_fprop(dev, B, H, Cin, Cout):
     assert rel(y, ref) < BF16_TOL
 
 
-@pytest.mark.parametrize("B,Hi,Cin,Cout", [(2, 8, 128, 64), (2, 1, 512, 512), (3, 4, 1024, 512), (2, 32, 512, 128), (2, 64, 256, 64), (20, 32, 128, 64)])
+@pytest.mark.parametrize("B,Hi,Cin,Cout", [(2, 8, 128, 64), (2, 1, 512, 512), (3, 4, 1024, 512), (2, 32, 512, 128), (2, 64, 256, 64), (20, 32, 128, 64),
+                                           (297, 8, 64, 64), (4, 128, 64, 64)])  # the last three: >= 148 pixel tiles at N = 64 (CTA pairs / odd tile count with masked rows / big)
 def test_convt_s2_fprop(dev, B, Hi, Cin, Cout):
     eng = _eng()
     torch.manual_seed(1)
@@ -77,7 +78,7 @@ def test_convt_s2_fprop(dev, B, Hi, Cin, Cout):
 
 
 @pytest.mark.parametrize("kind,B,H,Cin,Cout", [("conv", 3, 16, 64, 128), ("conv", 40, 32, 64, 128), ("conv", 5, 4, 512, 512), ("convt", 2, 8, 128, 64),
-                                               ("convt", 24, 16, 256, 64), ("convt", 3, 2, 512, 512)])
+                                               ("convt", 24, 16, 256, 64), ("convt", 3, 2, 512, 512), ("convt", 80, 16, 128, 64), ("convt", 299, 8, 64, 64)])
 def test_conv_epilogue_batchnorm_statistics(dev, kind, B, H, Cin, Cout):
     """The persistent GEMM's epilogue hands the following BatchNorm2d (networks.py:310, 341-349) its batch statistics: per-CTA partial
     rows + b200_bn_finalize must equal mean / biased variance of the STORED output, and update the running statistics like torch."""
@@ -120,7 +121,8 @@ def _bn_bwd_reference(y, dz, gamma, eps=1e-5):
 
 
 @pytest.mark.parametrize("B,H,Cin,Cy,skip,norm", [(3, 8, 128, 64, True, True), (20, 16, 128, 64, False, True), (2, 4, 512, 256, True, False),
-                                                      (8, 32, 256, 128, True, True), (8, 64, 128, 64, True, False)])
+                                                      (8, 32, 256, 128, True, True), (8, 64, 128, 64, True, False),
+                                                      (8, 64, 128, 64, False, False), (80, 16, 128, 64, True, True), (297, 8, 64, 64, False, True)])
 def test_fused_leaky_bn_backward_in_conv_dgrad_epilogue(dev, B, H, Cin, Cy, skip, norm):
     """Conv2d data gradient (4-phase kernel) whose epilogue applies the LeakyReLU backward of the layer below, merges the skip-connection
     gradient and reduces (sum dz, sum dz*y) for that layer's BatchNorm; b200_bn_bwd_fused finishes dgamma / dbeta / dy."""
