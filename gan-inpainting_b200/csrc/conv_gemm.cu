@@ -300,7 +300,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    {  // the whole warp runs the loop; elect.sync inside the *_w wrappers picks the issuing lane
       const uint32_t tx_bytes = (uint32_t)stage_bytes * (PAIR ? 2u : 1u);  // PAIR: both CTAs' bytes land on the even CTA's barrier
       const int nB = PAIR ? rank * (p.BN / 2) : 0;                         // this CTA's half of the weight tile
       int s = 0;
@@ -310,7 +310,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int ph_p = c.phase >> 1, ph_q = c.phase & 1;
         for (int i = 0; i < c.kb_count; i += p.kpb) {
           mbar_wait(&empty_bar[s], par ^ 1u);
-          if (!PAIR || rank == 0) mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+          if (!PAIR || rank == 0) mbar_arrive_expect_tx_w(&full_bar[s], tx_bytes);
           for (int u = 0; u < p.kpb; ++u) {
           uint8_t* sA = smem + s * stage_bytes + u * kATileBytes;
           uint8_t* sB = smem + s * stage_bytes + p.kpb * kATileBytes + u * b_bytes;
@@ -319,37 +319,37 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const int tap = kb >> p.cpt_sh, cc = kb & (p.cpt - 1);
             const int kh = tap >> 2, kw = tap & 3;
             if (PAIR) {
-              tma2_load_5d(sA, &tmA, &full_bar[s], ((kw + 1) & 1) * p.C_k + cc * 64, c.w0 + ((kw + 1) >> 1) - 1, (kh + 1) & 1,
+              tma2_load_5d_w(sA, &tmA, &full_bar[s], ((kw + 1) & 1) * p.C_k + cc * 64, c.w0 + ((kw + 1) >> 1) - 1, (kh + 1) & 1,
                            c.h0 + ((kh + 1) >> 1) - 1, c.b0);
-              tma2_load_2d(sB, &tmB, &full_bar[s], kb * 64, c.n0 + nB);
+              tma2_load_2d_w(sB, &tmB, &full_bar[s], kb * 64, c.n0 + nB);
             } else {
-              tma_load_5d(sA, &tmA, &full_bar[s], ((kw + 1) & 1) * p.C_k + cc * 64, c.w0 + ((kw + 1) >> 1) - 1, (kh + 1) & 1,
+              tma_load_5d_w(sA, &tmA, &full_bar[s], ((kw + 1) & 1) * p.C_k + cc * 64, c.w0 + ((kw + 1) >> 1) - 1, (kh + 1) & 1,
                           c.h0 + ((kh + 1) >> 1) - 1, c.b0);
-              tma_load_2d(sB, &tmB, &full_bar[s], kb * 64, c.n0);
+              tma_load_2d_w(sB, &tmB, &full_bar[s], kb * 64, c.n0);
             }
           } else if (p.mode == MODE_CONVT) {
             const int tap = kb >> p.cpt_sh, cc = kb & (p.cpt - 1);
             const int ta = tap >> 1, tb = tap & 1;
             if (PAIR) {
-              tma2_load_4d(sA, &tmA, &full_bar[s], cc * 64, c.w0 + ph_q + tb - 1, c.h0 + ph_p + ta - 1, c.b0);
-              tma2_load_2d(sB, &tmB, &full_bar[s], kb * 64, c.phase * p.Cout + c.n0 + nB);
+              tma2_load_4d_w(sA, &tmA, &full_bar[s], cc * 64, c.w0 + ph_q + tb - 1, c.h0 + ph_p + ta - 1, c.b0);
+              tma2_load_2d_w(sB, &tmB, &full_bar[s], kb * 64, c.phase * p.Cout + c.n0 + nB);
             } else {
-              tma_load_4d(sA, &tmA, &full_bar[s], cc * 64, c.w0 + ph_q + tb - 1, c.h0 + ph_p + ta - 1, c.b0);
-              tma_load_2d(sB, &tmB, &full_bar[s], kb * 64, c.phase * p.Cout + c.n0);
+              tma_load_4d_w(sA, &tmA, &full_bar[s], cc * 64, c.w0 + ph_q + tb - 1, c.h0 + ph_p + ta - 1, c.b0);
+              tma_load_2d_w(sB, &tmB, &full_bar[s], kb * 64, c.phase * p.Cout + c.n0);
             }
           } else {
             const int wt = kb & (p.tiles_w - 1);
             const int ht = (kb >> p.tiles_w_sh) & (p.tiles_h - 1);
             const int bt = kb >> (p.tiles_w_sh + p.tiles_h_sh);
             const int pw0 = wt << p.tw_sh, ph0 = ht << p.th_sh, pb0 = bt * p.nb;
-            tma_load_4d(sA, &tmA, &full_bar[s], c.m0, pw0, ph0, pb0);
-            tma_load_4d(sA + 8192, &tmA, &full_bar[s], c.m0 + 64, pw0, ph0, pb0);
+            tma_load_4d_w(sA, &tmA, &full_bar[s], c.m0, pw0, ph0, pb0);
+            tma_load_4d_w(sA + 8192, &tmA, &full_bar[s], c.m0 + 64, pw0, ph0, pb0);
             const int nsub = p.BN >> 6;
             for (int j = 0; j < nsub; ++j) {
               const int nidx = c.n0 + 64 * j;
               const int tap = nidx >> p.ck_sh, c0 = nidx & (p.C_k - 1);
               const int kh = tap >> 2, kw = tap & 3;
-              tma_load_5d(sB + j * 8192, &tmB, &full_bar[s], ((kw + 1) & 1) * p.C_k + c0, pw0 + ((kw + 1) >> 1) - 1, (kh + 1) & 1,
+              tma_load_5d_w(sB + j * 8192, &tmB, &full_bar[s], ((kw + 1) & 1) * p.C_k + c0, pw0 + ((kw + 1) >> 1) - 1, (kh + 1) & 1,
                           ph0 + ((kh + 1) >> 1) - 1, pb0);
             }
           }
@@ -363,7 +363,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && rank == 0) {
+    // the whole warp runs this loop with identical values (waits included); elect.sync inside the *_w wrappers picks the lane that
+    // issues, so descriptors and addresses stay in uniform registers (see common.cuh)
+    if (rank == 0) {
       const bool mn_major = (p.mode == MODE_WGRAD);
       const uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, p.BN, mn_major ? 1 : 0, mn_major ? 1 : 0);
       const uint32_t lbo = mn_major ? 8192u : 16u;
@@ -386,19 +388,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             for (int k = 0; k < 4; ++k) {
               const uint64_t da = make_smem_desc_sw128(a_addr + u * kATileBytes + k * kstep, lbo, 1024u);
               const uint64_t db = make_smem_desc_sw128(b_addr + u * b_bytes + k * kstep, lbo, 1024u);
-              if (PAIR) umma_bf16_2cta(d_addr, da, db, idesc, (i > 0 || u > 0 || k > 0) ? 1u : 0u);
-              else umma_bf16(d_addr, da, db, idesc, (i > 0 || u > 0 || k > 0) ? 1u : 0u);
+              if (PAIR) umma_bf16_2cta_w(d_addr, da, db, idesc, (i > 0 || u > 0 || k > 0) ? 1u : 0u);
+              else umma_bf16_w(d_addr, da, db, idesc, (i > 0 || u > 0 || k > 0) ? 1u : 0u);
             }
           }
-          if (PAIR) umma_commit_2cta(&empty_bar[s]);  // frees the slot in both CTAs
-          else umma_commit(&empty_bar[s]);            // frees the smem slot once these MMAs retire
+          if (PAIR) umma_commit_2cta_w(&empty_bar[s]);  // frees the slot in both CTAs
+          else umma_commit_w(&empty_bar[s]);            // frees the smem slot once these MMAs retire
           if (++s == p.stages) {
             s = 0;
             par ^= 1u;
           }
         }
-        if (PAIR) umma_commit_2cta(&tmem_full_bar[buf]);
-        else umma_commit(&tmem_full_bar[buf]);  // accumulator complete
+        if (PAIR) umma_commit_2cta_w(&tmem_full_bar[buf]);
+        else umma_commit_w(&tmem_full_bar[buf]);  // accumulator complete
       }
     }
   } else {
