@@ -205,7 +205,7 @@ __device__ __forceinline__ void tile_column_sums(uint8_t* wbuf, const uint32_t (
 // Same for the fused backward: dz rows are fp32 (unrounded, exactly what the BatchNorm apply pass will read), y rows bf16.
 // lane (cq, rg) reads 4 columns (chunk cq) of rows rg, rg+4, ..., rg+28; two shuffle stages fold the 4 row groups.
 // s[k] / q[k] = sum over the 32 rows of dz and dz*y for column 4*(lane & 7) + k.
-__device__ __forceinline__ void tile_column_sums_f32(uint8_t* wbuf, const uint32_t (&v)[32], const uint32_t (&yw)[16], int lane, float (&s)[4], float (&q)[4]) {
+__device__ __forceinline__ void tile_stage_f32(uint8_t* wbuf, const uint32_t (&v)[32], const uint32_t (&yw)[16], int lane) {
   uint4* rowz = reinterpret_cast<uint4*>(wbuf + lane * 128);
 #pragma unroll
   for (int j = 0; j < 8; ++j) rowz[j ^ (lane & 7)] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -214,6 +214,22 @@ __device__ __forceinline__ void tile_column_sums_f32(uint8_t* wbuf, const uint32
 #pragma unroll
   for (int j = 0; j < 4; ++j) rowy[j ^ sw] = make_uint4(yw[4 * j], yw[4 * j + 1], yw[4 * j + 2], yw[4 * j + 3]);
   __syncwarp();
+}
+// Coalesced store of the staged 32 x 32 fp32 tile: one instruction covers 4 pixel rows x 128 contiguous bytes (4 memory
+// wavefronts) instead of 32 rows x 16 bytes (32 wavefronts) when every lane stores its own row.  `row_off` = element offset of this
+// lane's row in the destination (fetched from the owning lane by shuffle), `ok` = row inside the batch.
+__device__ __forceinline__ void tile_store_f32(const uint8_t* wbuf, float* dst, unsigned long long row_off, bool ok, int lane) {
+  const int ch = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = i * 4 + (lane >> 3);
+    const uint4 d = *reinterpret_cast<const uint4*>(wbuf + rr * 128 + ((ch ^ (rr & 7)) * 16));
+    const unsigned long long off = __shfl_sync(0xffffffffu, row_off, rr);
+    const int rok = __shfl_sync(0xffffffffu, (int)ok, rr);
+    if (rok) *reinterpret_cast<uint4*>(dst + off + ch * 4) = d;
+  }
+}
+__device__ __forceinline__ void tile_column_sums_f32(uint8_t* wbuf, int lane, float (&s)[4], float (&q)[4]) {
   const int cq = lane & 7, rg = lane >> 3;
 #pragma unroll
   for (int k = 0; k < 4; ++k) s[k] = q[k] = 0.f;
@@ -540,9 +556,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
           } else if (valid) {
             if (E::BWD && E::STATS && fused && p.bwd.dz32 != nullptr) {
-              float* d32 = p.bwd.dz32 + pix * p.bwd.Cy + cb;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(d32 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              // stored below, coalesced, from the tile staged for the column sums
             } else {
 #pragma unroll
               for (int j = 0; j < 16; j += 4) *reinterpret_cast<uint4*>(dst + cc + 2 * j) = make_uint4(o[j], o[j + 1], o[j + 2], o[j + 3]);
@@ -555,7 +569,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               for (int j = 0; j < 32; ++j) v[j] = 0u;
             }
             float cs[4], cq[4];
-            tile_column_sums_f32(wbuf, v, yw, lane, cs, cq);
+            tile_stage_f32(wbuf, v, yw, lane);
+            if (fused && p.bwd.dz32 != nullptr) tile_store_f32(wbuf, p.bwd.dz32 + cb, (unsigned long long)pix * (unsigned long long)p.bwd.Cy, valid, lane);
+            tile_column_sums_f32(wbuf, lane, cs, cq);
             if (lane < 8) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
