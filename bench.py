@@ -35,6 +35,7 @@ sys.path.insert(0, ROOT)
 # stdout carries exactly ONE JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) out of it
 if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
     os.environ["NCCL_DEBUG"] = "WARN"
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL logs to stdout by default (and WARN still prints the version line)
 
 RECIPES = {
     # name: (trainer recipe, recon, sigmoid D, update_g)
