@@ -181,10 +181,18 @@ __global__ void __launch_bounds__(256) bn_act_kernel(const ApplyParams p) {
   const unsigned total = (unsigned)p.P << p.cshift;
   const unsigned cmask = (1u << p.cshift) - 1u;
   const uint32_t seed = p.dropout ? dropout_seed(p.seed, p.seed_ctr) : 0u;
-  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+  // software-pipelined: the next element's 16-byte load is in flight while this one is processed (2048 threads x 16 B per SM
+  // is less than the bandwidth-latency product of HBM3e)
+  const unsigned stride = gridDim.x * blockDim.x;
+  unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  uint4 vnext = make_uint4(0u, 0u, 0u, 0u);
+  if (idx < total) vnext = __ldg(reinterpret_cast<const uint4*>(p.y + (size_t)(idx >> p.cshift) * p.C + (int)(idx & cmask) * 8));
+  for (; idx < total; idx += stride) {
     const size_t pix = idx >> p.cshift;
     const int c0 = (int)(idx & cmask) * 8;
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.y + pix * p.C + c0));
+    const uint4 v = vnext;
+    const unsigned nidx = idx + stride;
+    if (nidx < total) vnext = __ldg(reinterpret_cast<const uint4*>(p.y + (size_t)(nidx >> p.cshift) * p.C + (int)(nidx & cmask) * 8));
     const uint32_t u[4] = {v.x, v.y, v.z, v.w};
     float f[8];
 #pragma unroll
