@@ -1,8 +1,9 @@
 """Drop-in ``lib.models.loss`` (reference lib/models/loss.py:11-47): ``RMSELoss`` and ``LocalLoss`` as fused CUDA
 reductions with hand-written backward kernels (csrc/losses.cu).
 
-The perceptual / style / TV losses of loss.py:49-151 need downloaded VGG19 weights and contribute no gradient
-(they run under ``no_grad`` on detached tensors); they are outside the hot path.
+``tv_loss`` (loss.py:138-151, part of g_loss in config 4) is a fused stencil + reduction with its own backward kernel
+(csrc/tv.cu).  The perceptual / style losses of loss.py:49-115 need downloaded VGG19 weights and contribute no gradient (they run
+under ``no_grad`` on detached tensors); they are the not-yet-built part of SURVEY.md §8f row 1.
 """
 from __future__ import annotations
 
@@ -99,3 +100,36 @@ class LocalLoss(nn.Module):
         call("b200_recon_loss", RECON_LOCAL_L1, ptr(a), ptr(b), ptr(m), a.numel(), 0.0, ptr(Scratch.get(a.device).recon), ptr(out), stream())
         words = out.view(torch.int32)[2:4].tolist()
         return int(words[0]) + (int(words[1]) << 31)
+
+
+class _TvFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, weight):
+        x = img.detach().contiguous().float()
+        if not x.is_cuda:
+            raise _lib.B200Error("tv_loss runs on CUDA tensors only; there is no CPU fallback")
+        if x.dim() < 2:
+            raise _lib.B200Error(f"tv_loss expects [..., H, W], got {tuple(x.shape)}")
+        H, W = x.shape[-2:]
+        planes = x.numel() // (H * W)
+        partial = torch.empty(2 * planes * H, dtype=torch.float32, device=x.device)
+        out = torch.empty(1, dtype=torch.float32, device=x.device)
+        call("b200_tv_loss", ptr(x), planes, H, W, float(weight), ptr(partial), ptr(out), stream())
+        ctx.x, ctx.weight, ctx.shape, ctx.dims = x, float(weight), img.shape, (planes, H, W)
+        return out[0].clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        if not ctx.needs_input_grad[0]:
+            return None, None
+        g = gout.contiguous().float().reshape(1)
+        d = torch.empty_like(ctx.x)
+        planes, H, W = ctx.dims
+        call("b200_tv_loss_bwd", ptr(ctx.x), planes, H, W, ctx.weight, ptr(g), ptr(d), 0, stream())
+        return d.view(ctx.shape), None
+
+
+def tv_loss(img, tv_weight):
+    """loss.py:138-151: ``tv_weight * (mean((img[..., :-1] - img[..., 1:])**2) + mean((img[..., :-1, :] - img[..., 1:, :])**2))``;
+    differentiable w.r.t. ``img`` (it is part of ``g_loss``, wgan_perceptual_style_faceparsing.py:219-221)."""
+    return _TvFunction.apply(img, tv_weight)

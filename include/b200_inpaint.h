@@ -224,6 +224,16 @@ long long b200_ssim_partials(int N, int C, int H, int W);
 int b200_ssim(const float* img1, const float* img2, int N, int C, int H, int W, const float* window11, int size_average, float* partial, float* out,
               b200_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Total-variation loss (csrc/tv.cu) — lib/models/loss.py:138-151 (`tv_loss`), part of g_loss at
+ * experiment_list/wgan_perceptual_style_faceparsing.py:219-221.  img: fp32 [planes = N*C, H, W];
+ * out[0] = weight * (mean of squared horizontal differences + mean of squared vertical differences).
+ * partial: 2 * planes * H floats of scratch.  _bwd: dimg (+)= gscale[0] * d loss / d img (gscale: device scalar, NULL = 1).
+ * ------------------------------------------------------------------------------------------------------------------ */
+int b200_tv_loss(const float* img, long long planes, int H, int W, float weight, float* partial, float* out, b200_stream_t stream);
+int b200_tv_loss_bwd(const float* img, long long planes, int H, int W, float weight, const float* gscale, float* dimg, int accumulate,
+                     b200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

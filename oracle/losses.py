@@ -45,3 +45,10 @@ def bce(pred: torch.Tensor, target_value: float) -> torch.Tensor:
 def lsgan(pred: torch.Tensor, target_value: float) -> torch.Tensor:
     """nn.MSELoss against ones / zeros (experiment1_global_local_D.py:119,162-163,183-194)."""
     return F.mse_loss(pred, torch.full_like(pred, target_value))
+
+
+def tv_loss(img: torch.Tensor, tv_weight: float) -> torch.Tensor:
+    """tv_loss — loss.py:138-151: tv_weight * (mean of squared horizontal differences + mean of squared vertical differences)."""
+    w_variance = torch.mean((img[:, :, :, :-1] - img[:, :, :, 1:]) ** 2)
+    h_variance = torch.mean((img[:, :, :-1, :] - img[:, :, 1:, :]) ** 2)
+    return tv_weight * (h_variance + w_variance)

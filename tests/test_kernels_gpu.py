@@ -605,3 +605,28 @@ def test_ssim_matches_oracle_and_reference_golden(dev):
         pytorch_ssim.ssim(a.to(dev), b.to(dev), window_size=7)
     with pytest.raises(Exception):
         pytorch_ssim.ssim(a, b)  # CPU tensors: no fallback
+
+
+# ------------------------------------------------------------------------------------------------ total-variation loss
+def test_tv_loss_forward_backward(dev):
+    """lib.models.loss.tv_loss (loss.py:138-151; part of g_loss in config 4) against the oracle and the reference golden values:
+    loss and the gradient w.r.t. the image (through autograd, with a non-trivial upstream gradient), NaN for a single-row image."""
+    import math
+    import os
+    from gan_inpainting_b200.lib.models import loss as bl
+    from oracle import losses as ol
+    from oracle import pin_tv_against_reference as pin
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_tv.pt"))
+    for name, (img, w) in pin.cases().items():
+        x = img.to(dev).requires_grad_(True)
+        out = bl.tv_loss(x, w)
+        if math.isnan(gold[name]["loss"]):
+            assert math.isnan(float(out)), name
+            continue
+        assert abs(float(out) - gold[name]["loss"]) <= 2e-6 * max(1.0, abs(gold[name]["loss"])), (name, float(out), gold[name]["loss"])
+        (3.0 * out).backward()
+        xr = img.clone().requires_grad_(True)
+        (3.0 * ol.tv_loss(xr, w)).backward()
+        assert rel(x.grad, xr.grad) < F32_TOL, name
+    with pytest.raises(Exception):
+        bl.tv_loss(img, 1.0)  # CPU tensor: no fallback

@@ -140,3 +140,21 @@ def test_ssim_oracle_matches_reference_golden():
         assert abs(float(ossim.ssim(a, b)) - gold[name]["mean"]) < 2e-6, name
         assert float((ossim.ssim(a, b, size_average=False) - gold[name]["per_image"]).abs().max()) < 2e-6, name
     assert abs(gold["b1_c1_256_same"]["mean"] - 1.0) < 1e-6  # identical images
+
+
+def test_tv_oracle_matches_reference_golden():
+    """oracle.losses.tv_loss against the values / gradients the REFERENCE's tv_loss produced (oracle/pin_tv_against_reference.py)."""
+    import math
+    import os
+    from oracle import pin_tv_against_reference as pin
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_tv.pt"))
+    for name, (img, w) in pin.cases().items():
+        x = img.clone().requires_grad_(True)
+        o = losses.tv_loss(x, w)
+        if math.isnan(gold[name]["loss"]):
+            assert math.isnan(float(o)), name  # a single row: mean over an empty tensor
+            continue
+        assert abs(float(o) - gold[name]["loss"]) < 1e-6, name
+        o.backward()
+        ne, se = summary_close(x.grad, gold[name]["grad"], 0)
+        assert ne < 1e-5 and se < 1e-5, name
