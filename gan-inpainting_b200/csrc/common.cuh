@@ -142,6 +142,7 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
+// TMA loads of a CTA pair: data lands in the executing CTA, the transaction bytes are counted on the even CTA's barrier
 __device__ __forceinline__ void tma2_load_2d_w(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
   asm volatile(B200_ELECT_ASM("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];") ::"r"(smem_u32(dst)),
                "l"((uint64_t)m), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
@@ -180,6 +181,7 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // one lane that issues.  Inside an `if (lane == 0)` region ptxas cannot prove the descriptors warp-uniform and wraps every
 // tcgen05.mma in an ELECT / 5x R2UR.BROADCAST / BRA.U.ANY waterfall (~19 dependent instructions, ~150 cycles per MMA on the one
 // issuing thread — measured as THE bound of every tile with N <= 128); issued warp-uniformly the operands live in uniform registers.
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (bf16 in, fp32 accumulate), single CTA.
 __device__ __forceinline__ void umma_bf16_w(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
@@ -191,6 +193,7 @@ __device__ __forceinline__ void umma_bf16_w(uint32_t tmem_d, uint64_t desc_a, ui
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem of both CTAs, 256 rows] (+)= A[128 rows from each CTA] * B[N/2 columns from each CTA]; issued by the even CTA only
 __device__ __forceinline__ void umma_bf16_2cta_w(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
@@ -202,6 +205,8 @@ __device__ __forceinline__ void umma_bf16_2cta_w(uint32_t tmem_d, uint64_t desc_
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// mbarrier arrive once every tcgen05.mma previously issued by the elected lane has completed (implies fence::before_thread_sync);
+// the _2cta form arrives on the barrier at this offset in BOTH CTAs of the pair
 __device__ __forceinline__ void umma_commit_w(uint64_t* bar) {
   asm volatile(
       "{\n\t"
