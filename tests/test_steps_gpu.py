@@ -314,13 +314,14 @@ def test_module_api_step_equals_fused_step(dev):
             assert rel(a, b) < 1e-3, k
 
 
-def test_inference_composite(dev):
-    """config 5: ceil -> mask out -> G (eval) -> composite (visualize.py:69-76)."""
+@pytest.mark.parametrize("R", [256, 512])
+def test_inference_composite(dev, R):
+    """config 5: ceil -> mask out -> G (eval) -> composite (visualize.py:69-76), at 256x256 and at config 5's 512x512."""
     trainer, nets, steps, synth = _imports()
-    ground, mask = synth.make_batch(2, 256, seed=26, soft_edge=True)
+    ground, mask = synth.make_batch(2, R, seed=26, soft_edge=True)
     gp = nets.init_unet(0)
     G = make_G(dev, gp).eval()
-    D = make_D(dev, nets.init_patchgan(1, res=256), 256, False)
+    D = make_D(dev, nets.init_patchgan(1, res=R), R, False)
     tr = trainer.InpaintingTrainer("wgan", G, D)
     out = tr.inpaint(ground.to(dev), mask.to(dev))
     ref = steps.inference({k: v.clone() for k, v in gp.items()}, ground, mask)
