@@ -187,3 +187,50 @@ def test_gradient_bucketing_world2_gloo():
     mp.spawn(_bucket_worker, args=(world, port, ret), nprocs=world, join=True)
     assert all(ret[r][0] for r in range(world)), dict(ret)
     assert ret[0][1] == ret[1][1] >= 2  # same bucket schedule on every rank
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to the B200 arm): one JSON line with the contract's keys, timed on
+    the host cores with the oracle port of the step; a bounded sample (here 1 step of 2 images at 128x128)."""
+    import json
+    import subprocess
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--res", "128",
+                        "--ref-batch", "2"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "images/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == os.cpu_count() and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0 and d["vs_baseline"] is None
+
+
+def test_bench_clock_sample_parsing(tmp_path):
+    """ClockSampler.stop: samples are filtered to the timed region by their nvidia-smi timestamps; throttle reasons are collected."""
+    import importlib.util
+    import time
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    class FakeProc:
+        def terminate(self):
+            pass
+
+        def wait(self):
+            pass
+
+    cs = bench.ClockSampler(0)
+    cs.p = FakeProc()
+    now = time.time()
+    fmt = lambda t: time.strftime("%Y/%m/%d %H:%M:%S", time.localtime(t)) + ".%03d" % int((t % 1) * 1000)
+    rows = [(now - 5.0, 1200, "Not Active"), (now - 1.0, 1950, "Active"), (now - 0.5, 1965, "Not Active"), (now + 5.0, 900, "Not Active")]
+    with open(cs.f.name, "w") as f:
+        for t, mhz, cap in rows:
+            f.write(f"{fmt(t)}, 0, {mhz}, 1965, 400.0, 0x0, Not Active, Not Active, Not Active, {cap}\n")
+    out = cs.stop(now - 2.0, now)
+    assert out["samples"] == 2 and out["samples_total"] == 4 and out["window"] == "timed region"
+    assert out["sm_mhz"] in (1950.0, 1965.0) and out["sm_max_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"]
