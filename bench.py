@@ -47,11 +47,32 @@ RECIPES = {
 METRIC = "train-step images/sec at 256x256"
 
 
+def conv_flops(res: int):
+    """Algorithmic forward conv / linear FLOPs (2*MAC) per image of the two networks: U-Net generator
+    (7 levels, ngf 64: 64-128-256-512-512-512-512, 4x4 stride-2 convolutions down and transposed convolutions up, decoder inputs
+    doubled by the skip concatenation except the innermost) and PatchGAN (1-64-128-256-512, 4x4/s1 head conv, Linear)."""
+    enc = [(1, 64), (64, 128), (128, 256), (256, 512), (512, 512), (512, 512), (512, 512)]
+    dec = [(512, 512), (1024, 512), (1024, 512), (1024, 256), (512, 128), (256, 64), (128, 1)]
+    g, r = 0.0, res
+    for cin, cout in enc:
+        r //= 2
+        g += 2.0 * r * r * cout * cin * 16
+    for cin, cout in dec:
+        g += 2.0 * r * r * cin * cout * 16
+        r *= 2
+    d, r, cin = 0.0, res, 1
+    for i in range(4):
+        r //= 2
+        d += 2.0 * r * r * (64 << i) * cin * 16
+        cin = 64 << i
+    r -= 3
+    d += 2.0 * r * r * cin * 16 + 2.0 * r * r
+    return g, d
+
+
 def flops_per_image(res: int, recipe: str) -> dict:
     """Algorithmic conv FLOPs (2*MAC) per image, SURVEY.md §8(d): full step = 3*G + 8*D."""
-    from oracle import nets
-
-    g, d = nets.conv_flops_unet(res), nets.conv_flops_patchgan(res)
+    g, d = conv_flops(res)
     # tensor-core part: everything but the 1-channel-side layers (d1, u1, c1) and the D head
     g1 = 2.0 * (res // 2) ** 2 * 64 * 16            # d1
     gu1 = 2.0 * (res // 2) ** 2 * 128 * 16          # u1
@@ -195,9 +216,8 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     from gan_inpainting_b200 import _lib, build
     from gan_inpainting_b200.lib.models import networks
-    from gan_inpainting_b200.data import DevicePrefetcher
+    from gan_inpainting_b200.data import DevicePrefetcher, synthetic_batch
     from gan_inpainting_b200.trainer import InpaintingTrainer
-    from oracle import synth  # synthetic input generator only
 
     if rank == 0:
         build.build(verbose=False)
@@ -209,7 +229,7 @@ def run_b200(args):
     G = networks.get_network("generator", "unet").to(dev).train()  # reference default: dropout ON
     D = networks.PatchGANDiscriminator(sigmoid=(kind != "wgan"), imagedim=R).to(dev).train()
     tr = InpaintingTrainer(kind, G, D, recon=recon, distributed=world > 1, bucket_mb=args.bucket_mb, graph=not args.no_graph)
-    ground_h, mask_h = synth.make_batch(B, R, seed=1234, rank=rank)
+    ground_h, mask_h = synthetic_batch(B, R, seed=1234, rank=rank)
     ground_h, mask_h = ground_h.pin_memory(), mask_h.pin_memory()
     ground, mask = ground_h.to(dev), mask_h.to(dev)
 

@@ -60,3 +60,19 @@ class DevicePrefetcher:
             done.record(torch.cuda.current_stream(self.device))  # everything the consumer enqueued for this batch
             self.consumed[i & 1] = done
             i += 1
+
+
+def synthetic_batch(batch: int, res: int, seed: int = 1234, rank: int = 0):
+    """The synthetic inputs of the benchmark, in the loader's format (lib/data/dataset.py:14-51): ``ground`` ~ U[0,1)
+    fp32 ``[B,1,R,R]``, ``mask`` = one axis-aligned rectangle of ones per image with sides in [R/8, R/2].  Host tensors; seeded per rank."""
+    g = torch.Generator().manual_seed(seed + rank)
+    ground = torch.rand(batch, 1, res, res, generator=g, dtype=torch.float32)
+    mask = torch.zeros(batch, 1, res, res, dtype=torch.float32)
+    lo, hi = res // 8, res // 2
+    for b in range(batch):
+        h = int(torch.randint(lo, hi + 1, (1,), generator=g))
+        w = int(torch.randint(lo, hi + 1, (1,), generator=g))
+        t = int(torch.randint(0, res - h + 1, (1,), generator=g))
+        l = int(torch.randint(0, res - w + 1, (1,), generator=g))
+        mask[b, 0, t : t + h, l : l + w] = 1.0
+    return ground, mask

@@ -234,3 +234,25 @@ def test_bench_clock_sample_parsing(tmp_path):
     out = cs.stop(now - 2.0, now)
     assert out["samples"] == 2 and out["samples_total"] == 4 and out["window"] == "timed region"
     assert out["sm_mhz"] in (1950.0, 1965.0) and out["sm_max_mhz"] == 1965.0 and out["reasons"] == ["sw_power_cap"]
+
+
+def test_bench_inputs_and_flop_counts_are_independent_of_the_oracle_but_equal_to_it():
+    """The B200 arm of bench.py imports nothing from oracle/ (the oracle is the checker, not part of what is measured): its synthetic
+    inputs (data.synthetic_batch) and FLOP counts (bench.conv_flops) are its own — and identical to the oracle's."""
+    import importlib.util
+
+    from gan_inpainting_b200.data import synthetic_batch
+    from oracle import synth
+
+    spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for res in (128, 256, 512):
+        g, d = bench.conv_flops(res)
+        assert g == onets.conv_flops_unet(res) and d == onets.conv_flops_patchgan(res)
+    assert abs(bench.flops_per_image(256, "wgan_l1")["total"] / 1e9 - 61.59) < 0.01  # SURVEY.md §8d: 3 G + 8 D
+    a, b = synthetic_batch(3, 128, seed=9, rank=1), synth.make_batch(3, 128, seed=9, rank=1)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    b200_arm = src[src.index("def run_b200("):src.index("def main(")]
+    assert "oracle" not in b200_arm.replace("oracle port", "").replace("time_cpu", "")

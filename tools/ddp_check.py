@@ -27,10 +27,10 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     from gan_inpainting_b200.lib.models import networks
     from gan_inpainting_b200.trainer import InpaintingTrainer
-    from oracle import synth  # synthetic inputs only
+    from gan_inpainting_b200.data import synthetic_batch
 
     R, B, steps = 128, 4, 4
-    batches = [tuple(t.to(dev) for t in synth.make_batch(B, R, seed=500 + 10 * i, rank=rank)) for i in range(steps)]
+    batches = [tuple(t.to(dev) for t in synthetic_batch(B, R, seed=500 + 10 * i, rank=rank)) for i in range(steps)]
 
     def make(seed):
         torch.manual_seed(seed)  # rank-dependent init on purpose: the trainer must broadcast rank 0's weights

@@ -7,7 +7,7 @@ import torch
 
 from gan_inpainting_b200.lib.models import networks
 from gan_inpainting_b200.trainer import InpaintingTrainer
-from oracle import synth
+from gan_inpainting_b200.data import synthetic_batch
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
@@ -18,7 +18,7 @@ torch.manual_seed(0)
 G = networks.get_network("generator", "unet").to(dev).train()
 D = networks.PatchGANDiscriminator(sigmoid=(recipe != "wgan"), imagedim=R).to(dev).train()
 tr = InpaintingTrainer(recipe, G, D, recon="l1")
-ground, mask = synth.make_batch(B, R, seed=1234)
+ground, mask = synthetic_batch(B, R, seed=1234)
 ground, mask = ground.to(dev), mask.to(dev)
 for _ in range(steps):
     tr.step(ground, mask, update_g=True)
