@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Benchmark of the GAN-inpainting train step (BASELINE.json metric: train-step images/sec at 256x256).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--recipe wgan_l1|minimaxgan_rmse|inference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--recipe wgan_l1|wgan_rmse|minimaxgan_rmse|minimaxgan_l1|wgan_d_only|inference]
 
 Workload at N=1 (BASELINE.json configs[1]): ``wgan_l1`` — U-Net generator + PatchGAN global discriminator, 256x256,
 batch 64 per GPU, bf16 operands / fp32 accumulation.  One "step" is the full step of experiment_list/wgan_l1.py:110-186
@@ -14,7 +15,14 @@ One JSON line on stdout (rank 0):
              (ground, mask) and a device -> host read of the loss vector, inside the timed region
   roofline   tensor-pipe roofline of the dominant kernel (the tcgen05 implicit-GEMM body that runs every 4x4/s2
              convolution, its data gradient and its weight gradient): algorithmic FLOPs / measured kernel time
+  tail       achieved HBM GB/s of every memory-bound kernel of the step (algorithmic bytes of the call / its CUDA-event time)
   cpu_baseline  the oracle port of the reference step on this box's host cores (bounded sample, rank 0, N=1)
+  also       (default recipe, N=1) short measurements of SURVEY.md §8(d)'s other two lines: the WGAN D-only step (4 of 5
+             steady-state batches, wgan_l1.py:157-163) and config 5's inference pass (512x512, batch 128)
+
+Other recipes: `--recipe wgan_d_only` (D update only), `--recipe inference` (config 5: ceil(mask) -> mask-out -> G (eval) ->
+composite through trainer.inpaint at 512x512, batch 128 per GPU; e2e copies the images H2D and the result D2H every step),
+`--recipe minimaxgan_rmse` (config 3).
 
 `--impl reference` times the reference algorithm's CPU implementation (oracle/, fp32 PyTorch on all host cores) on a
 bounded sample of the same workload and prints the same line with "impl": "reference".
@@ -32,19 +40,24 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly ONE JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) out of it
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL logs to stdout by default (and WARN still prints the version line)
+# stdout carries exactly ONE JSON line: NCCL logs to stdout by default, so its log file defaults to stderr (NCCL_DEBUG itself is
+# left as the caller set it)
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 RECIPES = {
-    # name: (trainer recipe, recon, sigmoid D, update_g)
+    # name: (trainer recipe, recon)
     "wgan_l1": ("wgan", "l1"),
     "wgan_rmse": ("wgan", "rmse"),
     "minimaxgan_rmse": ("minimax", "rmse"),
     "minimaxgan_l1": ("minimax", "l1"),
+    "wgan_d_only": ("wgan", "l1"),     # the D-only batches of the WGAN schedule (update_g=False)
+    "inference": ("wgan", "l1"),       # config 5: trainer.inpaint, no discriminator work
 }
-METRIC = "train-step images/sec at 256x256"
+DEFAULT_SHAPE = {"inference": (512, 128)}  # (res, batch per GPU); everything else 256x256, batch 64 (BASELINE configs[1])
+
+
+def metric_name(recipe: str, res: int) -> str:
+    return f"inference images/sec at {res}x{res}" if recipe == "inference" else f"train-step images/sec at {res}x{res}"
 
 
 def conv_flops(res: int):
@@ -81,6 +94,8 @@ def flops_per_image(res: int, recipe: str) -> dict:
     g_tc, d_tc = g - g1 - gu1, d - dc1 - dhead
     if recipe == "inference":
         return dict(total=g, tensor=g_tc)
+    if recipe == "wgan_d_only":  # G forward + D: 2 forward, 2 x (data + weight gradient)   (1*G + 6*D)
+        return dict(total=g + 6 * d, tensor=g_tc + 6 * d_tc)
     # G: fwd + dgrad + wgrad (d2's dgrad to a1 IS needed; d1 has none).  D: 2 fwd + 2*(dgrad+wgrad) in the D step
     # (c2's dgrad is needed for c1's wgrad) + 1 fwd + 1 dgrad in the G step.
     return dict(total=3 * g + 8 * d, tensor=3 * g_tc + 8 * d_tc)
@@ -156,14 +171,17 @@ def cpu_step_runner(recipe: str, res: int, batch: int):
 
     torch.set_num_threads(os.cpu_count())
     kind, recon = RECIPES[recipe]
+    ground, mask = synth.make_batch(batch, res, seed=1234)
+    if recipe == "inference":
+        G = nets.init_unet(0)
+        return lambda: steps.inference(G, ground, mask)
     G, D = steps.enable_grad(nets.init_unet(0)), steps.enable_grad(nets.init_patchgan(1, res=res))
     if kind == "wgan":
         go, do = steps.make_optimizer("rmsprop", G), steps.make_optimizer("rmsprop", D)
-        fn = lambda g, m: steps.wgan_step(G, D, go, do, g, m, recon=recon)
+        fn = lambda g, m: steps.wgan_step(G, D, go, do, g, m, recon=recon, update_g=(recipe != "wgan_d_only"))
     else:
         go, do = steps.make_optimizer("adam", G), steps.make_optimizer("adam", D)
         fn = lambda g, m: steps.minimax_step(G, D, go, do, g, m, recon=recon)
-    ground, mask = synth.make_batch(batch, res, seed=1234)
     return lambda: fn(ground, mask)
 
 
@@ -178,6 +196,14 @@ def time_cpu(recipe: str, res: int, batch: int, steps_n: int, warmup: int):
     return batch * steps_n / dt, dt / steps_n
 
 
+def workload_name(recipe: str, res: int, batch: int, what: str) -> str:
+    if recipe == "inference":
+        return f"inference (config 5): ceil(mask) -> mask-out -> U-Net generator (eval) -> composite, {res}x{res}, batch {batch} {what}"
+    if recipe == "wgan_d_only":
+        return f"wgan_l1 D-only batch (G forward + composite + D update, no G update; wgan_l1.py:157-163), {res}x{res}, batch {batch} {what}"
+    return f"{recipe}: U-Net generator + PatchGAN global D, full train step (D update + G update), {res}x{res}, batch {batch} {what}"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -186,15 +212,48 @@ def run_reference(args):
     ips, spt = time_cpu(args.recipe, args.res, batch, args.steps, args.warmup)
     sample = f"{args.steps} steps x {batch} images of the {args.recipe} step at {args.res}x{args.res} (fp32, torch CPU, {os.cpu_count()} threads)"
     line = {
-        "impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": spt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.recipe}: G + global D full train step, {args.res}x{args.res}, batch {batch} per step (bounded CPU sample)",
+        "impl": "reference", "metric": metric_name(args.recipe, args.res), "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": spt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args.recipe, args.res, batch, "per step (bounded CPU sample of the B200 arm's workload)"),
                    "recipe": args.recipe, "res": args.res, "batch_per_step": batch},
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# algorithmic HBM bytes of the memory-bound C-ABI calls (from their arguments; include/b200_inpaint.h gives the signatures)
+# ----------------------------------------------------------------------------------------------------------------
+def _has(a):
+    return a is not None and getattr(a, "value", a) not in (None, 0)
+
+
+def _i(a):
+    return int(getattr(a, "value", a))
+
+
+TAIL_BYTES = {
+    # read y (bf16) + one or two bf16 stores
+    "b200_bn_act": lambda a: _i(a[1]) * _i(a[2]) * 2 * (1 + _has(a[6]) + _has(a[9])),
+    # read y (bf16) + dz (fp32 or bf16), write dy (bf16)
+    "b200_bn_bwd_fused": lambda a: _i(a[1]) * _i(a[2]) * (2 + (4 if _i(a[8]) else 2) + 2),
+    # with batch statistics: a reduce pass and an apply pass, each reading y, g1 (and g2); one bf16 store
+    "b200_bn_act_bwd": lambda a: _i(a[1]) * _i(a[2]) * 2 * ((2 + _has(a[9])) * (2 if _has(a[3]) else 1) + 1),
+    "b200_conv_c1_fwd": lambda a: _i(a[2]) * _i(a[3]) * _i(a[4]) * 4 * (1 + _has(a[1])) + _i(a[2]) * (_i(a[3]) // 2) * (_i(a[4]) // 2) * _i(a[6]) * 2 * (1 + _has(a[9])),
+    "b200_convt_c1_fwd": lambda a: _i(a[1]) * _i(a[2]) * _i(a[3]) * _i(a[4]) * 2 + _i(a[1]) * 4 * _i(a[2]) * _i(a[3]) * 4 * (1 + _has(a[9]) + _has(a[10]) + _has(a[12])),
+    "b200_wgrad_c1": lambda a: _i(a[1]) * _i(a[2]) * _i(a[3]) * _i(a[4]) * 2 + _i(a[1]) * 4 * _i(a[2]) * _i(a[3]) * 4 * (1 + _has(a[7])),
+    "b200_wgrad_reduce": lambda a: 4 * (_i(a[1]) + 1 + _i(a[5])) * _i(a[2]) * _i(a[3]) * 16,
+    "b200_rmsprop_step": lambda a: 16 * _i(a[3]),
+    "b200_adam_step": lambda a: 28 * _i(a[4]),
+    "b200_mask_prepare": lambda a: 4 * _i(a[2]) * (2 + _has(a[4]) + _has(a[5])),
+    "b200_recon_loss": lambda a: 4 * _i(a[4]) * (2 + _has(a[3])),
+    "b200_gstep_seed": lambda a: 4 * _i(a[14]) * 6,
+    "b200_head_fwd": lambda a: 2 * _i(a[2]) * _i(a[3]),
+    "b200_head_bwd_input": lambda a: 2 * _i(a[2]) * _i(a[3]),
+}
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -225,13 +284,12 @@ def run_b200(args):
         dist.barrier()
     B, R = args.batch, args.res
     kind, recon = RECIPES[args.recipe]
+    infer = args.recipe == "inference"
+    update_g = args.recipe != "wgan_d_only"
     torch.manual_seed(0)
     G = networks.get_network("generator", "unet").to(dev).train()  # reference default: dropout ON
     D = networks.PatchGANDiscriminator(sigmoid=(kind != "wgan"), imagedim=R).to(dev).train()
-    tr = InpaintingTrainer(kind, G, D, recon=recon, distributed=world > 1, bucket_mb=args.bucket_mb, graph=not args.no_graph)
-    ground_h, mask_h = synthetic_batch(B, R, seed=1234, rank=rank)
-    ground_h, mask_h = ground_h.pin_memory(), mask_h.pin_memory()
-    ground, mask = ground_h.to(dev), mask_h.to(dev)
+    tr = InpaintingTrainer(kind, G, D, recon=recon, distributed=(world > 1 and not infer), bucket_mb=args.bucket_mb, graph=not args.no_graph, rank=rank)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -254,31 +312,53 @@ def run_b200(args):
             ms = float(t)
         return ms
 
-    step_dev = lambda: tr.step(ground, mask, update_g=True)
-    out_h = torch.empty(16, dtype=torch.float32).pin_memory()
-
     class HostBatches:
         """The pinned host batch, served n times (a DataLoader stand-in: every step gets its own host -> device copy)."""
 
-        def __init__(self, n):
-            self.n = n
+        def __init__(self, g, m, n):
+            self.g, self.m, self.n = g, m, n
 
         def __iter__(self):
             for _ in range(self.n):
-                yield ground_h, mask_h, None
+                yield self.g, self.m, None
 
-    def run_e2e(n):
-        """n steps through the public API: DevicePrefetcher (pinned host -> device copy of EVERY step's inputs, overlapped with
-        the previous step) -> InpaintingTrainer.step -> the loss vector read back to the host every step (wgan_l1.py:199-201)."""
-        for g_d, m_d, _ in DevicePrefetcher(HostBatches(n), dev):
-            tr.step(g_d, m_d, update_g=True)
-            out_h.copy_(tr.scalars, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+    def workload(recipe, R, B):
+        """(device-resident step, e2e runner, D2H bytes per step) of one recipe at one shape."""
+        ground_h, mask_h = synthetic_batch(B, R, seed=1234, rank=rank)
+        ground_h, mask_h = ground_h.pin_memory(), mask_h.pin_memory()
+        ground, mask = ground_h.to(dev), mask_h.to(dev)
+        if recipe == "inference":
+            step = lambda: tr.inpaint(ground, mask)
+            res_h = torch.empty((B, 1, R, R), dtype=torch.float32).pin_memory()
 
+            def e2e(n):
+                """DevicePrefetcher (pinned host -> device copy of every step's images and masks) -> trainer.inpaint -> the inpainted
+                images copied back to pinned host memory every step (visualize.py:69-76 then saves them)."""
+                for g_d, m_d, _ in DevicePrefetcher(HostBatches(ground_h, mask_h, n), dev):
+                    res_h.copy_(tr.inpaint(g_d, m_d), non_blocking=True)
+                    torch.cuda.current_stream().synchronize()
+
+            return step, e2e, 2 * ground_h.numel() * 4, res_h.numel() * 4
+        upd = recipe != "wgan_d_only"
+        step = lambda: tr.step(ground, mask, update_g=upd)
+        out_h = torch.empty(16, dtype=torch.float32).pin_memory()
+
+        def e2e(n):
+            """n steps through the public API: DevicePrefetcher (pinned host -> device copy of EVERY step's inputs, overlapped with
+            the previous step) -> InpaintingTrainer.step -> the loss vector read back to the host every step (wgan_l1.py:199-201)."""
+            for g_d, m_d, _ in DevicePrefetcher(HostBatches(ground_h, mask_h, n), dev):
+                tr.step(g_d, m_d, update_g=upd)
+                out_h.copy_(tr.scalars, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+
+        return step, e2e, 2 * ground_h.numel() * 4, out_h.numel() * 4
+
+    step_dev, run_e2e, h2d_bytes, d2h_bytes = workload(args.recipe, R, B)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step_dev()
     l0 = _lib.value("b200_launch_count")
     sync_all()
@@ -300,11 +380,13 @@ def run_b200(args):
     ips_e2e = B * world * args.steps / (ms_e2e * 1e-3)
 
     # ---- per-kernel time of one instrumented step (CUDA events around every C-ABI call, on the launching stream)
-    prof = {}
+    prof, nbytes = {}, {}
 
-    def hook(name):
+    def hook(name, cargs):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        if name in TAIL_BYTES:
+            nbytes[name] = nbytes.get(name, 0) + TAIL_BYTES[name](cargs)
 
         def after():
             e1.record()
@@ -324,6 +406,34 @@ def run_b200(args):
         kernel_ms = {k: sum(a.elapsed_time(b) for a, b in v) for k, v in prof.items()}
     if dist:
         dist.barrier()
+
+    # ---- SURVEY.md §8(d)'s other two lines, measured briefly next to the headline (default recipe, one GPU)
+    also = None
+    if world == 1 and args.recipe == "wgan_l1" and not args.no_also:
+        also = {}
+        try:
+            s2, e2, hb, db = workload("wgan_d_only", R, B)
+            for _ in range(3):
+                s2()
+            m2 = timed(s2, 10)
+            e2(2)
+            m2e = timed(lambda: e2(10), 1)
+            fl2 = flops_per_image(R, "wgan_d_only")
+            also["wgan_d_only"] = {"workload": workload_name("wgan_d_only", R, B, "per GPU"), "value": B * 10 / (m2 * 1e-3), "unit": "images/s",
+                                   "ms_per_step": m2 / 10, "e2e": B * 10 / (m2e * 1e-3), "steps": 10, "whole_step_tflops": fl2["total"] * B * 10 / (m2 * 1e-3) / 1e12}
+            Ri, Bi = DEFAULT_SHAPE["inference"]
+            s3, e3, hb, db = workload("inference", Ri, Bi)
+            for _ in range(3):
+                s3()
+            m3 = timed(s3, 5)
+            e3(1)
+            m3e = timed(lambda: e3(5), 1)
+            fl3 = flops_per_image(Ri, "inference")
+            also["inference"] = {"workload": workload_name("inference", Ri, Bi, "per GPU"), "value": Bi * 5 / (m3 * 1e-3), "unit": "images/s",
+                                 "ms_per_step": m3 / 5, "e2e": Bi * 5 / (m3e * 1e-3), "h2d_bytes_per_step": hb, "d2h_bytes_per_step": db, "steps": 5,
+                                 "whole_step_tflops": fl3["total"] * Bi * 5 / (m3 * 1e-3) / 1e12}
+        except Exception as exc:  # the headline line must survive a problem in the extras
+            also["error"] = repr(exc)
 
     def teardown():
         # captured NCCL collectives pin the communicator: drop the step graphs first; a watchdog guarantees that a teardown problem
@@ -346,43 +456,54 @@ def run_b200(args):
     gemm_ms = sum(kernel_ms.get(k, 0.0) for k in gemm_names)
     gemm_calls = sum(len(prof.get(k, [])) for k in gemm_names)
     achieved = fl["tensor"] * B / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
-    traffic = None  # DRAM bytes per igemm launch from the committed ncu capture of this command (profiles/)
-    tpath = os.path.join(ROOT, "profiles", "r1_igemm_traffic.json")
-    if os.path.exists(tpath) and B == 64 and R == 256 and args.recipe == "wgan_l1":
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    traffic, traffic_src = None, None  # DRAM bytes per igemm launch from the committed ncu capture of this command (profiles/)
+    for tname in ("r2_igemm_traffic.json", "r1_igemm_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if os.path.exists(tpath) and B == 64 and R == 256 and args.recipe == "wgan_l1":
+            traffic, traffic_src = json.load(open(tpath)).get("dram_bytes_per_launch"), tname
+            break
     step_ms_instr = sum(kernel_ms.values())
+    # which measured peak applies: the timed region of a default run is a fraction of a second at boost clocks and far below the
+    # power cap — the burst figure (a kernel timed alone); a long run that pulls the clocks down is compared with the sustained one
+    at_boost = bool(clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz") and clocks["sm_mhz"] >= 0.95 * clocks["sm_max_mhz"])
+    peak, peak_name = (peaks["tf_burst"], "bf16_tflops (burst)") if at_boost else (peaks["tf_sustained"], "bf16_tflops_sustained")
     roofline = {
         "bound": "tensor", "kernel": "igemm_kernel (tcgen05 implicit GEMM: conv / convT phases / wgrad)", "achieved": achieved,
-        "peak": peaks["tf_sustained"], "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)", "unit": "TFLOP/s",
-        "frac": (achieved / peaks["tf_sustained"]) if achieved else None, "traffic": traffic,
-        "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_igemm_traffic.json)",
+        "peak": peak, "peak_source": f"{peaks['source']} {peak_name}: SM clock {clocks.get('sm_mhz') if clocks else None} MHz during the timed region",
+        "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
+        "frac_of_burst": (achieved / peaks["tf_burst"]) if achieved else None, "frac_of_sustained": (achieved / peaks["tf_sustained"]) if achieved else None,
+        "traffic": traffic, "traffic_unit": f"DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/{traffic_src})",
         "launches_per_step": gemm_calls, "avg_launch_ms": gemm_ms / max(gemm_calls, 1), "algorithmic_gflop_per_step": fl["tensor"] * B / 1e9,
         "share_of_step": gemm_ms / step_ms_instr if step_ms_instr else None,
         "step_breakdown_ms": {k: round(v, 4) for k, v in sorted(kernel_ms.items(), key=lambda kv: -kv[1])},
         "whole_step_tflops": fl["total"] * B * world * args.steps / (ms * 1e-3) / 1e12,
     }
+    tail = {k: {"ms": round(kernel_ms[k], 4), "algorithmic_mb": round(nbytes[k] / 1e6, 1), "gbps": round(nbytes[k] / (kernel_ms[k] * 1e-3) / 1e9, 1),
+                "frac_of_hbm_peak": round(nbytes[k] / (kernel_ms[k] * 1e-3) / 1e9 / peaks["hbm_gbs"], 3), "calls": len(prof[k])}
+            for k in sorted(nbytes, key=lambda k: -kernel_ms.get(k, 0.0)) if kernel_ms.get(k, 0.0) > 0}
+    tail_ms = sum(v for k, v in kernel_ms.items() if k not in gemm_names)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cb = args.ref_batch
-        c_ips, c_spt = time_cpu(args.recipe, R, cb, 2, 1)
+        c_ips, c_spt = time_cpu(args.recipe, R, cb, 5, 1)
         cpu = {"value": c_ips, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": f"2 steps x {cb} images of the same {args.recipe} step at {R}x{R} (oracle port of the reference, fp32 torch CPU, all host threads)"}
-    nbytes = ground_h.numel() * 4
+               "sample": f"5 steps x {cb} images of the same {args.recipe} workload at {R}x{R} (oracle port of the reference, fp32 torch CPU, all host threads)"}
     line = {
-        "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": metric_name(args.recipe, R), "value": ips, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"{args.recipe}: U-Net generator + PatchGAN global D, full train step (D update + G update), {R}x{R}, batch {B} per GPU",
+        "config": {"workload": workload_name(args.recipe, R, B, "per GPU"),
                    "recipe": args.recipe, "res": R, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
-                   "dropout": True, "l2": "no flush: one step streams ~6 GB of activations/gradients, far larger than the 126 MB L2",
-                   "bn": "per-replica batch statistics", "bucket_mb": args.bucket_mb,
-                   "launch": "eager (one ctypes call per kernel)" if args.no_graph else "whole step replayed as one CUDA graph"},
-        "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": 2 * nbytes, "d2h_bytes_per_step": out_h.numel() * 4,
-                "ms_per_step": ms_e2e / args.steps},
+                   "dropout": not infer, "l2": "no flush: one step streams several GB of activations/gradients, far larger than the 126 MB L2",
+                   "bn": "running statistics (eval)" if infer else "per-replica batch statistics", "bucket_mb": args.bucket_mb,
+                   "launch": "eager (one ctypes call per kernel)" if (args.no_graph or infer) else "whole step replayed as one CUDA graph"},
+        "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "host_enqueue_ms_per_step": host_ms,
         "clocks": clocks,
         "roofline": roofline,
+        "tail": {"ms_per_step": round(tail_ms, 4), "hbm_peak_gbs": peaks["hbm_gbs"], "kernels": tail},
         "cpu_baseline": cpu,
+        "also": also,
     }
     print(json.dumps(line), flush=True)
     teardown()
@@ -395,13 +516,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--recipe", default="wgan_l1", choices=list(RECIPES))
-    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
-    ap.add_argument("--res", type=int, default=256)
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU per step (default 64; inference 128)")
+    ap.add_argument("--res", type=int, default=None, help="image side (default 256; inference 512)")
     ap.add_argument("--ref-batch", type=int, default=4, help="images per step of the bounded CPU sample")
     ap.add_argument("--bucket-mb", type=float, default=25.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the short D-only / inference measurements of the default run")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying the captured step graph")
     args = ap.parse_args()
+    dres, dbatch = DEFAULT_SHAPE.get(args.recipe, (256, 64))
+    args.res = args.res or dres
+    args.batch = args.batch or dbatch
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "b200" and args.gpus != world:
         if world == 1 and args.gpus > 1:

@@ -124,13 +124,14 @@ def exported_symbols():
     return list(VALUE_FUNCS) + list(SIGNATURES)
 
 
-# optional per-call hook: PROFILE(name) -> callable run after the call (bench.py times kernels with CUDA events this way)
+# optional per-call hook: PROFILE(name, args) -> callable run after the call (bench.py times kernels with CUDA events this way and derives
+# the algorithmic bytes of the memory-bound calls from their arguments)
 PROFILE = None
 
 
 def call(name: str, *args):
     lib = load()
-    after = PROFILE(name) if PROFILE is not None else None
+    after = PROFILE(name, args) if PROFILE is not None else None
     rc = getattr(lib, name)(*args)
     if after is not None:
         after()

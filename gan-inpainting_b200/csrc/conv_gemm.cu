@@ -735,6 +735,11 @@ static int map_weights(CUtensorMap* m, const void* base, int rows, int K, int BN
 
 static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && e[0]) ? atoi(e) : dflt;
+}
+
 static void pixel_box(int Hs, int Ws, int npix, int* tw, int* th, int* nb) {
   *tw = Ws < npix ? Ws : npix;
   int rest = npix / *tw;
@@ -797,8 +802,16 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, IGemmParams& p, cu
   p.tiles_h_sh = ilog2(p.tiles_h);
   p.ck_sh = ilog2(p.C_k);
   p.cpt_sh = ilog2(p.cpt);
-  p.kpb = (p.mode != MODE_WGRAD && p.BN <= 128 && p.kb_per_tile % 2 == 0) ? 2 : 1;
-  const int stage_bytes = p.kpb * (kATileBytes + (p.pair ? p.BN / 2 : p.BN) * 128);  // per CTA
+  // 64-wide k-blocks per pipeline stage.  The per-stage hand-shake (full / empty mbarrier round trip through the two single-issuer
+  // warps) is a first-order cost of the narrow tiles: measured on B200, N = 64 tiles gain 8 % with four k-blocks per stage (two
+  // 80 KB stages), N = 128 tiles are fastest with two (four leave too few stages); wide tiles keep one.  B200_KPB64 / B200_KPB128
+  // override the choice for A/B runs.
+  static const int kpb64 = env_int("B200_KPB64", 4), kpb128 = env_int("B200_KPB128", 2);
+  p.kpb = 1;
+  if (p.mode != MODE_WGRAD && p.BN <= 128) {
+    p.kpb = p.BN <= 64 ? kpb64 : kpb128;
+    while (p.kpb > 1 && p.kb_per_tile % p.kpb) p.kpb >>= 1;
+  }
   const bool has_stats = p.stats != nullptr, has_bwd = p.bwd.y != nullptr;
   // shared memory behind the pipeline stages, sized per epilogue variant: barriers, the per-quadrant statistics buffer
   // (double buffered over tiles unless that would cost a pipeline stage), the per-CTA running sums, the BatchNorm
@@ -817,9 +830,14 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, IGemmParams& p, cu
     off += kEpiWarps * tile_bytes;
     return 1024 + 256 + off;
   };
-  int extra = layout(2);
-  if (has_stats && (227 * 1024 - layout(1)) / stage_bytes > (227 * 1024 - extra) / stage_bytes) extra = layout(1);
-  else extra = layout(2);
+  int extra = 0, stage_bytes = 0;
+  for (;; p.kpb >>= 1) {  // fewer k-blocks per stage until at least two stages fit
+    stage_bytes = p.kpb * (kATileBytes + (p.pair ? p.BN / 2 : p.BN) * 128);  // per CTA
+    extra = layout(2);
+    if (has_stats && (227 * 1024 - layout(1)) / stage_bytes > (227 * 1024 - extra) / stage_bytes) extra = layout(1);
+    else extra = layout(2);
+    if (p.kpb == 1 || (227 * 1024 - extra) / stage_bytes >= 2) break;
+  }
   if (p.stages <= 0) {
     p.stages = (227 * 1024 - extra) / stage_bytes;
     if (p.stages > 8) p.stages = 8;

@@ -176,60 +176,67 @@ struct ApplyParams {
   const uint32_t* seed_ctr;  // optional device counter (b200_set_seed_counter)
 };
 
+__device__ __forceinline__ void bn_act_one(const ApplyParams& p, uint32_t seed, unsigned idx, unsigned cmask, const uint4 v) {
+  const size_t pix = idx >> p.cshift;
+  const int c0 = (int)(idx & cmask) * 8;
+  const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+  float f[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = unpack_bf16x2(u[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+  if (p.scale) {
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + c0)), s1 = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + 4));
+    const float4 h0 = __ldg(reinterpret_cast<const float4*>(p.shift + c0)), h1 = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + 4));
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], sc[i], sh[i]);
+  }
+  if (p.dropout) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = dropout_keep(seed, (uint64_t)(pix * p.C + c0 + i)) ? 2.f * f[i] : 0.f;
+  }
+  if (p.act == ACT_LEAKY) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = f[i] > 0.f ? f[i] : 0.2f * f[i];
+  } else if (p.act == ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+  }
+  if (p.out1) {
+    uint4 o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    *reinterpret_cast<uint4*>(p.out1 + pix * p.ld1 + p.off1 + c0) = o;
+  }
+  if (p.out2) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+    uint4 o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    *reinterpret_cast<uint4*>(p.out2 + pix * p.ld2 + p.off2 + c0) = o;
+  }
+}
+
 __global__ void __launch_bounds__(256) bn_act_kernel(const ApplyParams p) {
   b200::pdl_enter();
   const unsigned total = (unsigned)p.P << p.cshift;
   const unsigned cmask = (1u << p.cshift) - 1u;
   const uint32_t seed = p.dropout ? dropout_seed(p.seed, p.seed_ctr) : 0u;
-  // software-pipelined: the next element's 16-byte load is in flight while this one is processed (2048 threads x 16 B per SM
-  // is less than the bandwidth-latency product of HBM3e)
+  // software-pipelined, two 16-byte elements per thread and iteration: the next pair's loads are in flight while this pair is
+  // processed (up to 4 x 16 B outstanding per thread; 2048 threads x 16 B per SM is less than the bandwidth-latency product of HBM3e)
   const unsigned stride = gridDim.x * blockDim.x;
   unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
-  uint4 vnext = make_uint4(0u, 0u, 0u, 0u);
-  if (idx < total) vnext = __ldg(reinterpret_cast<const uint4*>(p.y + (size_t)(idx >> p.cshift) * p.C + (int)(idx & cmask) * 8));
-  for (; idx < total; idx += stride) {
-    const size_t pix = idx >> p.cshift;
-    const int c0 = (int)(idx & cmask) * 8;
-    const uint4 v = vnext;
-    const unsigned nidx = idx + stride;
-    if (nidx < total) vnext = __ldg(reinterpret_cast<const uint4*>(p.y + (size_t)(nidx >> p.cshift) * p.C + (int)(nidx & cmask) * 8));
-    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
-    float f[8];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 t = unpack_bf16x2(u[i]);
-      f[2 * i] = t.x;
-      f[2 * i + 1] = t.y;
-    }
-    if (p.scale) {
-      const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + c0)), s1 = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + 4));
-      const float4 h0 = __ldg(reinterpret_cast<const float4*>(p.shift + c0)), h1 = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + 4));
-      const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-      const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], sc[i], sh[i]);
-    }
-    if (p.dropout) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = dropout_keep(seed, (uint64_t)(pix * p.C + c0 + i)) ? 2.f * f[i] : 0.f;
-    }
-    if (p.act == ACT_LEAKY) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = f[i] > 0.f ? f[i] : 0.2f * f[i];
-    } else if (p.act == ACT_RELU) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
-    }
-    if (p.out1) {
-      uint4 o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-      *reinterpret_cast<uint4*>(p.out1 + pix * p.ld1 + p.off1 + c0) = o;
-    }
-    if (p.out2) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
-      uint4 o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-      *reinterpret_cast<uint4*>(p.out2 + pix * p.ld2 + p.off2 + c0) = o;
-    }
+  auto ld = [&](unsigned i) {
+    return i < total ? __ldg(reinterpret_cast<const uint4*>(p.y + (size_t)(i >> p.cshift) * p.C + (int)(i & cmask) * 8)) : make_uint4(0u, 0u, 0u, 0u);
+  };
+  uint4 n0 = ld(idx), n1 = ld(idx + stride);
+  for (; idx < total; idx += 2 * stride) {
+    const uint4 v0 = n0, v1 = n1;
+    n0 = ld(idx + 2 * stride);
+    n1 = ld(idx + 3 * stride);
+    bn_act_one(p, seed, idx, cmask, v0);
+    if (idx + stride < total) bn_act_one(p, seed, idx + stride, cmask, v1);
   }
 }
 

@@ -105,7 +105,7 @@ class GradBucketer:
 
 class InpaintingTrainer:
     def __init__(self, recipe: str, net_G, net_D, net_D_local=None, recon: str = "l1", lambdas=(300.0, 300.0), clip: float = 0.01,
-                 distributed: bool = False, bucket_mb: float = 25.0, log_grad_means: bool = False, graph: bool = False):
+                 distributed: bool = False, bucket_mb: float = 25.0, log_grad_means: bool = False, graph: bool = False, rank: Optional[int] = None):
         if recipe not in ("wgan", "minimax", "global_local"):
             raise ValueError(recipe)
         if recipe == "global_local" and net_D_local is None:
@@ -135,11 +135,13 @@ class InpaintingTrainer:
         self.scalars = torch.zeros(NSCALARS, dtype=torch.float32, device=dev)
         self.step_count = 0
         self.world = 1
+        self.rank = 0
         self.buckets: Dict[int, GradBucketer] = {}
         if distributed:
             import torch.distributed as dist
 
             self.world = dist.get_world_size()
+            self.rank = dist.get_rank()
             for fg in (self.fG, self.fD, self.fDl):
                 if fg is not None:
                     dist.broadcast(fg.params, src=0)
@@ -159,6 +161,11 @@ class InpaintingTrainer:
         self._graphs: Dict[tuple, "_CapturedStep"] = {}
         self._seed_ctr = torch.zeros(1, dtype=torch.int32, device=dev)  # device-side dropout seed counter (b200_set_seed_counter)
         self._seed_ctr_host = 0
+        if rank is not None:
+            self.rank = int(rank)
+        # every data-parallel replica draws its own dropout masks (stock DDP: one RNG stream per rank): the rank enters the seed
+        # of every mask; rank 0 keeps the single-GPU stream
+        self._seed_base = (self.rank * 0x632BE5AB) & 0x3FFFFFF
 
     # ------------------------------------------------------------------------------------------ helpers
     def _slot(self, name_or_index):
@@ -211,7 +218,7 @@ class InpaintingTrainer:
         if self.graph and seed is None:
             return self._step_graphed(ground, mask, bool(update_g))
         self.step_count += 1
-        seed = self.step_count if seed is None else seed
+        seed = self.step_count + self._seed_base if seed is None else seed
         if self.recipe == "global_local":
             return self._step_global_local(ground.contiguous().float(), mask.contiguous().float(), seed)
         return self._step_gan(ground.contiguous().float(), mask.contiguous().float(), update_g, seed)
@@ -228,7 +235,7 @@ class InpaintingTrainer:
             # first batch of this shape: a real eager step (allocates every scratch buffer / pack table at its final size), then
             # the capture — which only records — for all later batches
             self.step_count += 1
-            out = self._run(ground.contiguous().float(), mask.contiguous().float(), update_g, self.step_count)
+            out = self._run(ground.contiguous().float(), mask.contiguous().float(), update_g, self.step_count + self._seed_base)
             self._graphs[key] = _CapturedStep(self, ground, mask, update_g)
             return out
         self.step_count += 1
@@ -399,7 +406,7 @@ class _CapturedStep:
         try:
             with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
                 call("b200_step_inc", ptr(tr._seed_ctr), stream())
-                tr._run(self.ground, self.mask, update_g, 0)
+                tr._run(self.ground, self.mask, update_g, tr._seed_base)
         finally:
             _lib.value("b200_set_seed_counter", None)
         self.launches = int(_lib.value("b200_launch_count") - n0)
