@@ -79,6 +79,11 @@ struct IGemmParams {
   int pair;              // 1: CTA pairs (cta_group::2), num_tiles counts 256-pixel pair tiles
   int kpb;               // 64-wide k-blocks per pipeline stage (2 for narrow N tiles: halves the per-stage barrier overhead
                          // of the single issuing thread, which otherwise exceeds the MMA time of a 128 x 64 x 64 block)
+  int win;               // 1: window operand staging (see igemm_kernel): the activation operand of a 16 x 8-pixel tile is staged ONCE per
+                         // parity plane (conv) / phase (convT) and 64-channel block as a 17 x 9-pixel halo window; the four filter taps
+                         // that read it are four shared-memory descriptors into that window instead of four TMA boxes
+  int sa;                // window slots of the activation ring (win)
+  int tpb;               // filter taps (weight boxes) per stage of the weight ring (win); `stages` counts the weight stages
   float* stats;          // optional (fprop modes): per-CTA column sums of the stored bf16 outputs,
                          // [gridDim.x][2][Cout] (sum, sum of squares) for the BatchNorm that follows;
                          // with `bwd`: (sum dz, sum dz*y) of the fused columns instead
@@ -89,6 +94,13 @@ constexpr int kNumSMs = 148;
 constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quadrant, alternating 32-column chunks
 constexpr int kThreads = 64 + 32 * kEpiWarps;      // warp 0 = TMA, warp 1 = MMA, warps 2.. = epilogue
 constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 bf16 (K-major) or 2 x (64 px x 64 ch) (MN-major)
+// window operand staging: a pixel tile is 8 wide x 16 high; its halo window is 9 x 17 pixels x 64 channels = 153 rows of 128 bytes
+constexpr int kWinTw = 8, kWinTh = 16;
+constexpr int kWinRows = (kWinTw + 1) * (kWinTh + 1);
+constexpr int kWinBytes = kWinRows * 128;              // 19584
+constexpr int kWinSlotBytes = 20 * 1024;               // slot pitch (1024-byte aligned: SWIZZLE_128B)
+constexpr int kWinSbo = (kWinTw + 1) * 128;            // byte distance of consecutive 8-pixel row groups inside a window
+constexpr int kBarrierBytes = 512;                     // mbarriers + TMEM pointer behind the operand rings
 constexpr int kStatTileBytes = 4096 + 2048;           // per epilogue warp: 32 x 32 fp32 of dz + 32 x 32 bf16 of y (forward: 32 x 32 bf16 only)
 
 // Epilogue variants (compile-time: the per-element code has no branches and each variant is a small kernel)
@@ -257,7 +269,17 @@ __device__ __forceinline__ void tile_column_sums_f32(uint8_t* wbuf, int lane, fl
 // L2 per flop drop by a third at BN = 256 — the GEMMs with 128 x BN single-CTA tiles are bound by exactly that traffic.
 // The even CTA issues the MMAs; TMA transaction bytes of both CTAs are counted on its barriers; tcgen05.commit multicasts
 // the "slot free" / "accumulator ready" arrivals to both CTAs; both epilogues release the accumulator on the even CTA.
-template <class E, bool PAIR>
+//
+// WIN (window operand staging, fprop / dgrad modes with at least 16 x 8 output pixels per image): every input pixel of a
+// stride-2 4x4 convolution is read by 4 filter taps (of the 2x2-tap phase of a transposed convolution: by all 4), so staging
+// one TMA box per tap pulls each activation through L2 -> shared memory four times — and that stream, not the tensor pipe,
+// bounds these GEMMs (~42 B/clk/SM of L2 bandwidth against 128 x N x 16 MACs per 4 KB of A).  Here the 17 x 9-pixel halo
+// window of a 16 x 8-pixel tile is staged ONCE per (parity plane | phase, 64-channel block) and tap (eh, ew) is the K-major
+// SWIZZLE_128B descriptor that starts at window row eh * 9 + ew with a stride of 9 rows between its 8-row groups: the tensor
+// core applies the 128-byte swizzle to absolute shared-memory addresses, so a descriptor may start at any 128-byte row of a
+// TMA-written window (tools/umma_probe.cu checks exactly this on the hardware).  Activation bytes per MMA drop 3.3x; the
+// weights ride in their own ring (`tpb` taps per stage) because the two operands now arrive at different rates.
+template <class E, bool PAIR, bool WIN>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const IGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -265,16 +287,20 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   // LDS / STS instead of generic loads / stores for everything the epilogue stages here
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int b_bytes = (PAIR ? p.BN / 2 : p.BN) * 128;  // per CTA
-  const int stage_bytes = p.kpb * (kATileBytes + b_bytes);
+  // WIN: [sa window slots][stages weight stages of tpb boxes]; else [stages of kpb (A tile + B tile)]
+  const int stage_bytes = WIN ? p.tpb * b_bytes : p.kpb * (kATileBytes + b_bytes);
+  uint8_t* smem_b = smem + (WIN ? p.sa * kWinSlotBytes : 0);
   const int rank = PAIR ? (int)cluster_ctarank() : 0;
   const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // first work item of this CTA (pair)
   const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  uint64_t* full_bar = (uint64_t*)(smem + p.stages * stage_bytes);
+  uint64_t* full_bar = (uint64_t*)(smem_b + p.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full_bar = empty_bar + p.stages;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
-  uint32_t* tmem_ptr_smem = (uint32_t*)(tmem_empty_bar + 2);
-  uint8_t* epi_smem = (uint8_t*)(tmem_ptr_smem + 4);
+  uint64_t* fullA_bar = tmem_empty_bar + 2;         // [sa] (WIN)
+  uint64_t* emptyA_bar = fullA_bar + (WIN ? p.sa : 0);
+  uint32_t* tmem_ptr_smem = (uint32_t*)(emptyA_bar + (WIN ? p.sa : 0));
+  uint8_t* epi_smem = (uint8_t*)full_bar + kBarrierBytes;
   float* stat_smem = (float*)epi_smem;                        // [parity][TMEM quadrant][sum | sumsq][BN]
   float* stat_acc = (float*)(epi_smem + p.off_acc);           // per-CTA running [sum | sumsq][Cout]
   float* bn_ss = (float*)(epi_smem + p.off_ss);               // interleaved (scale, shift)[Cy]
@@ -293,6 +319,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
       mbar_init(&tmem_empty_bar[b], PAIR ? 2 * kEpiWarps : kEpiWarps);  // one arrival per epilogue warp (of both CTAs)
+    }
+    if (WIN) {
+      for (int a = 0; a < p.sa; ++a) {
+        mbar_init(&fullA_bar[a], 1);
+        mbar_init(&emptyA_bar[a], 1);
+      }
     }
     fence_barrier_init();
   }
@@ -314,7 +346,63 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   // and may overlap the previous kernel's tail; from here on its results are needed
   pdl_enter();
 
-  if (warp == 0) {
+  if (warp == 0 && WIN) {
+    // ===================== TMA producer, window operand staging =====================
+    const uint32_t a_tx = (uint32_t)kWinBytes * (PAIR ? 2u : 1u);
+    const uint32_t b_tx = (uint32_t)stage_bytes * (PAIR ? 2u : 1u);
+    const int nB = PAIR ? rank * (p.BN / 2) : 0;
+    const int planes = (p.mode == MODE_CONV_S2) ? 4 : 1;
+    int sa = 0, sb = 0;
+    uint32_t para = 0, parb = 0;
+    for (int t = tile0; t < p.num_tiles; t += tile_step) {
+      const TileCoord c = decode_tile<PAIR>(p, t, rank);
+      const int ph_p = c.phase >> 1, ph_q = c.phase & 1;
+      for (int pl = 0; pl < planes; ++pl) {
+        const int pr = pl >> 1, pc = pl & 1;  // row / column parity of the input plane (conv)
+        for (int cc = 0; cc < p.cpt; ++cc) {
+          mbar_wait(&emptyA_bar[sa], para ^ 1u);
+          if (!PAIR || rank == 0) mbar_arrive_expect_tx_w(&fullA_bar[sa], a_tx);
+          uint8_t* sW = smem + sa * kWinSlotBytes;
+          if (p.mode == MODE_CONV_S2) {
+            // plane (pr, pc) holds input rows 2*h2 + pr: taps kh = 2*eh + 1 - pr read h2 = oh + eh - pr, so the window starts at h0 - pr
+            if (PAIR) tma2_load_5d_w(sW, &tmA, &fullA_bar[sa], pc * p.C_k + cc * 64, c.w0 - pc, pr, c.h0 - pr, c.b0);
+            else tma_load_5d_w(sW, &tmA, &fullA_bar[sa], pc * p.C_k + cc * 64, c.w0 - pc, pr, c.h0 - pr, c.b0);
+          } else {
+            // phase (p, q), tap (a, b) reads input pixel (i + p + a - 1, j + q + b - 1): the window starts at (h0 + p - 1, w0 + q - 1)
+            if (PAIR) tma2_load_4d_w(sW, &tmA, &fullA_bar[sa], cc * 64, c.w0 + ph_q - 1, c.h0 + ph_p - 1, c.b0);
+            else tma_load_4d_w(sW, &tmA, &fullA_bar[sa], cc * 64, c.w0 + ph_q - 1, c.h0 + ph_p - 1, c.b0);
+          }
+          for (int tg = 0; tg < 4; tg += p.tpb) {
+            mbar_wait(&empty_bar[sb], parb ^ 1u);
+            if (!PAIR || rank == 0) mbar_arrive_expect_tx_w(&full_bar[sb], b_tx);
+            for (int u = 0; u < p.tpb; ++u) {
+              const int j = tg + u, eh = j >> 1, ew = j & 1;
+              uint8_t* sB = smem_b + sb * stage_bytes + u * b_bytes;
+              int kb, row;
+              if (p.mode == MODE_CONV_S2) {
+                const int kh = 2 * eh + 1 - pr, kw = 2 * ew + 1 - pc;
+                kb = ((kh * 4 + kw) << p.cpt_sh) + cc;
+                row = c.n0 + nB;
+              } else {
+                kb = (j << p.cpt_sh) + cc;
+                row = c.phase * p.Cout + c.n0 + nB;
+              }
+              if (PAIR) tma2_load_2d_w(sB, &tmB, &full_bar[sb], kb * 64, row);
+              else tma_load_2d_w(sB, &tmB, &full_bar[sb], kb * 64, row);
+            }
+            if (++sb == p.stages) {
+              sb = 0;
+              parb ^= 1u;
+            }
+          }
+          if (++sa == p.sa) {
+            sa = 0;
+            para ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 0) {
     // ===================== TMA producer =====================
     {  // the whole warp runs the loop; elect.sync inside the *_w wrappers picks the issuing lane
       const uint32_t tx_bytes = (uint32_t)stage_bytes * (PAIR ? 2u : 1u);  // PAIR: both CTAs' bytes land on the even CTA's barrier
@@ -375,6 +463,55 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             par ^= 1u;
           }
         }
+      }
+    }
+  } else if (warp == 1 && WIN) {
+    // ===================== MMA issuer, window operand staging =====================
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, p.BN, 0, 0);
+      const int nwin = ((p.mode == MODE_CONV_S2) ? 4 : 1) * p.cpt;
+      int sa = 0, sb = 0, lt = 0;
+      uint32_t para = 0, parb = 0;
+      for (int t = tile0; t < p.num_tiles; t += tile_step, ++lt) {
+        const int buf = lt & 1;
+        mbar_wait(&tmem_empty_bar[buf], (uint32_t)(((lt >> 1) & 1) ^ 1));  // the epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_addr = tmem_base + (uint32_t)(buf * p.BN);
+        for (int wi = 0; wi < nwin; ++wi) {
+          mbar_wait(&fullA_bar[sa], para);
+          tc_fence_after();
+          const uint32_t w_addr = smem_u32(smem + sa * kWinSlotBytes);
+          for (int tg = 0; tg < 4; tg += p.tpb) {
+            mbar_wait(&full_bar[sb], parb);
+            tc_fence_after();
+            const uint32_t b_addr = smem_u32(smem_b + sb * stage_bytes);
+            for (int u = 0; u < p.tpb; ++u) {
+              const int j = tg + u;
+              const uint32_t a_addr = w_addr + (uint32_t)(((j >> 1) * (kWinTw + 1) + (j & 1)) * 128);  // tap (eh, ew) = window row eh * 9 + ew
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 16u, (uint32_t)kWinSbo);
+                const uint64_t db = make_smem_desc_sw128(b_addr + u * b_bytes + k * 32, 16u, 1024u);
+                if (PAIR) umma_bf16_2cta_w(d_addr, da, db, idesc, (wi > 0 || j > 0 || k > 0) ? 1u : 0u);
+                else umma_bf16_w(d_addr, da, db, idesc, (wi > 0 || j > 0 || k > 0) ? 1u : 0u);
+              }
+            }
+            if (PAIR) umma_commit_2cta_w(&empty_bar[sb]);
+            else umma_commit_w(&empty_bar[sb]);
+            if (++sb == p.stages) {
+              sb = 0;
+              parb ^= 1u;
+            }
+          }
+          if (PAIR) umma_commit_2cta_w(&emptyA_bar[sa]);  // the window is free once the MMAs of its last tap have retired
+          else umma_commit_w(&emptyA_bar[sa]);
+          if (++sa == p.sa) {
+            sa = 0;
+            para ^= 1u;
+          }
+        }
+        if (PAIR) umma_commit_2cta_w(&tmem_full_bar[buf]);
+        else umma_commit_w(&tmem_full_bar[buf]);
       }
     }
   } else if (warp == 1) {
@@ -711,7 +848,7 @@ static int encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* 
   return B200_OK;
 }
 
-// plain [B,H,W,C] view, box [64 ch, tw, th, nb]
+// plain [B,H,W,C] view, box [64 ch, tw, th, nb] (window operand staging passes the halo window tw + 1, th + 1)
 static int map_nhwc(CUtensorMap* m, const void* base, int B, int H, int W, int C, int ld, int tw, int th, int nb) {
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t st[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
@@ -753,11 +890,11 @@ static int ilog2(int v) {
   return s;
 }
 
-template <class E>
-static void launch_variant(const CUtensorMap& a, const CUtensorMap& b, const IGemmParams& p, int grid, size_t smem, cudaStream_t stream) {
+template <class E, bool WIN>
+static void launch_variant_w(const CUtensorMap& a, const CUtensorMap& b, const IGemmParams& p, int grid, size_t smem, cudaStream_t stream) {
   if (p.pair) {
     static std::once_flag once2;
-    std::call_once(once2, [] { cudaFuncSetAttribute(igemm_kernel<E, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+    std::call_once(once2, [] { cudaFuncSetAttribute(igemm_kernel<E, true, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kThreads);
@@ -772,12 +909,24 @@ static void launch_variant(const CUtensorMap& a, const CUtensorMap& b, const IGe
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = b200_pdl_enabled() ? 2 : 1;
-    cudaLaunchKernelEx(&cfg, igemm_kernel<E, true>, a, b, p);
+    cudaLaunchKernelEx(&cfg, igemm_kernel<E, true, WIN>, a, b, p);
     return;
   }
   static std::once_flag once;
-  std::call_once(once, [] { cudaFuncSetAttribute(igemm_kernel<E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
-  B200_LAUNCH((igemm_kernel<E, false>), grid, kThreads, smem, stream, a, b, p);
+  std::call_once(once, [] { cudaFuncSetAttribute(igemm_kernel<E, false, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+  B200_LAUNCH((igemm_kernel<E, false, WIN>), grid, kThreads, smem, stream, a, b, p);
+}
+template <class E>
+static void launch_variant(const CUtensorMap& a, const CUtensorMap& b, const IGemmParams& p, int grid, size_t smem, cudaStream_t stream) {
+  if (p.win) launch_variant_w<E, true>(a, b, p, grid, smem, stream);
+  else launch_variant_w<E, false>(a, b, p, grid, smem, stream);
+}
+
+// Window operand staging applies to the fprop / dgrad modes when an image holds at least one 16 x 8-pixel tile and K is not
+// split; B200_WINDOW=0 falls back to one TMA box per filter tap (A/B comparison).
+static bool want_window(int Hs, int Ws, int ksplit) {
+  static const bool enabled = env_int("B200_WINDOW", 1) != 0;
+  return enabled && ksplit <= 1 && Hs >= kWinTh && Ws >= kWinTw;
 }
 
 // CTA pairs pay when the single-CTA tiles are bound by operand traffic: fprop / dgrad with enough pixel tiles to give every
@@ -828,28 +977,51 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, IGemmParams& p, cu
     p.off_tile = off;
     p.tile_bytes = tile_bytes;
     off += kEpiWarps * tile_bytes;
-    return 1024 + 256 + off;
+    return 1024 + kBarrierBytes + off;
   };
-  int extra = 0, stage_bytes = 0;
-  for (;; p.kpb >>= 1) {  // fewer k-blocks per stage until at least two stages fit
-    stage_bytes = p.kpb * (kATileBytes + (p.pair ? p.BN / 2 : p.BN) * 128);  // per CTA
+  int extra = 0, stage_bytes = 0, ring_a = 0;
+  if (p.win) {
+    // activation ring: `sa` halo windows; weight ring: stages of `tpb` taps (at most 32 KB per stage).  The statistics buffer is
+    // double buffered when that leaves at least 3 window slots and 2 windows' worth of weights in flight.
+    const int b_bytes = (p.pair ? p.BN / 2 : p.BN) * 128;
+    static const int tpb_env = env_int("B200_WIN_TPB", 0), sa_env = env_int("B200_WIN_SA", 0);
+    p.tpb = b_bytes * 4 <= 32 * 1024 ? 4 : (b_bytes * 2 <= 32 * 1024 ? 2 : 1);
+    if (tpb_env == 1 || tpb_env == 2 || tpb_env == 4) p.tpb = tpb_env;
+    stage_bytes = p.tpb * b_bytes;
+    const int per_window = (4 / p.tpb) * stage_bytes;  // weight bytes one window consumes
+    auto fits = [&](int ex, int sa) { return (227 * 1024 - ex - sa * kWinSlotBytes) / stage_bytes; };
     extra = layout(2);
-    if (has_stats && (227 * 1024 - layout(1)) / stage_bytes > (227 * 1024 - extra) / stage_bytes) extra = layout(1);
-    else extra = layout(2);
-    if (p.kpb == 1 || (227 * 1024 - extra) / stage_bytes >= 2) break;
+    if (has_stats && fits(extra, 3) * stage_bytes < 2 * per_window) extra = layout(1);
+    p.sa = sa_env > 0 ? sa_env : (fits(extra, 4) * stage_bytes >= 2 * per_window ? 4 : 3);
+    while (p.sa > 2 && fits(extra, p.sa) < 2) --p.sa;
+    ring_a = p.sa * kWinSlotBytes;
+    p.stages = fits(extra, p.sa);
+    if (p.stages > 12) p.stages = 12;
+    if (2 * p.sa + 2 * p.stages + 4 > (kBarrierBytes - 16) / 8) {
+      b200_set_error("igemm: too many pipeline barriers");
+      return B200_ERR_ARG;
+    }
+  } else {
+    for (;; p.kpb >>= 1) {  // fewer k-blocks per stage until at least two stages fit
+      stage_bytes = p.kpb * (kATileBytes + (p.pair ? p.BN / 2 : p.BN) * 128);  // per CTA
+      extra = layout(2);
+      if (has_stats && (227 * 1024 - layout(1)) / stage_bytes > (227 * 1024 - extra) / stage_bytes) extra = layout(1);
+      else extra = layout(2);
+      if (p.kpb == 1 || (227 * 1024 - extra) / stage_bytes >= 2) break;
+    }
+    if (p.stages <= 0) {
+      p.stages = (227 * 1024 - extra) / stage_bytes;
+      if (p.stages > 8) p.stages = 8;
+    }
   }
-  if (p.stages <= 0) {
-    p.stages = (227 * 1024 - extra) / stage_bytes;
-    if (p.stages > 8) p.stages = 8;
-  }
-  if (p.stages < 2 || (size_t)p.stages * stage_bytes + extra > 227 * 1024) {
+  if (p.stages < 2 || (size_t)p.stages * stage_bytes + ring_a + extra > 227 * 1024) {
     b200_set_error("igemm: pipeline does not fit shared memory");
     return B200_ERR_ARG;
   }
   uint32_t cols = 32;
   while ((int)cols < 2 * p.BN) cols <<= 1;
   p.tmem_cols = cols;
-  const size_t smem = (size_t)p.stages * stage_bytes + extra;
+  const size_t smem = (size_t)p.stages * stage_bytes + ring_a + extra;
   const int grid = p.pair ? 2 * (p.num_tiles < kNumSMs / 2 ? p.num_tiles : kNumSMs / 2) : (p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs);
   if (grid_out) *grid_out = grid;
   const bool bn = p.bwd.scale != nullptr, g2 = p.bwd.g2 != nullptr;
@@ -963,7 +1135,9 @@ int b200_conv_s2_gemm(const void* x, int B, int H, int W, int Cin, const void* w
   p.B = B;
   p.Hs = H / 2;
   p.Ws = W / 2;
-  pixel_box(p.Hs, p.Ws, 128, &p.tw, &p.th, &p.nb);
+  p.win = want_window(p.Hs, p.Ws, ksplit) ? 1 : 0;
+  if (p.win) p.tw = kWinTw, p.th = kWinTh, p.nb = 1;
+  else pixel_box(p.Hs, p.Ws, 128, &p.tw, &p.th, &p.nb);
   p.tiles_w = p.Ws / p.tw;
   p.tiles_h = p.Hs / p.th;
   const int tiles_b = (B + p.nb - 1) / p.nb;
@@ -991,7 +1165,7 @@ int b200_conv_s2_gemm(const void* x, int B, int H, int W, int Cin, const void* w
   p.pair = want_pair(p, ksplit) ? 1 : 0;
   if (p.pair) p.num_tiles /= 2;
   CUtensorMap ta, tb;
-  if ((rc = map_nhwc_parity(&ta, x, B, H, W, Cin, p.tw, p.th, p.nb))) return rc;
+  if ((rc = map_nhwc_parity(&ta, x, B, H, W, Cin, p.tw + p.win, p.th + p.win, p.nb))) return rc;
   if ((rc = map_weights(&tb, wpk, Cout, 16 * Cin, p.pair ? p.BN / 2 : p.BN))) return rc;
   return launch(ta, tb, p, stream, stat_rows);
 }
@@ -1008,7 +1182,9 @@ int b200_convt_s2_gemm(const void* z, int B, int Hi, int Wi, int Cin, int ldz, c
   p.B = B;
   p.Hs = Hi;
   p.Ws = Wi;
-  pixel_box(p.Hs, p.Ws, 128, &p.tw, &p.th, &p.nb);
+  p.win = want_window(p.Hs, p.Ws, ksplit) ? 1 : 0;
+  if (p.win) p.tw = kWinTw, p.th = kWinTh, p.nb = 1;
+  else pixel_box(p.Hs, p.Ws, 128, &p.tw, &p.th, &p.nb);
   p.tiles_w = p.Ws / p.tw;
   p.tiles_h = p.Hs / p.th;
   const int tiles_b = (B + p.nb - 1) / p.nb;
@@ -1036,7 +1212,7 @@ int b200_convt_s2_gemm(const void* z, int B, int Hi, int Wi, int Cin, int ldz, c
   p.pair = want_pair(p, ksplit) ? 1 : 0;
   if (p.pair) p.num_tiles /= 2;
   CUtensorMap ta, tb;
-  if ((rc = map_nhwc(&ta, z, B, Hi, Wi, Cin, ldz, p.tw, p.th, p.nb))) return rc;
+  if ((rc = map_nhwc(&ta, z, B, Hi, Wi, Cin, ldz, p.tw + p.win, p.th + p.win, p.nb))) return rc;
   if ((rc = map_weights(&tb, wpk, 4 * Cout, 4 * Cin, p.pair ? p.BN / 2 : p.BN))) return rc;
   return launch(ta, tb, p, stream, stat_rows);
 }

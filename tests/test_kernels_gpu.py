@@ -54,7 +54,10 @@ def test_pack_all_equals_single_layer_packs(dev):
         assert torch.equal(a.gather, b.gather) and torch.equal(a.phase, b.phase)
 
 
-@pytest.mark.parametrize("B,H,Cin,Cout", [(2, 16, 64, 128), (3, 8, 256, 512), (8, 2, 512, 512), (2, 64, 64, 128), (5, 4, 512, 512), (48, 32, 128, 256)])
+@pytest.mark.parametrize("B,H,Cin,Cout", [(2, 16, 64, 128), (3, 8, 256, 512), (8, 2, 512, 512), (2, 64, 64, 128), (5, 4, 512, 512), (48, 32, 128, 256),
+                                          # window operand staging (>= 16 x 8 output pixels per image): several channel blocks, N = 256 / 128 / 64
+                                          # tiles, CTA pairs and single CTAs, an odd tile count
+                                          (3, 32, 256, 512), (64, 64, 128, 256), (2, 128, 64, 64), (5, 64, 256, 128), (37, 32, 64, 64)])
 def test_conv_s2_fprop(dev, B, H, Cin, Cout):
     eng = _eng()
     torch.manual_seed(0)
@@ -66,7 +69,8 @@ def test_conv_s2_fprop(dev, B, H, Cin, Cout):
 
 
 @pytest.mark.parametrize("B,Hi,Cin,Cout", [(2, 8, 128, 64), (2, 1, 512, 512), (3, 4, 1024, 512), (2, 32, 512, 128), (2, 64, 256, 64), (20, 32, 128, 64),
-                                           (297, 8, 64, 64), (4, 128, 64, 64)])  # the last three: >= 148 pixel tiles at N = 64 (CTA pairs / odd tile count with masked rows / big)
+                                           (297, 8, 64, 64), (4, 128, 64, 64),  # these three: >= 148 pixel tiles at N = 64 (CTA pairs / odd tile count with masked rows / big)
+                                           (5, 16, 1024, 256), (16, 32, 512, 128), (3, 16, 512, 512), (75, 16, 64, 64)])  # window operand staging, more channel blocks
 def test_convt_s2_fprop(dev, B, Hi, Cin, Cout):
     eng = _eng()
     torch.manual_seed(1)
