@@ -108,6 +108,12 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
 
 // ---- warp-uniform ("_w") TMA issue: see umma_bf16_w — the whole converged warp calls, elect.sync picks the issuing lane
 #define B200_ELECT_ASM(INSTR) "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t@e " INSTR "\n\t}"
+__device__ __forceinline__ void mbar_init_w(uint64_t* bar, uint32_t count) {
+  asm volatile(B200_ELECT_ASM("mbarrier.init.shared::cta.b64 [%0], %1;") ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc_w(const CUtensorMap* m) {
+  asm volatile(B200_ELECT_ASM("prefetch.tensormap [%0];") ::"l"((uint64_t)m) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx_w(uint64_t* bar, uint32_t bytes) {
   asm volatile(B200_ELECT_ASM("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;") ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -204,6 +210,44 @@ __device__ __forceinline__ void umma_bf16_2cta_w(uint32_t tmem_d, uint64_t desc_
       "}" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// ---- descriptors as 32-bit halves.  The low word of a shared-memory matrix descriptor is (address >> 4) | (LBO >> 4) << 16 and
+// advances by a plain integer add per K slice / tile; the high word ((SBO >> 4) | version 1 << 14 | SWIZZLE_128B << 29) is a
+// compile-time constant spliced in inside the asm.  Fed this way ptxas keeps the whole issue loop on the UNIFORM datapath (UIADD3 /
+// UMOV / UTCHMMA, ~6 instructions per MMA); with 64-bit descriptors built by shifts and masks it computes them in vector registers
+// and pays ELECT + VOTEU + 5-6 R2UR.BROADCAST per MMA (~29 instructions, ~100 clocks: measured as THE bound of every N <= 128 tile,
+// profiles/experiments/README.md round 2).
+constexpr uint32_t kDescHiSw128 = 0x40004000u;  // version 1, SWIZZLE_128B; OR in (SBO >> 4)
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) { return ((smem_addr >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16); }
+template <uint32_t HI_A, uint32_t HI_B, bool PAIR>
+__device__ __forceinline__ void umma_bf16_lo_w(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  if (PAIR) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, e;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %6};\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "n"(HI_A), "n"(HI_B)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, e;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %6};\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "n"(HI_A), "n"(HI_B)
+        : "memory");
+  }
 }
 // mbarrier arrive once every tcgen05.mma previously issued by the elected lane has completed (implies fence::before_thread_sync);
 // the _2cta form arrives on the barrier at this offset in BOTH CTAs of the pair

@@ -264,6 +264,20 @@ __device__ __forceinline__ void tile_column_sums_f32(uint8_t* wbuf, int lane, fl
     }
 }
 
+// End of every warp role: all warps of the CTA (pair) meet, then the TMEM owner frees the accumulators.  The LAST statement of each
+// role branch of igemm_kernel (see the note at its role dispatch).
+template <bool PAIR>
+__device__ __forceinline__ void igemm_teardown(bool tmem_owner, uint32_t tmem_base, uint32_t tmem_cols) {
+  tc_fence_before();
+  asm volatile("bar.sync 0, %0;" ::"n"(kThreads) : "memory");
+  if (PAIR) cluster_sync_all();  // the peer may still be reading operands / TMEM this CTA's MMAs touched
+  if (tmem_owner) {
+    tc_fence_after();
+    if (PAIR) tmem_dealloc2(tmem_base, tmem_cols);
+    else tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
 // PAIR: two CTAs of a cluster (the two SMs of a TPC) run ONE tcgen05.mma.cta_group::2 per K step over a 256-pixel x BN tile:
 // each CTA stages its own 128 pixel rows of A and HALF of the weight tile (BN/2 rows), so the operand bytes pulled through
 // L2 per flop drop by a third at BN = 256 — the GEMMs with 128 x BN single-CTA tiles are bound by exactly that traffic.
@@ -290,7 +304,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   // WIN: [sa window slots][stages weight stages of tpb boxes]; else [stages of kpb (A tile + B tile)]
   const int stage_bytes = WIN ? p.tpb * b_bytes : p.kpb * (kATileBytes + b_bytes);
   uint8_t* smem_b = smem + (WIN ? p.sa * kWinSlotBytes : 0);
-  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int rank = PAIR ? (int)(blockIdx.x & 1u) : 0;  // == %cluster_ctarank for 2 x 1 x 1 clusters; read from blockIdx it is provably warp-uniform (the MMA / TMA loops then compile to the uniform datapath)
   const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // first work item of this CTA (pair)
   const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   uint64_t* full_bar = (uint64_t*)(smem_b + p.stages * stage_bytes);
@@ -309,44 +323,44 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
+  // Every warp role starts with its share of the set-up and then role_begin(): all warps (of both CTAs of a pair) meet once the
+  // barriers are initialised and TMEM is allocated.  The role dispatch below is the FIRST thread-dependent branch of the kernel and
+  // NOTHING follows it (each role ends with igemm_teardown): ptxas keeps the single-issuer loops on the uniform datapath only then
+  // — an `if (threadIdx.x == 0)` set-up block before the dispatch, or a common teardown after it, and every tcgen05.mma / TMA issue
+  // pays ELECT + VOTEU + 5-8 R2UR.BROADCAST (found by bisecting the SASS; profiles/experiments/README.md, round 2).
+  auto role_begin = [&]() -> uint32_t {
+    tc_fence_before();
+    asm volatile("bar.sync 0, %0;" ::"n"(kThreads) : "memory");
+    if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them remotely
+    tc_fence_after();
+    const uint32_t tb = *tmem_ptr_smem;
+    // programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) touched no global
+    // memory and may overlap the previous kernel's tail; from here on its results are needed
+    pdl_enter();
+    return tb;
+  };
+
+  if (warp == 0) {
+    // ---- set-up: descriptor prefetch and barrier initialisation (the whole warp runs it, elect.sync picks the lane)
+    tma_prefetch_desc_w(&tmA);
+    tma_prefetch_desc_w(&tmB);
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init_w(&full_bar[s], 1);
+      mbar_init_w(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], PAIR ? 2 * kEpiWarps : kEpiWarps);  // one arrival per epilogue warp (of both CTAs)
+      mbar_init_w(&tmem_full_bar[b], 1);
+      mbar_init_w(&tmem_empty_bar[b], PAIR ? 2 * kEpiWarps : kEpiWarps);  // one arrival per epilogue warp (of both CTAs)
     }
     if (WIN) {
       for (int a = 0; a < p.sa; ++a) {
-        mbar_init(&fullA_bar[a], 1);
-        mbar_init(&emptyA_bar[a], 1);
+        mbar_init_w(&fullA_bar[a], 1);
+        mbar_init_w(&emptyA_bar[a], 1);
       }
     }
     fence_barrier_init();
-  }
-  if (warp == 1) {
-    if (PAIR) {
-      tmem_alloc2(tmem_ptr_smem, p.tmem_cols);
-      tmem_relinquish2();
-    } else {
-      tmem_alloc(tmem_ptr_smem, p.tmem_cols);
-      tmem_relinquish();
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them remotely
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-  // programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) touched no global memory
-  // and may overlap the previous kernel's tail; from here on its results are needed
-  pdl_enter();
-
-  if (warp == 0 && WIN) {
+    const uint32_t tmem_base = role_begin();
+    if (WIN) {
     // ===================== TMA producer, window operand staging =====================
     const uint32_t a_tx = (uint32_t)kWinBytes * (PAIR ? 2u : 1u);
     const uint32_t b_tx = (uint32_t)stage_bytes * (PAIR ? 2u : 1u);
@@ -402,7 +416,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
       }
     }
-  } else if (warp == 0) {
+    } else {
     // ===================== TMA producer =====================
     {  // the whole warp runs the loop; elect.sync inside the *_w wrappers picks the issuing lane
       const uint32_t tx_bytes = (uint32_t)stage_bytes * (PAIR ? 2u : 1u);  // PAIR: both CTAs' bytes land on the even CTA's barrier
@@ -465,7 +479,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
       }
     }
-  } else if (warp == 1 && WIN) {
+    }
+    igemm_teardown<PAIR>(false, tmem_base, p.tmem_cols);
+  } else if (warp == 1) {
+    // ---- set-up: this warp owns the tensor memory
+    if (PAIR) {
+      tmem_alloc2(tmem_ptr_smem, p.tmem_cols);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_ptr_smem, p.tmem_cols);
+      tmem_relinquish();
+    }
+    const uint32_t tmem_base = role_begin();
+    if (WIN) {
     // ===================== MMA issuer, window operand staging =====================
     if (rank == 0) {
       const uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, p.BN, 0, 0);
@@ -480,21 +506,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int wi = 0; wi < nwin; ++wi) {
           mbar_wait(&fullA_bar[sa], para);
           tc_fence_after();
-          const uint32_t w_addr = smem_u32(smem + sa * kWinSlotBytes);
+          const uint32_t w_lo = desc_lo(smem_u32(smem + sa * kWinSlotBytes), 16u);
           for (int tg = 0; tg < 4; tg += p.tpb) {
             mbar_wait(&full_bar[sb], parb);
             tc_fence_after();
-            const uint32_t b_addr = smem_u32(smem_b + sb * stage_bytes);
+            const uint32_t b_lo0 = desc_lo(smem_u32(smem_b + sb * stage_bytes), 16u);
             for (int u = 0; u < p.tpb; ++u) {
               const int j = tg + u;
-              const uint32_t a_addr = w_addr + (uint32_t)(((j >> 1) * (kWinTw + 1) + (j & 1)) * 128);  // tap (eh, ew) = window row eh * 9 + ew
+              const uint32_t a_lo = w_lo + (uint32_t)(((j >> 1) * (kWinTw + 1) + (j & 1)) * 8);  // tap (eh, ew) = window row eh * 9 + ew (128 B = 8 units)
+              const uint32_t b_lo = b_lo0 + (uint32_t)u * ((uint32_t)b_bytes >> 4);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 16u, (uint32_t)kWinSbo);
-                const uint64_t db = make_smem_desc_sw128(b_addr + u * b_bytes + k * 32, 16u, 1024u);
-                if (PAIR) umma_bf16_2cta_w(d_addr, da, db, idesc, (wi > 0 || j > 0 || k > 0) ? 1u : 0u);
-                else umma_bf16_w(d_addr, da, db, idesc, (wi > 0 || j > 0 || k > 0) ? 1u : 0u);
-              }
+              for (int k = 0; k < 4; ++k)  // K = 16 slices: 32 bytes = 2 descriptor units apart
+                umma_bf16_lo_w<kDescHiSw128 | (kWinSbo >> 4), kDescHiSw128 | (1024 >> 4), PAIR>(d_addr, a_lo + 2 * k, b_lo + 2 * k, idesc,
+                                                                                                   (wi > 0 || j > 0 || k > 0) ? 1u : 0u);
             }
             if (PAIR) umma_commit_2cta_w(&empty_bar[sb]);
             else umma_commit_w(&empty_bar[sb]);
@@ -514,7 +538,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         else umma_commit_w(&tmem_full_bar[buf]);
       }
     }
-  } else if (warp == 1) {
+    } else {
     // ===================== MMA issuer =====================
     // the whole warp runs this loop with identical values (waits included); elect.sync inside the *_w wrappers picks the lane that
     // issues, so descriptors and addresses stay in uniform registers (see common.cuh)
@@ -522,7 +546,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const bool mn_major = (p.mode == MODE_WGRAD);
       const uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, p.BN, mn_major ? 1 : 0, mn_major ? 1 : 0);
       const uint32_t lbo = mn_major ? 8192u : 16u;
-      const uint32_t kstep = mn_major ? 2048u : 32u;  // bytes per K=16 slice inside a stage
+      const uint32_t kstep = mn_major ? 2048u / 16u : 32u / 16u;  // descriptor units (16 bytes) per K = 16 slice inside a stage
       int s = 0, lt = 0;
       uint32_t par = 0;
       for (int t = tile0; t < p.num_tiles; t += tile_step, ++lt) {
@@ -535,15 +559,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           mbar_wait(&full_bar[s], par);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
-          const uint32_t b_addr = a_addr + p.kpb * kATileBytes;
+          const uint32_t a_lo0 = desc_lo(a_addr, lbo), b_lo0 = desc_lo(a_addr + p.kpb * kATileBytes, lbo);
           for (int u = 0; u < p.kpb; ++u) {
+            const uint32_t a_lo = a_lo0 + (uint32_t)u * (kATileBytes >> 4), b_lo = b_lo0 + (uint32_t)u * ((uint32_t)b_bytes >> 4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t da = make_smem_desc_sw128(a_addr + u * kATileBytes + k * kstep, lbo, 1024u);
-              const uint64_t db = make_smem_desc_sw128(b_addr + u * b_bytes + k * kstep, lbo, 1024u);
-              if (PAIR) umma_bf16_2cta_w(d_addr, da, db, idesc, (i > 0 || u > 0 || k > 0) ? 1u : 0u);
-              else umma_bf16_w(d_addr, da, db, idesc, (i > 0 || u > 0 || k > 0) ? 1u : 0u);
-            }
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_lo_w<kDescHiSw128 | (1024 >> 4), kDescHiSw128 | (1024 >> 4), PAIR>(d_addr, a_lo + k * kstep, b_lo + k * kstep, idesc,
+                                                                                             (i > 0 || u > 0 || k > 0) ? 1u : 0u);
           }
           if (PAIR) umma_commit_2cta_w(&empty_bar[s]);  // frees the slot in both CTAs
           else umma_commit_w(&empty_bar[s]);            // frees the smem slot once these MMAs retire
@@ -556,8 +578,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         else umma_commit_w(&tmem_full_bar[buf]);  // accumulator complete
       }
     }
+    }
+    igemm_teardown<PAIR>(true, tmem_base, p.tmem_cols);
   } else {
     // ===================== epilogue (overlaps the next tile's main loop) =====================
+    const uint32_t tmem_base = role_begin();
     const int quad = warp & 3;          // a warp may only touch TMEM lanes [32*(warp%4), +32)
     const int half = (warp - 2) >> 2;   // which of the alternating 32-column chunks this warp takes
     const int r = quad * 32 + lane;
@@ -757,16 +782,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       float* gdst = p.stats + (size_t)blockIdx.x * 2 * p.Cout;
       for (int e = et; e < 2 * p.Cout; e += kEpiThreads) gdst[e] = stat_acc[e];
     }
-  }
-
-  // ---- teardown
-  tc_fence_before();
-  __syncthreads();
-  if (PAIR) cluster_sync_all();  // the peer may still be reading operands / TMEM this CTA's MMAs touched
-  if (warp == 1) {
-    tc_fence_after();
-    if (PAIR) tmem_dealloc2(tmem_base, p.tmem_cols);
-    else tmem_dealloc(tmem_base, p.tmem_cols);
+    igemm_teardown<PAIR>(false, tmem_base, p.tmem_cols);
   }
 }
 
