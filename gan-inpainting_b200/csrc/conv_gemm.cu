@@ -100,7 +100,7 @@ constexpr int kWinRows = (kWinTw + 1) * (kWinTh + 1);
 constexpr int kWinBytes = kWinRows * 128;              // 19584
 constexpr int kWinSlotBytes = 20 * 1024;               // slot pitch (1024-byte aligned: SWIZZLE_128B)
 constexpr int kWinSbo = (kWinTw + 1) * 128;            // byte distance of consecutive 8-pixel row groups inside a window
-constexpr int kBarrierBytes = 512;                     // mbarriers + TMEM pointer behind the operand rings
+constexpr int kBarrierBytes = 1024;                    // mbarriers + TMEM pointer behind the operand rings (keeps the epilogue tiles 1024-byte aligned)
 constexpr int kStatTileBytes = 4096 + 2048;           // per epilogue warp: 32 x 32 fp32 of dz + 32 x 32 bf16 of y (forward: 32 x 32 bf16 only)
 
 // Epilogue variants (compile-time: the per-element code has no branches and each variant is a small kernel)
@@ -278,6 +278,81 @@ __device__ __forceinline__ void igemm_teardown(bool tmem_owner, uint32_t tmem_ba
   }
 }
 
+// ---- staging tiles of the window-mode epilogue (one 32-row x 32-column chunk per warp).  Both layouts are exactly what TMA's
+// SWIZZLE_64B / SWIZZLE_128B boxes look like in shared memory, so the same tile serves the per-lane row access (conflict-free
+// 128-bit LDS / STS), the transposed column sums, the cp.async operand loads and the TMA store.
+//   bf16 tile: 32 rows x 64 B, 16-byte chunk j of row r at  r * 64 + ((j ^ ((r >> 1) & 3)) * 16)       (SWIZZLE_64B)
+//   fp32 tile: 32 rows x 128 B, chunk j of row r at         r * 128 + ((j ^ (r & 7)) * 16)            (SWIZZLE_128B)
+__device__ __forceinline__ void stage_bf16_row(uint8_t* tile, const uint32_t (&o)[16], int lane) {
+  const int sw = (lane >> 1) & 3;
+  uint4* rowp = reinterpret_cast<uint4*>(tile + lane * 64);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) rowp[j ^ sw] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+}
+__device__ __forceinline__ void load_bf16_row(const uint8_t* tile, uint32_t (&o)[16], int lane) {
+  const int sw = (lane >> 1) & 3;
+  const uint4* rowp = reinterpret_cast<const uint4*>(tile + lane * 64);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4 d = rowp[j ^ sw];
+    o[4 * j] = d.x, o[4 * j + 1] = d.y, o[4 * j + 2] = d.z, o[4 * j + 3] = d.w;
+  }
+}
+__device__ __forceinline__ void stage_f32_row(uint8_t* tile, const uint32_t (&v)[32], int lane) {
+  uint4* rowz = reinterpret_cast<uint4*>(tile + lane * 128);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) rowz[j ^ (lane & 7)] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+// s[k] / q[k] = sum over the 32 rows of x and x * x for column 8 * (lane & 3) + k of a staged bf16 tile (identical in lanes with equal lane & 3)
+__device__ __forceinline__ void column_sums_bf16(const uint8_t* tile, int lane, float (&s)[8], float (&q)[8]) {
+  const int cg = lane & 3, rg = lane >> 2;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s[k] = q[k] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = i * 8 + rg;
+    const uint4 d = *reinterpret_cast<const uint4*>(tile + row * 64 + ((cg ^ ((row >> 1) & 3)) * 16));
+    const uint32_t dw[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack_bf16x2(dw[k]);
+      s[2 * k] += f.x;
+      s[2 * k + 1] += f.y;
+      q[2 * k] = fmaf(f.x, f.x, q[2 * k]);
+      q[2 * k + 1] = fmaf(f.y, f.y, q[2 * k + 1]);
+    }
+  }
+#pragma unroll
+  for (int h = 4; h <= 16; h <<= 1)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s[k] += __shfl_xor_sync(0xffffffffu, s[k], h);
+      q[k] += __shfl_xor_sync(0xffffffffu, q[k], h);
+    }
+}
+// s[k] / q[k] = sum over the 32 rows of dz and dz * y for column 4 * (lane & 7) + k: dz from a staged fp32 tile, y from a staged bf16 tile
+__device__ __forceinline__ void column_sums_f32(const uint8_t* ztile, const uint8_t* ytile, int lane, float (&s)[4], float (&q)[4]) {
+  const int cq = lane & 7, rg = lane >> 3;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) s[k] = q[k] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = rg + 4 * i;
+    const float4 d = *reinterpret_cast<const float4*>(ztile + row * 128 + ((cq ^ (row & 7)) * 16));
+    const uint2 yy = *reinterpret_cast<const uint2*>(ytile + row * 64 + (((cq >> 1) ^ ((row >> 1) & 3)) * 16) + (cq & 1) * 8);
+    const float2 y0 = unpack_bf16x2(yy.x), y1 = unpack_bf16x2(yy.y);
+    s[0] += d.x, s[1] += d.y, s[2] += d.z, s[3] += d.w;
+    q[0] = fmaf(d.x, y0.x, q[0]), q[1] = fmaf(d.y, y0.y, q[1]), q[2] = fmaf(d.z, y1.x, q[2]), q[3] = fmaf(d.w, y1.y, q[3]);
+  }
+#pragma unroll
+  for (int h = 8; h <= 16; h <<= 1)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      s[k] += __shfl_xor_sync(0xffffffffu, s[k], h);
+      q[k] += __shfl_xor_sync(0xffffffffu, q[k], h);
+    }
+}
+
 // PAIR: two CTAs of a cluster (the two SMs of a TPC) run ONE tcgen05.mma.cta_group::2 per K step over a 256-pixel x BN tile:
 // each CTA stages its own 128 pixel rows of A and HALF of the weight tile (BN/2 rows), so the operand bytes pulled through
 // L2 per flop drop by a third at BN = 256 — the GEMMs with 128 x BN single-CTA tiles are bound by exactly that traffic.
@@ -295,7 +370,8 @@ __device__ __forceinline__ void igemm_teardown(bool tmem_owner, uint32_t tmem_ba
 // weights ride in their own ring (`tpb` taps per stage) because the two operands now arrive at different rates.
 template <class E, bool PAIR, bool WIN>
 __global__ void __launch_bounds__(kThreads, 1)
-igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const IGemmParams p) {
+igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
+             const __grid_constant__ CUtensorMap tmZ, const IGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by pointer arithmetic (no integer round trip): the compiler keeps the shared address space and emits
   // LDS / STS instead of generic loads / stores for everything the epilogue stages here
@@ -601,6 +677,165 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint8_t* wbuf = stat_tile + (warp - 2) * p.tile_bytes;
     const uint32_t drop_seed = (E::BWD && p.bwd.dropout) ? dropout_seed(p.bwd.seed, p.bwd.seed_ctr) : 0u;
     int lt = 0;
+    if (WIN) {
+      // ---- window mode (16 x 8-pixel tiles, never masked): coalesced epilogue I/O.  A warp's 32 accumulator rows are 4 image rows
+      // of 8 adjacent pixels, so a 32-row x 32-channel chunk of any NHWC tensor is a 4-D / 5-D TMA box:
+      //  * the forward conv output y and the skip gradient the fused backward needs are fetched with cp.async, 4 lanes per pixel
+      //    row (8 full 64-byte segments per instruction instead of 32 scattered 16-byte pieces), one chunk ahead, straight into
+      //    the swizzled tile layout the column sums read anyway;
+      //  * every output chunk (bf16 tile, or the unrounded fp32 dz of a BatchNorm backward) is staged in a swizzled tile and
+      //    leaves through ONE TMA store (cp.async.bulk.tensor shared -> global) issued by lane 0.
+      // Per-lane 16-byte global accesses made these epilogues LSU-bound (32 L1 wavefronts per instruction): e.g. the data
+      // gradient into a 64-channel layer took 141 us against 62 us of MMA time.
+      constexpr int kZ = (E::STATS && E::BWD) ? 4096 : 2048;
+      uint8_t* zbuf = wbuf;         // fp32 dz tile (SWIZZLE_128B) or bf16 output tile (SWIZZLE_64B)
+      uint8_t* ybuf = wbuf + kZ;    // [2][2048] y chunks (double buffered: fetched one chunk ahead)
+      uint8_t* gbuf = ybuf + 4096;  // [2][2048] skip-gradient chunks
+      const int hq = quad * 4;      // first tile row of this warp's accumulator rows
+      const int frow = lane >> 2, fch = lane & 3;  // cp.async mapping: pixel of the image row, 16-byte channel chunk
+      const bool convt = (p.mode == MODE_CONVT);
+      uint32_t nchunk = 0;
+      for (int t = tile0; t < p.num_tiles; t += tile_step, ++lt) {
+        const TileCoord c = decode_tile<PAIR>(p, t, rank);
+        const int buf = lt & 1;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.BN);
+        const int ph_p = c.phase >> 1, ph_q = c.phase & 1;
+        auto pixel = [&](int hl, int wl) -> size_t {
+          if (!convt) return ((size_t)c.b0 * p.Hs + (c.h0 + hl)) * p.Ws + (c.w0 + wl);
+          return ((size_t)c.b0 * (2 * p.Hs) + (2 * (c.h0 + hl) + ph_p)) * (size_t)(2 * p.Ws) + (2 * (c.w0 + wl) + ph_q);
+        };
+        const size_t pix = pixel(r >> 3, r & 7);  // this lane's own accumulator row
+        const int sp = (p.stat_parity == 2) ? (lt & 1) : 0;
+        float* st = stat_smem + (sp * 4 + quad) * 2 * p.BN;
+        auto fetch = [&](int cc, uint32_t slot) {  // one cp.async group per call (empty when the chunk needs nothing)
+          const int cb = c.n0 + cc - p.bwd.col0;
+          if (cb >= 0 && cc < p.BN) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int row = 8 * i + frow;
+              const size_t fp = pixel(hq + i, frow);
+              const int off = (int)slot * 2048 + row * 64 + ((fch ^ ((row >> 1) & 3)) * 16);
+              cp_async16(ybuf + off, p.bwd.y + fp * p.bwd.ldy + cb + fch * 8);
+              if (E::G2) cp_async16(gbuf + off, p.bwd.g2 + fp * p.bwd.ldg2 + p.bwd.offg2 + cb + fch * 8);
+            }
+          }
+          cp_async_commit();
+        };
+        if (E::BWD) fetch(half * 32, nchunk & 1u);  // the first chunk's operands travel while the tile's MMAs are still running
+        mbar_wait(&tmem_full_bar[buf], (uint32_t)((lt >> 1) & 1));
+        tc_fence_after();
+        for (int cc = half * 32; cc < p.BN; cc += 64, ++nchunk) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + cc, v);
+          const uint32_t slot = nchunk & 1u;
+          if (E::BWD) {
+            fetch(cc + 64, slot ^ 1u);
+            cp_async_wait<1>();  // this chunk's group (the next chunk's may still be in flight)
+          }
+          if (lane == 0) tma_store_wait_read();  // the previous store has read the staging tile
+          __syncwarp();                          // ... and every lane's cp.async data is visible to the whole warp
+          tmem_ld_wait();
+          const int cb = c.n0 + cc - p.bwd.col0;  // first channel of y this chunk is the gradient of (fused columns only)
+          const bool fused = E::BWD && cb >= 0;
+          if (fused) {
+            // ---- backward of [BatchNorm ->] [dropout ->] activation, evaluated at the forward's stored conv output
+            uint32_t yw[16], gw[16];
+            load_bf16_row(ybuf + slot * 2048, yw, lane);
+            if (E::G2) load_bf16_row(gbuf + slot * 2048, gw, lane);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const float2 yf = unpack_bf16x2(yw[k]);
+              float2 gf = make_float2(0.f, 0.f);
+              if (E::G2) gf = unpack_bf16x2(gw[k]);
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int jj = 2 * k + e;
+                const float yy = e ? yf.y : yf.x;
+                float z = yy;
+                if (E::BN) {
+                  const float2 ss = *reinterpret_cast<const float2*>(bn_ss + 2 * (cb + jj));
+                  z = fmaf(yy, ss.x, ss.y);
+                }
+                float g = __uint_as_float(v[jj]);
+                if (E::ACT == ACT_BWD_LEAKY) {
+                  g = z > 0.f ? (E::G2 ? g + (e ? gf.y : gf.x) : g) : 0.2f * g;
+                } else if (E::ACT == ACT_BWD_RELU) {
+                  g = z > 0.f ? g : 0.f;
+                  if (p.bwd.dropout) g = dropout_keep(drop_seed, (uint64_t)(pix * p.bwd.Cy + cb + jj)) ? 2.f * g : 0.f;
+                }
+                v[jj] = __float_as_uint(g);
+              }
+            }
+          }
+          if (E::STATS && E::BWD && fused) {
+            // dz feeds a BatchNorm backward: stored unrounded (fp32) and summed per channel together with dz * y
+            stage_f32_row(zbuf, v, lane);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              if (convt) tma_store_5d(&tmZ, zbuf, ph_q * p.bwd.Cy + cb, c.w0, ph_p, c.h0 + hq, c.b0);
+              else tma_store_4d(&tmZ, zbuf, cb, c.w0, c.h0 + hq, c.b0);
+              tma_store_commit();
+            }
+            float cs[4], cq[4];
+            column_sums_f32(zbuf, ybuf + slot * 2048, lane, cs, cq);
+            if (lane < 8) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                st[cc + lane * 4 + k] = cs[k];
+                st[p.BN + cc + lane * 4 + k] = cq[k];
+              }
+            }
+          } else {
+            uint32_t o[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+            stage_bf16_row(zbuf, o, lane);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              if (convt) tma_store_5d(&tmO, zbuf, ph_q * p.ldc + c.n0 + cc, c.w0, ph_p, c.h0 + hq, c.b0);
+              else tma_store_4d(&tmO, zbuf, c.n0 + cc, c.w0, c.h0 + hq, c.b0);
+              tma_store_commit();
+            }
+            if (E::STATS && E::BWD) {  // unfused columns of a fused-backward GEMM carry no statistics
+              st[cc + lane] = 0.f;
+              st[p.BN + cc + lane] = 0.f;
+            } else if (E::STATS) {     // per-channel sums of the values as stored
+              float cs[8], cq[8];
+              column_sums_bf16(zbuf, lane, cs, cq);
+              if (lane < 4) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                  st[cc + lane * 8 + k] = cs[k];
+                  st[p.BN + cc + lane * 8 + k] = cq[k];
+                }
+              }
+            }
+          }
+          __syncwarp();  // every lane is done with the staging tiles of this chunk
+        }
+        tc_fence_before();  // the accumulator has been read: hand the TMEM buffer back before the cross-warp statistics
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_leader(&tmem_empty_bar[buf]);
+          else mbar_arrive(&tmem_empty_bar[buf]);
+        }
+        if (E::STATS) {
+          asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // all epilogue warps
+          const float* sb = stat_smem + sp * 4 * 2 * p.BN;
+          const int qs = 2 * p.BN;  // quadrant stride
+          for (int e = et; e < 2 * p.BN; e += kEpiThreads) {  // element (k, n0 + col) is always owned by the same thread
+            const int k = e >= p.BN, col = e - k * p.BN;
+            const float a = (sb[e] + sb[qs + e]) + (sb[2 * qs + e] + sb[3 * qs + e]);
+            stat_acc[k * p.Cout + c.n0 + col] += a;
+          }
+          if (p.stat_parity == 1) asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // before the next tile rewrites the buffer
+        }
+      }
+      if (E::BWD) cp_async_wait<0>();
+      if (lane == 0) tma_store_wait_all();
+    } else
     for (int t = tile0; t < p.num_tiles; t += tile_step, ++lt) {
       const TileCoord c = decode_tile<PAIR>(p, t, rank);
       const int buf = lt & 1;
@@ -848,15 +1083,16 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // NHWC bf16 tensor map helpers.  `ld` = channel stride (elements) of one pixel.
-static int encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box) {
+static int encode(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box,
+                  CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     b200_set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
     return B200_ERR_DRIVER;
   }
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(m, dtype, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     b200_set_error(("cuTensorMapEncodeTiled failed, CUresult=" + std::to_string((int)r)).c_str());
     return B200_ERR_DRIVER;
@@ -877,6 +1113,25 @@ static int map_nhwc_parity(CUtensorMap* m, const void* base, int B, int H, int W
   cuuint64_t st[4] = {(cuuint64_t)2 * C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)2 * W * C * 2, (cuuint64_t)H * W * C * 2};
   cuuint32_t box[5] = {64, (cuuint32_t)tw, 1, (cuuint32_t)th, (cuuint32_t)nb};
   return encode(m, base, 5, dims, st, box);
+}
+// Store maps of the window-mode epilogue: a warp's 32 rows x 32 channels chunk (4 image rows of 8 pixels) of an NHWC tensor with
+// `ld` channels per pixel and elements of `esize` bytes (2: bf16 tile, SWIZZLE_64B; 4: fp32 tile, SWIZZLE_128B).
+//   plain:  [ld, W, H, B], box [32, 8, 4, 1]           (stride-2 convolution: output pixel = accumulator row)
+//   parity: [2 ld, W/2, 2, H/2, B], box [32, 8, 1, 4, 1] (transposed convolution: accumulator row (i, j) of phase (p, q) is pixel (2i+p, 2j+q))
+static int map_store(CUtensorMap* m, const void* base, int B, int H, int W, int ld, int esize, bool parity) {
+  const CUtensorMapDataType dt = esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapSwizzle sw = esize == 4 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  const cuuint64_t e = (cuuint64_t)esize;
+  if (!parity) {
+    cuuint64_t dims[4] = {(cuuint64_t)ld, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t st[3] = {(cuuint64_t)ld * e, (cuuint64_t)W * ld * e, (cuuint64_t)H * W * ld * e};
+    cuuint32_t box[4] = {32, 8, 4, 1};
+    return encode(m, base, 4, dims, st, box, dt, sw);
+  }
+  cuuint64_t dims[5] = {(cuuint64_t)2 * ld, (cuuint64_t)W / 2, 2, (cuuint64_t)H / 2, (cuuint64_t)B};
+  cuuint64_t st[4] = {(cuuint64_t)2 * ld * e, (cuuint64_t)W * ld * e, (cuuint64_t)2 * W * ld * e, (cuuint64_t)H * W * ld * e};
+  cuuint32_t box[5] = {32, 8, 1, 4, 1};
+  return encode(m, base, 5, dims, st, box, dt, sw);
 }
 // packed weights [rows][K] (K contiguous), box [64, BN]
 static int map_weights(CUtensorMap* m, const void* base, int rows, int K, int BN) {
@@ -906,8 +1161,12 @@ static int ilog2(int v) {
   return s;
 }
 
+struct StoreMaps {
+  CUtensorMap out, dz;  // window-mode epilogue: bf16 output tensor, fp32 dz tensor of a fused BatchNorm backward (zeroed when unused)
+};
 template <class E, bool WIN>
-static void launch_variant_w(const CUtensorMap& a, const CUtensorMap& b, const IGemmParams& p, int grid, size_t smem, cudaStream_t stream) {
+static void launch_variant_w(const CUtensorMap& a, const CUtensorMap& b, const StoreMaps& sm, const IGemmParams& p, int grid, size_t smem,
+                             cudaStream_t stream) {
   if (p.pair) {
     static std::once_flag once2;
     std::call_once(once2, [] { cudaFuncSetAttribute(igemm_kernel<E, true, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
@@ -925,17 +1184,18 @@ static void launch_variant_w(const CUtensorMap& a, const CUtensorMap& b, const I
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = b200_pdl_enabled() ? 2 : 1;
-    cudaLaunchKernelEx(&cfg, igemm_kernel<E, true, WIN>, a, b, p);
+    cudaLaunchKernelEx(&cfg, igemm_kernel<E, true, WIN>, a, b, sm.out, sm.dz, p);
     return;
   }
   static std::once_flag once;
   std::call_once(once, [] { cudaFuncSetAttribute(igemm_kernel<E, false, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
-  B200_LAUNCH((igemm_kernel<E, false, WIN>), grid, kThreads, smem, stream, a, b, p);
+  B200_LAUNCH((igemm_kernel<E, false, WIN>), grid, kThreads, smem, stream, a, b, sm.out, sm.dz, p);
 }
 template <class E>
-static void launch_variant(const CUtensorMap& a, const CUtensorMap& b, const IGemmParams& p, int grid, size_t smem, cudaStream_t stream) {
-  if (p.win) launch_variant_w<E, true>(a, b, p, grid, smem, stream);
-  else launch_variant_w<E, false>(a, b, p, grid, smem, stream);
+static void launch_variant(const CUtensorMap& a, const CUtensorMap& b, const StoreMaps& sm, const IGemmParams& p, int grid, size_t smem,
+                           cudaStream_t stream) {
+  if (p.win) launch_variant_w<E, true>(a, b, sm, p, grid, smem, stream);
+  else launch_variant_w<E, false>(a, b, sm, p, grid, smem, stream);
 }
 
 // Window operand staging applies to the fprop / dgrad modes when an image holds at least one 16 x 8-pixel tile and K is not
@@ -956,7 +1216,7 @@ static bool want_pair(const IGemmParams& p, int ksplit) {
   return (p.num_ptiles / 2) * p.n_tiles * p.phases >= kNumSMs / 2;
 }
 
-static int launch(const CUtensorMap& a, const CUtensorMap& b, IGemmParams& p, cudaStream_t stream, int* grid_out) {
+static int launch(const CUtensorMap& a, const CUtensorMap& b, const StoreMaps& sm, IGemmParams& p, cudaStream_t stream, int* grid_out) {
   if (!is_pow2(p.tw) || !is_pow2(p.th) || !is_pow2(p.tiles_w) || !is_pow2(p.tiles_h) || !is_pow2(p.C_k) || !is_pow2(p.cpt)) {
     b200_set_error("igemm: image sides and channel counts must be powers of two");
     return B200_ERR_ARG;
@@ -981,7 +1241,10 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, IGemmParams& p, cu
   // shared memory behind the pipeline stages, sized per epilogue variant: barriers, the per-quadrant statistics buffer
   // (double buffered over tiles unless that would cost a pipeline stage), the per-CTA running sums, the BatchNorm
   // coefficients of the fused backward, and the per-warp transpose tiles
-  const int tile_bytes = !has_stats ? 0 : (has_bwd ? kStatTileBytes : 2048);
+  // per-warp staging behind the statistics buffers.  Window mode: output tile (2 KB bf16 / 4 KB fp32 dz) + double-buffered y
+  // (+ skip-gradient) chunks of a fused backward; otherwise the transpose tiles of the statistics epilogues
+  const int tile_bytes = p.win ? (!has_bwd ? 2048 : ((has_stats ? 4096 : 2048) + 4096 + (p.bwd.g2 ? 4096 : 0)))
+                               : (!has_stats ? 0 : (has_bwd ? kStatTileBytes : 2048));
   auto layout = [&](int parity) {
     int off = has_stats ? parity * 4 * 2 * p.BN * 4 : 0;
     p.stat_parity = parity;
@@ -990,6 +1253,7 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, IGemmParams& p, cu
     p.off_ss = off;
     off += (has_bwd && p.bwd.scale) ? 2 * p.bwd.Cy * 4 : 0;
     off = (off + 15) & ~15;
+    if (p.win) off = (off + 1023) & ~1023;  // TMA-swizzled tiles
     p.off_tile = off;
     p.tile_bytes = tile_bytes;
     off += kEpiWarps * tile_bytes;
@@ -1043,20 +1307,20 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, IGemmParams& p, cu
   const bool bn = p.bwd.scale != nullptr, g2 = p.bwd.g2 != nullptr;
   const int act = p.bwd.act;
   if (!has_bwd) {
-    if (has_stats) launch_variant<Epi<true, false, 0, false, false>>(a, b, p, grid, smem, stream);
-    else launch_variant<Epi<false, false, 0, false, false>>(a, b, p, grid, smem, stream);
+    if (has_stats) launch_variant<Epi<true, false, 0, false, false>>(a, b, sm, p, grid, smem, stream);
+    else launch_variant<Epi<false, false, 0, false, false>>(a, b, sm, p, grid, smem, stream);
   } else if (act == ACT_BWD_LEAKY && bn && g2 && has_stats) {
-    launch_variant<Epi<true, true, ACT_BWD_LEAKY, true, true>>(a, b, p, grid, smem, stream);
+    launch_variant<Epi<true, true, ACT_BWD_LEAKY, true, true>>(a, b, sm, p, grid, smem, stream);
   } else if (act == ACT_BWD_LEAKY && bn && !g2 && has_stats) {
-    launch_variant<Epi<true, true, ACT_BWD_LEAKY, false, true>>(a, b, p, grid, smem, stream);
+    launch_variant<Epi<true, true, ACT_BWD_LEAKY, false, true>>(a, b, sm, p, grid, smem, stream);
   } else if (act == ACT_BWD_LEAKY && !bn && g2 && !has_stats) {
-    launch_variant<Epi<false, true, ACT_BWD_LEAKY, true, false>>(a, b, p, grid, smem, stream);
+    launch_variant<Epi<false, true, ACT_BWD_LEAKY, true, false>>(a, b, sm, p, grid, smem, stream);
   } else if (act == ACT_BWD_LEAKY && !bn && !g2 && !has_stats) {
-    launch_variant<Epi<false, true, ACT_BWD_LEAKY, false, false>>(a, b, p, grid, smem, stream);
+    launch_variant<Epi<false, true, ACT_BWD_LEAKY, false, false>>(a, b, sm, p, grid, smem, stream);
   } else if (act == ACT_BWD_RELU && bn && !g2 && has_stats) {
-    launch_variant<Epi<true, true, ACT_BWD_RELU, false, true>>(a, b, p, grid, smem, stream);
+    launch_variant<Epi<true, true, ACT_BWD_RELU, false, true>>(a, b, sm, p, grid, smem, stream);
   } else if (act == ACT_BWD_RELU && !bn && !g2 && !has_stats) {
-    launch_variant<Epi<false, true, ACT_BWD_RELU, false, false>>(a, b, p, grid, smem, stream);
+    launch_variant<Epi<false, true, ACT_BWD_RELU, false, false>>(a, b, sm, p, grid, smem, stream);
   } else {
     b200_set_error("igemm: unsupported fused backward epilogue (supported: LeakyReLU [+skip] with/without BatchNorm statistics, ReLU [+dropout] "
                    "with/without BatchNorm statistics; statistics are required exactly when a BatchNorm scale/shift is given)");
@@ -1151,7 +1415,8 @@ int b200_conv_s2_gemm(const void* x, int B, int H, int W, int Cin, const void* w
   p.B = B;
   p.Hs = H / 2;
   p.Ws = W / 2;
-  p.win = want_window(p.Hs, p.Ws, ksplit) ? 1 : 0;
+  // (a fused BatchNorm backward without the fp32 dz tensor keeps dz in the bf16 output: legacy epilogue only)
+  p.win = (want_window(p.Hs, p.Ws, ksplit) && !(stats && bwd && bwd->y && !bwd->dz32)) ? 1 : 0;
   if (p.win) p.tw = kWinTw, p.th = kWinTh, p.nb = 1;
   else pixel_box(p.Hs, p.Ws, 128, &p.tw, &p.th, &p.nb);
   p.tiles_w = p.Ws / p.tw;
@@ -1183,7 +1448,12 @@ int b200_conv_s2_gemm(const void* x, int B, int H, int W, int Cin, const void* w
   CUtensorMap ta, tb;
   if ((rc = map_nhwc_parity(&ta, x, B, H, W, Cin, p.tw + p.win, p.th + p.win, p.nb))) return rc;
   if ((rc = map_weights(&tb, wpk, Cout, 16 * Cin, p.pair ? p.BN / 2 : p.BN))) return rc;
-  return launch(ta, tb, p, stream, stat_rows);
+  StoreMaps sm{};
+  if (p.win) {
+    if ((rc = map_store(&sm.out, y, B, p.Hs, p.Ws, ldy, 2, false))) return rc;
+    if (p.bwd.dz32 && (rc = map_store(&sm.dz, p.bwd.dz32, B, p.Hs, p.Ws, p.bwd.Cy, 4, false))) return rc;
+  }
+  return launch(ta, tb, sm, p, stream, stat_rows);
 }
 
 // y[B,2Hi,2Wi,ldy] (bf16) = convT4x4/s2/p1(z[B,Hi,Wi,Cin] (pixel stride ldz), wpk[4 phases][Cout][4*Cin]); stats as above.
@@ -1198,7 +1468,7 @@ int b200_convt_s2_gemm(const void* z, int B, int Hi, int Wi, int Cin, int ldz, c
   p.B = B;
   p.Hs = Hi;
   p.Ws = Wi;
-  p.win = want_window(p.Hs, p.Ws, ksplit) ? 1 : 0;
+  p.win = (want_window(p.Hs, p.Ws, ksplit) && !(stats && bwd && bwd->y && !bwd->dz32)) ? 1 : 0;
   if (p.win) p.tw = kWinTw, p.th = kWinTh, p.nb = 1;
   else pixel_box(p.Hs, p.Ws, 128, &p.tw, &p.th, &p.nb);
   p.tiles_w = p.Ws / p.tw;
@@ -1230,7 +1500,12 @@ int b200_convt_s2_gemm(const void* z, int B, int Hi, int Wi, int Cin, int ldz, c
   CUtensorMap ta, tb;
   if ((rc = map_nhwc(&ta, z, B, Hi, Wi, Cin, ldz, p.tw + p.win, p.th + p.win, p.nb))) return rc;
   if ((rc = map_weights(&tb, wpk, 4 * Cout, 4 * Cin, p.pair ? p.BN / 2 : p.BN))) return rc;
-  return launch(ta, tb, p, stream, stat_rows);
+  StoreMaps sm{};
+  if (p.win) {
+    if ((rc = map_store(&sm.out, y, B, 2 * Hi, 2 * Wi, ldy, 2, true))) return rc;
+    if (p.bwd.dz32 && (rc = map_store(&sm.dz, p.bwd.dz32, B, 2 * Hi, 2 * Wi, p.bwd.Cy, 4, true))) return rc;
+  }
+  return launch(ta, tb, sm, p, stream, stat_rows);
 }
 
 // partial[splits][Cs][16*Cl] (fp32): per-split sums of S[b,i,j,cs] * L[b,2i+kh-1,2j+kw-1,cl], column = (kh*4+kw)*Cl + cl.
@@ -1282,7 +1557,7 @@ int b200_wgrad_gemm(const void* S, int B, int Hs, int Ws, int Cs, int lds, const
   int rc;
   if ((rc = map_nhwc(&ta, S, B, Hs, Ws, Cs, lds, p.tw, p.th, p.nb))) return rc;
   if ((rc = map_nhwc_parity(&tb, L, B, 2 * Hs, 2 * Ws, Cl, p.tw, p.th, p.nb))) return rc;
-  return launch(ta, tb, p, stream, nullptr);
+  return launch(ta, tb, StoreMaps{}, p, stream, nullptr);
 }
 
 int b200_splitk_reduce(const float* partial, int ksplit, long long P, int C, void* out, int ldy, cudaStream_t stream) {
