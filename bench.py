@@ -289,7 +289,8 @@ def run_b200(args):
     torch.manual_seed(0)
     G = networks.get_network("generator", "unet").to(dev).train()  # reference default: dropout ON
     D = networks.PatchGANDiscriminator(sigmoid=(kind != "wgan"), imagedim=R).to(dev).train()
-    tr = InpaintingTrainer(kind, G, D, recon=recon, distributed=(world > 1 and not infer), bucket_mb=args.bucket_mb, graph=not args.no_graph, rank=rank)
+    tr = InpaintingTrainer(kind, G, D, recon=recon, distributed=(world > 1 and not infer), bucket_mb=args.bucket_mb, graph=not args.no_graph, rank=rank,
+                           comm_sms=args.comm_sms)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -398,6 +399,9 @@ def run_b200(args):
     if rank == 0:
         _lib.PROFILE = hook
     tr.graph = False  # the instrumented step is enqueued kernel by kernel (events around every C-ABI call)
+    # keep the GPU BEHIND the host while the ~210 calls and ~420 events are enqueued (about 5 ms of Python): every event then
+    # brackets its kernel back to back with its neighbours, and no interval contains time the GPU spent waiting for a launch
+    torch.cuda._sleep(int(0.03 * 1.9e9))
     step_dev()  # every rank takes part (the step contains the gradient all-reduces); only rank 0 is instrumented
     torch.cuda.synchronize()
     tr.graph = not args.no_graph
@@ -495,6 +499,7 @@ def run_b200(args):
                    "recipe": args.recipe, "res": R, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                    "dropout": not infer, "l2": "no flush: one step streams several GB of activations/gradients, far larger than the 126 MB L2",
                    "bn": "running statistics (eval)" if infer else "per-replica batch statistics", "bucket_mb": args.bucket_mb,
+                   "comm_sms": (args.comm_sms if args.comm_sms is not None else int(os.environ.get("B200_COMM_SMS", "8"))) if world > 1 else 0,
                    "launch": "eager (one ctypes call per kernel)" if (args.no_graph or infer) else "whole step replayed as one CUDA graph"},
         "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
@@ -520,6 +525,7 @@ def main():
     ap.add_argument("--res", type=int, default=None, help="image side (default 256; inference 512)")
     ap.add_argument("--ref-batch", type=int, default=4, help="images per step of the bounded CPU sample")
     ap.add_argument("--bucket-mb", type=float, default=25.0)
+    ap.add_argument("--comm-sms", type=int, default=None, help="SMs kept free for the gradient all-reduces while they are in flight (default: B200_COMM_SMS or 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the short D-only / inference measurements of the default run")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying the captured step graph")

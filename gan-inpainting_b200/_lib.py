@@ -30,7 +30,6 @@ SIGNATURES = {
     "b200_convt_s2_gemm": [P, I, I, I, I, I, P, I, P, I, I, I, P, POINTER(c_int), P, I, P, S],
     "b200_splitk_reduce": [P, I, L, I, P, I, S],
     "b200_wgrad_gemm": [P, I, I, I, I, I, P, I, P, POINTER(c_int), I, I, S],
-    "b200_debug_tma_probe": [P, I, I, I, I, I, I, I, I, I, I, I, I, I, P, S],
     # ---- weight layouts (csrc/pack.cu)
     "b200_pack_gather": [P, I, I, P, S],
     "b200_pack_phase": [P, I, I, P, S],
@@ -78,6 +77,7 @@ VALUE_FUNCS = {
     "b200_launch_count": (c_longlong, []),
     "b200_launch_count_add": (None, [c_longlong]),
     "b200_set_seed_counter": (None, [c_void_p]),
+    "b200_set_sm_limit": (None, [c_int]),
     "b200_bn_stat_blocks": (c_int, [L, I]),
     "b200_igemm_stat_rows": (c_int, []),
     "b200_wgrad_c1_blocks": (c_int, []),

@@ -27,7 +27,14 @@ bool b200_pdl_enabled(void) {
 static const uint32_t* g_seed_counter = nullptr;
 const uint32_t* b200_seed_counter_ptr(void) { return g_seed_counter; }
 
+static int g_sm_limit = 148;
+int b200_sm_limit(void) { return g_sm_limit; }
+
 extern "C" {
+// SMs the persistent GEMM kernels may occupy (one CTA per SM, static tile schedule).  A data-parallel trainer lowers it while
+// gradient all-reduces are in flight: the collective's CTAs then never take an SM a persistent CTA was counting on (a CTA that
+// starts late stretches the whole launch).  n <= 0 or n > 148 restores all SMs.
+void b200_set_sm_limit(int n) { g_sm_limit = (n <= 0 || n > 148) ? 148 : n; }
 // device uint32 added (x odd constant) to the seed of every dropout mask drawn by kernels enqueued afterwards; NULL = off
 void b200_set_seed_counter(const unsigned* dev_counter) { g_seed_counter = dev_counter; }
 // replaying a captured graph launches kernels this library enqueued at capture time: account for them

@@ -25,6 +25,7 @@ void b200_set_error(const char* msg);
 void b200_count_launch(void);
 bool b200_pdl_enabled(void);  // programmatic dependent launch for every kernel of this library (opt-in: env B200_PDL=1)
 const uint32_t* b200_seed_counter_ptr(void);  // device counter added to every dropout seed (null: none)
+int b200_sm_limit(void);                      // SMs the persistent GEMMs may use (b200_set_sm_limit)
 
 namespace b200 {
 

@@ -1040,30 +1040,6 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
   }
 }
 
-// Debug aid: load one TMA box into shared memory and copy the raw (swizzled) bytes out.
-__global__ void tma_probe_kernel(const __grid_constant__ CUtensorMap tm, int rank, int c0, int c1, int c2, int c3, int c4, int bytes,
-                                 uint8_t* out) {
-  b200::pdl_enter();
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t bar;
-  if (threadIdx.x == 0) {
-    mbar_init(&bar, 1);
-    fence_barrier_init();
-  }
-  for (int i = threadIdx.x; i < bytes; i += blockDim.x) smem[i] = 0xEE;
-  fence_proxy_async();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    mbar_arrive_expect_tx(&bar, (uint32_t)bytes);
-    if (rank == 2) tma_load_2d(smem, &tm, &bar, c0, c1);
-    if (rank == 4) tma_load_4d(smem, &tm, &bar, c0, c1, c2, c3);
-    if (rank == 5) tma_load_5d(smem, &tm, &bar, c0, c1, c2, c3, c4);
-  }
-  mbar_wait(&bar, 0);
-  for (int i = threadIdx.x; i < bytes; i += blockDim.x) out[i] = smem[i];
-}
-
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -1302,7 +1278,8 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const StoreMaps& s
   while ((int)cols < 2 * p.BN) cols <<= 1;
   p.tmem_cols = cols;
   const size_t smem = (size_t)p.stages * stage_bytes + ring_a + extra;
-  const int grid = p.pair ? 2 * (p.num_tiles < kNumSMs / 2 ? p.num_tiles : kNumSMs / 2) : (p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs);
+  const int sms = b200_sm_limit();  // all 148, or fewer while a trainer keeps SMs free for gradient all-reduces
+  const int grid = p.pair ? 2 * (p.num_tiles < sms / 2 ? p.num_tiles : sms / 2) : (p.num_tiles < sms ? p.num_tiles : sms);
   if (grid_out) *grid_out = grid;
   const bool bn = p.bwd.scale != nullptr, g2 = p.bwd.g2 != nullptr;
   const int act = p.bwd.act;
@@ -1568,23 +1545,6 @@ int b200_splitk_reduce(const float* partial, int ksplit, long long P, int C, voi
   long long blocks = (P * (C >> 3) + 255) / 256;
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
   B200_LAUNCH((splitk_reduce_kernel), (int)blocks, 256, 0, stream, partial, ksplit, P, C, (__nv_bfloat16*)out, ldy);
-  B200_CHECK_LAUNCH();
-  return B200_OK;
-}
-
-// Debug: raw shared-memory image of one TMA box of the parity view (kind 0) or the plain view (kind 1).
-int b200_debug_tma_probe(const void* x, int B, int H, int W, int C, int kind, int tw, int th, int nb, int c0, int c1, int c2, int c3, int c4, void* out,
-                         cudaStream_t stream) {
-  CUtensorMap tm;
-  int rc;
-  if (kind == 0) {
-    if ((rc = map_nhwc_parity(&tm, x, B, H, W, C, tw, th, nb))) return rc;
-  } else {
-    if ((rc = map_nhwc(&tm, x, B, H, W, C, C, tw, th, nb))) return rc;
-  }
-  const int bytes = 128 * tw * th * nb;
-  cudaFuncSetAttribute(tma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  B200_LAUNCH((tma_probe_kernel), 1, 128, bytes + 1024, stream, tm, kind == 0 ? 5 : 4, c0, c1, c2, c3, c4, bytes, (uint8_t*)out);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

@@ -45,13 +45,17 @@ class GradBucketer:
     """Bucketed, overlapped gradient all-reduce over a flat gradient buffer whose tensors complete in descending
     address order during backward (decoder outermost..innermost, then encoder innermost..outermost)."""
 
-    def __init__(self, group: optim.FlatGroup, bucket_mb: float = 25.0, process_group=None):
+    def __init__(self, group: optim.FlatGroup, bucket_mb: float = 25.0, process_group=None, comm_sms: int = 0):
         import torch.distributed as dist
 
         self.dist = dist
         self.pg = process_group
         self.world = dist.get_world_size(process_group)
         self.group = group
+        # SMs left to the collective while buckets are in flight: the persistent GEMMs (one CTA per SM, static tile schedule) are
+        # launched on 148 - comm_sms SMs from the first bucket until finish(), so that NCCL's CTAs never hold an SM a persistent
+        # CTA was counting on (a late-starting CTA stretches its whole launch — the 0.4-0.7 ms a step lost at 2-8 GPUs in round 1)
+        self.comm_sms = int(comm_sms)
         self.bucket_elems = max(1, int(bucket_mb * (1 << 20) / 4))
         self.cuda = group.grads.is_cuda
         self.comm = torch.cuda.Stream() if self.cuda else None
@@ -82,6 +86,8 @@ class GradBucketer:
         if lo >= self.hi:
             return
         bucket = self.group.grads[lo : self.hi]
+        if self.cuda and self.comm_sms > 0 and self.launched == 0:
+            _lib.value("b200_set_sm_limit", 148 - self.comm_sms)
         if self.cuda:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream())
@@ -98,6 +104,8 @@ class GradBucketer:
         self._launch(0)
         if self.cuda:
             torch.cuda.current_stream().wait_stream(self.comm)
+            if self.comm_sms > 0:
+                _lib.value("b200_set_sm_limit", 0)
         n = self.launched
         self.reset()
         return n
@@ -105,7 +113,8 @@ class GradBucketer:
 
 class InpaintingTrainer:
     def __init__(self, recipe: str, net_G, net_D, net_D_local=None, recon: str = "l1", lambdas=(300.0, 300.0), clip: float = 0.01,
-                 distributed: bool = False, bucket_mb: float = 25.0, log_grad_means: bool = False, graph: bool = False, rank: Optional[int] = None):
+                 distributed: bool = False, bucket_mb: float = 25.0, log_grad_means: bool = False, graph: bool = False, rank: Optional[int] = None,
+                 comm_sms: Optional[int] = None, bucket_mb_d: float = 4.0):
         if recipe not in ("wgan", "minimax", "global_local"):
             raise ValueError(recipe)
         if recipe == "global_local" and net_D_local is None:
@@ -140,12 +149,18 @@ class InpaintingTrainer:
         if distributed:
             import torch.distributed as dist
 
+            import os
+
             self.world = dist.get_world_size()
             self.rank = dist.get_rank()
+            if comm_sms is None:
+                comm_sms = int(os.environ.get("B200_COMM_SMS", "8"))
             for fg in (self.fG, self.fD, self.fDl):
                 if fg is not None:
                     dist.broadcast(fg.params, src=0)
-                    self.buckets[id(fg)] = GradBucketer(fg, bucket_mb)
+                    # the discriminators' 11 MB of gradients use small buckets: their all-reduce then overlaps the rest of the D
+                    # backward pass instead of starting after it
+                    self.buckets[id(fg)] = GradBucketer(fg, bucket_mb if fg is self.fG else min(bucket_mb, bucket_mb_d), comm_sms=comm_sms)
             for net in (net_G, net_D, net_D_local):
                 if net is not None:
                     for b in net.buffers():

@@ -53,6 +53,10 @@ void b200_launch_count_add(long long n); /* a replayed CUDA graph re-launches n 
  * effective seed of every kernel enqueued afterwards is seed + *dev_counter * odd constant, read when the kernel RUNS: a captured
  * CUDA graph of the whole train step then draws fresh masks on every replay (bump the counter with b200_step_inc).  NULL = off. */
 void b200_set_seed_counter(const unsigned* dev_counter);
+/* SMs the persistent GEMM kernels may occupy (default: all 148).  The data-parallel trainer lowers it while bucketed gradient
+ * all-reduces are in flight (the reference is single-GPU, wgan_l1.py:50-52), so that the collective's CTAs never hold
+ * an SM that a statically scheduled persistent CTA was counting on.  n <= 0 restores all SMs. */
+void b200_set_sm_limit(int n);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * tcgen05 implicit-GEMM convolutions (csrc/conv_gemm.cu).  4x4 kernel, stride 2, padding 1; TMA-staged NHWC bf16
@@ -107,10 +111,6 @@ int b200_splitk_reduce(const float* partial, int ksplit, long long P, int C, voi
  * partial: (*splits_io) * Cs * 16 * Cl floats.  Reduce with b200_wgrad_reduce. */
 int b200_wgrad_gemm(const void* S, int B, int Hs, int Ws, int Cs, int lds, const void* L, int Cl, void* partial, int* splits_io, int bn_hint, int stages,
                     b200_stream_t stream);
-
-/* bring-up aid: raw shared-memory image of one TMA box */
-int b200_debug_tma_probe(const void* x, int B, int H, int W, int C, int kind, int tw, int th, int nb, int c0, int c1, int c2, int c3, int c4, void* out,
-                         b200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * weight layouts (csrc/pack.cu).  w is the fp32 checkpoint tensor [D0][D1][4][4]

@@ -471,3 +471,8 @@ def test_two_rank_data_parallel_graph_step(dev):
            os.path.join(root, "tools", "ddp_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "DDP_CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+    # ... and against the oracle: N reference replicas at batch b with averaged gradients
+    cmd[-1] = os.path.join(root, "tests", "ddp_oracle_check.py")
+    cmd[cmd.index("29611")] = "29612"
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=500)
+    assert r.returncode == 0 and "DDP_ORACLE_CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]

@@ -1,19 +1,11 @@
 #!/bin/bash
-# One gpurun call of round 2 (kept for reproducibility): GPU tests, per-layer timings, bench.
+# One gpurun --gpus 2 call of round 2 (kept for reproducibility): 2-rank checks (self-consistency + oracle) and all-reduce overlap A/B.
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q --deselect tests/test_headline_gpu.py > gpurun_out/pytest_gpu.log 2>&1; tail -5 gpurun_out/pytest_gpu.log
-for st in 0 1; do
-python tools/one_layer.py conv 64 128 64 128 10 $st
-python tools/one_layer.py conv 64 64 128 256 10 $st
-python tools/one_layer.py conv 64 32 256 512 10 $st
-python tools/one_layer.py convt 64 64 256 64 10 $st
-python tools/one_layer.py convt 64 32 512 128 10 $st
-python tools/one_layer.py convt 64 16 1024 256 10 $st
-done > gpurun_out/one_layer_cio.log 2>&1
-cat gpurun_out/one_layer_cio.log
-python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-also > gpurun_out/bench_cio.json 2> gpurun_out/bench_cio.err; cut -c1-300 gpurun_out/bench_cio.json; tail -3 gpurun_out/bench_cio.err
-B200_WINDOW=0 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-also > gpurun_out/bench_cio_nowin.json 2> gpurun_out/bench_cio_nowin.err; cut -c1-300 gpurun_out/bench_cio_nowin.json
-python bench.py --recipe inference --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_inf_cio.json 2> gpurun_out/bench_inf_cio.err; cut -c1-300 gpurun_out/bench_inf_cio.json
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 1300 --csv --log-file gpurun_out/launches_cio.csv \
-  python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-graph --no-also > gpurun_out/ncu.log 2>&1
-tail -2 gpurun_out/ncu.log | cut -c 1-200
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 tools/ddp_check.py > gpurun_out/ddp_check.log 2>&1; tail -2 gpurun_out/ddp_check.log
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29612 tests/ddp_oracle_check.py > gpurun_out/ddp_oracle_check.log 2>&1; tail -2 gpurun_out/ddp_oracle_check.log
+python bench.py --gpus 1 --steps 20 --warmup 5 --no-cpu-baseline --no-also > gpurun_out/b2_n1.json 2> gpurun_out/b2_n1.err; cut -c1-260 gpurun_out/b2_n1.json
+python bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/b2_default.json 2> gpurun_out/b2_default.err; cut -c1-260 gpurun_out/b2_default.json; tail -2 gpurun_out/b2_default.err
+python bench.py --gpus 2 --steps 20 --warmup 5 --comm-sms 0 > gpurun_out/b2_sms0.json 2> gpurun_out/b2_sms0.err; cut -c1-260 gpurun_out/b2_sms0.json
+NCCL_MAX_CTAS=8 python bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/b2_cta8.json 2> gpurun_out/b2_cta8.err; cut -c1-260 gpurun_out/b2_cta8.json
+NCCL_MAX_CTAS=16 python bench.py --gpus 2 --steps 20 --warmup 5 --comm-sms 16 > gpurun_out/b2_cta16.json 2> gpurun_out/b2_cta16.err; cut -c1-260 gpurun_out/b2_cta16.json
+NCCL_MAX_CTAS=4 python bench.py --gpus 2 --steps 20 --warmup 5 --comm-sms 4 > gpurun_out/b2_cta4.json 2> gpurun_out/b2_cta4.err; cut -c1-260 gpurun_out/b2_cta4.json
