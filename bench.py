@@ -499,7 +499,7 @@ def run_b200(args):
                    "recipe": args.recipe, "res": R, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                    "dropout": not infer, "l2": "no flush: one step streams several GB of activations/gradients, far larger than the 126 MB L2",
                    "bn": "running statistics (eval)" if infer else "per-replica batch statistics", "bucket_mb": args.bucket_mb,
-                   "comm_sms": (args.comm_sms if args.comm_sms is not None else int(os.environ.get("B200_COMM_SMS", "8"))) if world > 1 else 0,
+                   "comm_sms": (args.comm_sms if args.comm_sms is not None else int(os.environ.get("B200_COMM_SMS", "0"))) if world > 1 else 0,
                    "launch": "eager (one ctypes call per kernel)" if (args.no_graph or infer) else "whole step replayed as one CUDA graph"},
         "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
@@ -525,7 +525,7 @@ def main():
     ap.add_argument("--res", type=int, default=None, help="image side (default 256; inference 512)")
     ap.add_argument("--ref-batch", type=int, default=4, help="images per step of the bounded CPU sample")
     ap.add_argument("--bucket-mb", type=float, default=25.0)
-    ap.add_argument("--comm-sms", type=int, default=None, help="SMs kept free for the gradient all-reduces while they are in flight (default: B200_COMM_SMS or 8)")
+    ap.add_argument("--comm-sms", type=int, default=None, help="SMs kept free for the gradient all-reduces while they are in flight (default: B200_COMM_SMS or 0 = none)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the short D-only / inference measurements of the default run")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying the captured step graph")

@@ -66,6 +66,8 @@ SIGNATURES = {
     "b200_absmean": [P, P, I, P, S],
     # ---- SSIM metric (csrc/ssim.cu)
     "b200_ssim": [P, P, I, I, I, I, POINTER(c_float), I, P, P, S],
+    # ---- input pipeline: greyscale + resize + ToTensor (csrc/preprocess.cu)
+    "b200_preprocess": [P, I, I, I, I, I, I, P, P, P, I, P, P, P, I, P, P, S],
     # ---- total-variation loss (csrc/tv.cu)
     "b200_tv_loss": [P, L, I, I, F, P, P, S],
     "b200_tv_loss_bwd": [P, L, I, I, F, P, P, I, S],

@@ -154,7 +154,7 @@ class InpaintingTrainer:
             self.world = dist.get_world_size()
             self.rank = dist.get_rank()
             if comm_sms is None:
-                comm_sms = int(os.environ.get("B200_COMM_SMS", "8"))
+                comm_sms = int(os.environ.get("B200_COMM_SMS", "0"))
             for fg in (self.fG, self.fD, self.fDl):
                 if fg is not None:
                     dist.broadcast(fg.params, src=0)

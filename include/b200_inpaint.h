@@ -234,6 +234,18 @@ int b200_tv_loss(const float* img, long long planes, int H, int W, float weight,
 int b200_tv_loss_bwd(const float* img, long long planes, int H, int W, float weight, const float* gscale, float* dimg, int accumulate,
                      b200_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Input pipeline (csrc/preprocess.cu) — what the reference does to every decoded image on the host, for a batch on the GPU:
+ * lib/data/dataset.py:6-12 (`Image.open(f).convert('L')`) and train.py:69-72 (`transforms.Resize(size)` + `transforms.ToTensor()`).
+ * src: uint8 [B,H,W,channels] (3 = RGB, 1 = L); out: fp32 [B,1,outH,outW] in [0,1]; tmp: B*H*outW bytes.  Bit-exact with
+ * Pillow + torchvision: L = (R*19595 + G*38470 + B*7471 + 0x8000) >> 16; separable triangle-filter resample in 22-bit fixed point,
+ * horizontal pass first with an 8-bit intermediate; division by 255.f.  (xmin, xcnt, xk[outW][ksize_x]) and
+ * (ymin, ycnt, yk[outH][ksize_y]) are device arrays: first source index, tap count and fixed-point weights per output column / row
+ * (Pillow's precompute_coeffs + normalize_coeffs_8bpc; gan-inpainting_b200/data.py computes them).
+ * ------------------------------------------------------------------------------------------------------------------ */
+int b200_preprocess(const void* src, int B, int H, int W, int channels, int outH, int outW, const int* xmin, const int* xcnt, const int* xk, int ksize_x,
+                    const int* ymin, const int* ycnt, const int* yk, int ksize_y, void* tmp, float* out, b200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

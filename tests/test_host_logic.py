@@ -256,3 +256,19 @@ def test_bench_inputs_and_flop_counts_are_independent_of_the_oracle_but_equal_to
     src = open(os.path.join(ROOT, "bench.py")).read()
     b200_arm = src[src.index("def run_b200("):src.index("def main(")]
     assert "oracle" not in b200_arm.replace("oracle port", "").replace("time_cpu", "")
+
+
+def test_gpu_load_transform_tap_tables_match_the_oracle():
+    """data.GpuLoadTransform computes Pillow's resample taps on the host (the kernel only does the integer MACs): same first index,
+    tap count and 22-bit weights as the oracle's restatement, same output size rule as transforms.Resize(int) (train.py:69-72)."""
+    import numpy as np
+    from gan_inpainting_b200 import data
+    from oracle import preprocess
+
+    for n_in, n_out in [(256, 128), (260, 128), (96, 128), (128, 128), (513, 256), (1024, 256), (7, 3)]:
+        ksize, first, count, weights = data._triangle_taps(n_in, n_out)
+        k2, xmin, xcnt, kk = preprocess.bilinear_coeffs(n_in, n_out)
+        assert ksize == k2 and list(xmin) == first and list(xcnt) == count and np.array_equal(kk, np.array(weights, dtype=np.int32))
+    t = data.GpuLoadTransform(128, "cpu")
+    for h, w in [(300, 260), (260, 300), (128, 128), (64, 200)]:
+        assert t.output_size(h, w) == preprocess.resize_output_size(h, w, 128)

@@ -634,3 +634,26 @@ def test_tv_loss_forward_backward(dev):
         assert rel(x.grad, xr.grad) < F32_TOL, name
     with pytest.raises(Exception):
         bl.tv_loss(img, 1.0)  # CPU tensor: no fallback
+
+
+def test_gpu_load_transform_bit_exact(dev):
+    """b200_preprocess (greyscale + Resize + ToTensor of a batch on the GPU; lib/data/dataset.py:6-12, train.py:69-72): bit-exact
+    against the tensors Pillow + torchvision produced (tests/golden/reference_preprocess.pt) and against the oracle on a batch."""
+    import os
+
+    import numpy as np
+    from gan_inpainting_b200 import data
+    from oracle import preprocess
+
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_preprocess.pt"))
+    for c in g["cases"]:
+        t = data.GpuLoadTransform(c["size"], dev)
+        out = t(c["image"][None].to(dev))
+        assert out.shape[1:] == c["out"].shape and torch.equal(out[0].cpu(), c["out"])
+    rng = np.random.default_rng(3)
+    batch = rng.integers(0, 256, (5, 200, 168, 3), dtype=np.uint8)
+    out = data.GpuLoadTransform(64, dev)(torch.from_numpy(batch))
+    ref = np.stack([preprocess.load_transform(b, 64) for b in batch])
+    assert torch.equal(out.cpu(), torch.from_numpy(ref))
+    with pytest.raises(_lib().B200Error):
+        data.GpuLoadTransform(64, dev)(torch.zeros(2, 8, 8, 2, dtype=torch.uint8))

@@ -158,3 +158,25 @@ def test_tv_oracle_matches_reference_golden():
         o.backward()
         ne, se = summary_close(x.grad, gold[name]["grad"], 0)
         assert ne < 1e-5 and se < 1e-5, name
+
+
+def test_preprocess_oracle_matches_pillow_torchvision_golden():
+    """oracle/preprocess.py (greyscale + Resize + ToTensor, lib/data/dataset.py:6-12 / train.py:69-72) against the tensors Pillow +
+    torchvision produced in the build container (oracle/pin_preprocess_against_reference.py): bit for bit."""
+    import os
+
+    import numpy as np
+    from oracle import preprocess
+
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_preprocess.pt"))
+    assert len(g["cases"]) >= 5
+    for c in g["cases"]:
+        got = torch.from_numpy(preprocess.load_transform(c["image"].numpy(), c["size"]))
+        assert got.shape == c["out"].shape and torch.equal(got, c["out"])
+    # edge cases: a 1-pixel-high strip, identity size, extreme down-scale
+    rng = np.random.default_rng(1)
+    img = rng.integers(0, 256, (1, 40), dtype=np.uint8)
+    assert preprocess.load_transform(img, 1).shape == (1, 1, 40)
+    img = rng.integers(0, 256, (64, 64), dtype=np.uint8)
+    assert np.array_equal(preprocess.load_transform(img, 64)[0], img.astype(np.float32) / np.float32(255))
+    assert preprocess.load_transform(rng.integers(0, 256, (512, 512, 3), dtype=np.uint8), 4).shape == (1, 4, 4)

@@ -376,6 +376,27 @@ def test_device_prefetcher_feeds_identical_batches(dev):
         assert torch.equal(g.cpu(), hg) and torch.equal(m.cpu(), hm)
 
 
+def test_device_prefetcher_with_gpu_load_transform(dev):
+    """Decoded uint8 images through DevicePrefetcher(transform=GpuLoadTransform): the batches the train step sees equal the
+    reference's host pipeline (pil_loader -> Resize -> ToTensor, lib/data/dataset.py:6-12 / train.py:69-72) bit for bit."""
+    import numpy as np
+    from gan_inpainting_b200.data import DevicePrefetcher, GpuLoadTransform
+    from oracle import preprocess
+    rng = np.random.default_rng(11)
+    batches = []
+    for i in range(3):
+        img = rng.integers(0, 256, (2, 160, 160, 3), dtype=np.uint8)
+        msk = np.zeros((2, 160, 160), np.uint8)
+        msk[:, 30 + i:90, 40:120 - i] = 255
+        batches.append((torch.from_numpy(img), torch.from_numpy(msk), i))
+    for (g, m, tag), (hg, hm, _) in zip(DevicePrefetcher(batches, dev, transform=GpuLoadTransform(128, dev)), batches):
+        assert g.shape == (2, 1, 128, 128) and g.dtype == torch.float32 and m.shape == (2, 1, 128, 128)
+        ref_g = np.stack([preprocess.load_transform(x, 128) for x in hg.numpy()])
+        ref_m = np.stack([preprocess.load_transform(x, 128) for x in hm.numpy()])
+        assert torch.equal(g.cpu(), torch.from_numpy(ref_g)) and torch.equal(m.cpu(), torch.from_numpy(ref_m))
+        assert float(m.max()) == 1.0 and 0.0 < float(m[m > 0].min()) < 1.0  # resized masks have soft edges: ceil() binarises them (wgan_l1.py:114)
+
+
 @pytest.mark.parametrize("recipe", ["wgan", "minimax"])
 def test_graph_replayed_step_equals_eager_step(dev, recipe):
     """InpaintingTrainer(graph=True): the first batch runs eagerly, the step is captured into a CUDA graph, later batches replay
