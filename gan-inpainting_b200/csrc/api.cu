@@ -14,15 +14,18 @@ void b200_set_error(const char* msg) {
 static long long g_launches = 0;
 void b200_count_launch(void) { ++g_launches; }
 
-bool b200_pdl_enabled(void) {
-  static const bool on = [] {
-    // measured on B200 (bench.py, step replayed as a CUDA graph): 7.44 ms/step with programmatic edges vs 7.32 ms without — the
-    // graph already hides the launch latency and early-resident dependents only add contention, so it is opt-in (B200_PDL=1)
+// Programmatic dependent launch: B200_PDL=1 every kernel, B200_PDL=2 every kernel EXCEPT the persistent tcgen05 GEMMs (a GEMM needs
+// all 227 KB of shared memory of every SM, so letting it become resident early buys nothing and its spinning CTAs delay the
+// predecessor's tail), unset / 0: off.  Measured on B200 with the step replayed as a CUDA graph: see profiles/experiments/README.md.
+static int pdl_mode(void) {
+  static const int mode = [] {
     const char* e = getenv("B200_PDL");
-    return e && e[0] == '1';
+    return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0;
   }();
-  return on;
+  return mode;
 }
+bool b200_pdl_enabled(void) { return pdl_mode() != 0; }
+bool b200_pdl_gemm_enabled(void) { return pdl_mode() == 1; }
 
 static const uint32_t* g_seed_counter = nullptr;
 const uint32_t* b200_seed_counter_ptr(void) { return g_seed_counter; }

@@ -23,7 +23,8 @@
 
 void b200_set_error(const char* msg);
 void b200_count_launch(void);
-bool b200_pdl_enabled(void);  // programmatic dependent launch for every kernel of this library (opt-in: env B200_PDL=1)
+bool b200_pdl_enabled(void);       // programmatic dependent launch (opt-in: env B200_PDL=1 all kernels, 2 all but the persistent GEMMs)
+bool b200_pdl_gemm_enabled(void);  // ... for the persistent GEMM kernels
 const uint32_t* b200_seed_counter_ptr(void);  // device counter added to every dropout seed (null: none)
 int b200_sm_limit(void);                      // SMs the persistent GEMMs may use (b200_set_sm_limit)
 

@@ -1159,13 +1159,25 @@ static void launch_variant_w(const CUtensorMap& a, const CUtensorMap& b, const S
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = b200_pdl_enabled() ? 2 : 1;
+    cfg.numAttrs = b200_pdl_gemm_enabled() ? 2 : 1;
     cudaLaunchKernelEx(&cfg, igemm_kernel<E, true, WIN>, a, b, sm.out, sm.dz, p);
     return;
   }
   static std::once_flag once;
   std::call_once(once, [] { cudaFuncSetAttribute(igemm_kernel<E, false, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
-  B200_LAUNCH((igemm_kernel<E, false, WIN>), grid, kThreads, smem, stream, a, b, sm.out, sm.dz, p);
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = b200_pdl_gemm_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, igemm_kernel<E, false, WIN>, a, b, sm.out, sm.dz, p);
+  }
 }
 template <class E>
 static void launch_variant(const CUtensorMap& a, const CUtensorMap& b, const StoreMaps& sm, const IGemmParams& p, int grid, size_t smem,
