@@ -50,8 +50,12 @@ def every_batch(batch_idx: int, g_iter: int) -> bool:
     return True
 
 
-def _logger(title: str, log_dir: str) -> logging.Logger:
+def _logger(title: str, log_dir: str, to_file: bool = True) -> logging.Logger:
     logger = logging.getLogger(title)
+    if not to_file:  # data-parallel ranks other than 0
+        if not logger.handlers:
+            logger.addHandler(logging.NullHandler())
+        return logger
     os.makedirs(log_dir, exist_ok=True)
     if not logger.handlers:
         hdlr = logging.FileHandler(os.path.join(log_dir, "{}.log".format(title)))
@@ -68,10 +72,17 @@ def run(state: dict, loaders: dict, title: str, recipe: str, recon: str, schedul
     train_loader, test_loader = loaders["train"], loaders.get("test")
     experiment_dir = state.get("experiment_dir") or os.path.join("model", title)
     os.makedirs(experiment_dir, exist_ok=True)
-    logger = _logger(title, state.get("log_dir", "log"))
     if not torch.cuda.is_available():
         raise RuntimeError("the B200 train step has no CPU path (the reference falls back to CPU at wgan_l1.py:50-52; this build does not)")
     distributed = bool(state.get("distributed", False))
+    # data parallel (one process per GPU): every rank trains, only rank 0 writes checkpoints / history pickles / the log file and
+    # runs the evaluation pass; the others wait at a barrier so that nobody races ahead of a half-written checkpoint
+    rank0 = True
+    if distributed:
+        import torch.distributed as dist
+
+        rank0 = dist.get_rank() == 0
+    logger = _logger(title, state.get("log_dir", "log"), to_file=rank0)
     device = torch.device("cuda", torch.cuda.current_device())
     logger.info("using device %s", device)
     R = int(state.get("imagedim", 128))
@@ -147,7 +158,7 @@ def run(state: dict, loaders: dict, title: str, recipe: str, recon: str, schedul
             eg["ssim"] = float(ssim_acc) / n_images
         training_epoch_hist.append({"g": eg, "d": ed, "gradients": gh})
 
-        if epoch % evaluate_every == 0 and epoch > 0:
+        if epoch % evaluate_every == 0 and epoch > 0 and rank0:
             entry = {"train": evaluate_fn(net_G, train_loader, "train"), "test": evaluate_fn(net_G, test_loader, "test") if test_loader is not None else None}
             eval_hist.append(entry)
             logger.info("VALIDATION: train - {}, test - {}".format(str(entry["train"]), str(entry["test"])))
@@ -155,11 +166,15 @@ def run(state: dict, loaders: dict, title: str, recipe: str, recon: str, schedul
                 pickle.dump(training_epoch_hist, handle, protocol=pickle.HIGHEST_PROTOCOL)
             with open(os.path.join(experiment_dir, "eval_history.obj"), "wb") as handle:
                 pickle.dump(eval_hist, handle, protocol=pickle.HIGHEST_PROTOCOL)
-        if epoch % save_every == 0 and epoch > 0:
+        if epoch % save_every == 0 and epoch > 0 and rank0:
             try:
                 torch.save(net_G.state_dict(), os.path.join(experiment_dir, "epoch{}_G.pt".format(epoch)))
             except Exception:  # the reference logs and carries on (wgan_l1.py:270-274)
                 logger.exception("checkpoint failed")
+        if distributed and (epoch % evaluate_every == 0 or epoch % save_every == 0) and epoch > 0:
+            dist.barrier()
         logger.info("epoch %d done in %.1fs" % (epoch, time.time() - start))
+    if distributed:
+        tr.release_graphs()  # captured NCCL collectives pin the communicator: must go before the caller's destroy_process_group()
     return {"net_G": net_G, "net_D": net_D, "net_D_local": net_Dl, "trainer": tr, "history": training_epoch_hist, "eval_history": eval_hist,
             "g_iter": g_iter, "d_iter": d_iter}

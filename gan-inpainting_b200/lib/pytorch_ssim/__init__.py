@@ -6,7 +6,6 @@ out of shared memory + the pointwise SSIM formula + block reduction) instead of 
 from __future__ import annotations
 
 import ctypes
-from math import exp
 
 import torch
 
@@ -15,17 +14,18 @@ from ..._lib import call, ptr, stream
 
 
 def gaussian(window_size, sigma):
-    """pytorch_ssim gaussian (:10-12): normalised 1-D Gaussian, fp32."""
-    gauss = torch.Tensor([exp(-(x - window_size // 2) ** 2 / float(2 * sigma ** 2)) for x in range(window_size)])
-    return gauss / gauss.sum()
+    """The 1-D window of the metric: ``window_size`` samples of a zero-centred Gaussian of width ``sigma``, normalised to sum 1
+    (fp32, like the reference's helper of the same name)."""
+    offsets = torch.arange(window_size, dtype=torch.float64) - (window_size // 2)
+    taps = torch.exp(-(offsets * offsets) / (2.0 * float(sigma) ** 2))
+    return (taps / taps.sum()).float()
 
 
 def create_window(window_size, channel):
-    """pytorch_ssim create_window (:14-18): [channel, 1, ws, ws] outer product of the 1-D Gaussian (kept for callers that build
-    their own window; the kernel applies the two 1-D passes)."""
-    w1 = gaussian(window_size, 1.5).unsqueeze(1)
-    w2 = w1.mm(w1.t()).float().unsqueeze(0).unsqueeze(0)
-    return w2.expand(channel, 1, window_size, window_size).contiguous()
+    """``[channel, 1, window_size, window_size]``: one 2-D window (outer product of the 1-D taps, sigma 1.5) per channel, for
+    callers that convolve themselves; the fused kernel applies the two 1-D passes."""
+    taps = gaussian(window_size, 1.5)
+    return torch.outer(taps, taps)[None, None].repeat(channel, 1, 1, 1).contiguous()
 
 
 def _ssim_cuda(img1, img2, window_size, size_average):
