@@ -695,37 +695,33 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int frow = lane >> 2, fch = lane & 3;  // cp.async mapping: pixel of the image row, 16-byte channel chunk
       const bool convt = (p.mode == MODE_CONVT);
       uint32_t nchunk = 0;
-      auto pixel_of = [&](const TileCoord& ct, int hl, int wl) -> size_t {
-        if (!convt) return ((size_t)ct.b0 * p.Hs + (ct.h0 + hl)) * p.Ws + (ct.w0 + wl);
-        return ((size_t)ct.b0 * (2 * p.Hs) + (2 * (ct.h0 + hl) + (ct.phase >> 1))) * (size_t)(2 * p.Ws) + (2 * (ct.w0 + wl) + (ct.phase & 1));
-      };
-      // The chunks this warp handles form ONE stream over all its tiles (tile t: columns half*32, +64, ...; then tile t + tile_step).
-      // The y / skip-gradient slices of a chunk are requested one chunk ahead IN THAT STREAM — for narrow tiles (N = 64: a single
-      // chunk per warp and tile) that is a whole tile of lead time instead of none.  One cp.async group per call, empty when the
-      // chunk needs nothing (unfused columns, end of the stream), so the group accounting stays uniform.
-      auto fetch = [&](const TileCoord& ct, int cc, uint32_t slot, bool live) {
-        const int cb = ct.n0 + cc - p.bwd.col0;
-        if (live && cb >= 0) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int row = 8 * i + frow;
-            const size_t fp = pixel_of(ct, hq + i, frow);
-            const int off = (int)slot * 2048 + row * 64 + ((fch ^ ((row >> 1) & 3)) * 16);
-            cp_async16(ybuf + off, p.bwd.y + fp * p.bwd.ldy + cb + fch * 8);
-            if (E::G2) cp_async16(gbuf + off, p.bwd.g2 + fp * p.bwd.ldg2 + p.bwd.offg2 + cb + fch * 8);
-          }
-        }
-        cp_async_commit();
-      };
-      if (E::BWD && tile0 < p.num_tiles) fetch(decode_tile<PAIR>(p, tile0, rank), half * 32, 0u, half * 32 < p.BN);
       for (int t = tile0; t < p.num_tiles; t += tile_step, ++lt) {
         const TileCoord c = decode_tile<PAIR>(p, t, rank);
         const int buf = lt & 1;
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.BN);
         const int ph_p = c.phase >> 1, ph_q = c.phase & 1;
-        const size_t pix = pixel_of(c, r >> 3, r & 7);  // this lane's own accumulator row
+        auto pixel = [&](int hl, int wl) -> size_t {
+          if (!convt) return ((size_t)c.b0 * p.Hs + (c.h0 + hl)) * p.Ws + (c.w0 + wl);
+          return ((size_t)c.b0 * (2 * p.Hs) + (2 * (c.h0 + hl) + ph_p)) * (size_t)(2 * p.Ws) + (2 * (c.w0 + wl) + ph_q);
+        };
+        const size_t pix = pixel(r >> 3, r & 7);  // this lane's own accumulator row
         const int sp = (p.stat_parity == 2) ? (lt & 1) : 0;
         float* st = stat_smem + (sp * 4 + quad) * 2 * p.BN;
+        auto fetch = [&](int cc, uint32_t slot) {  // one cp.async group per call (empty when the chunk needs nothing)
+          const int cb = c.n0 + cc - p.bwd.col0;
+          if (cb >= 0 && cc < p.BN) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int row = 8 * i + frow;
+              const size_t fp = pixel(hq + i, frow);
+              const int off = (int)slot * 2048 + row * 64 + ((fch ^ ((row >> 1) & 3)) * 16);
+              cp_async16(ybuf + off, p.bwd.y + fp * p.bwd.ldy + cb + fch * 8);
+              if (E::G2) cp_async16(gbuf + off, p.bwd.g2 + fp * p.bwd.ldg2 + p.bwd.offg2 + cb + fch * 8);
+            }
+          }
+          cp_async_commit();
+        };
+        if (E::BWD) fetch(half * 32, nchunk & 1u);  // the first chunk's operands travel while the tile's MMAs are still running
         mbar_wait(&tmem_full_bar[buf], (uint32_t)((lt >> 1) & 1));
         tc_fence_after();
         for (int cc = half * 32; cc < p.BN; cc += 64, ++nchunk) {
@@ -733,8 +729,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tmem_ld_32x32(taddr + cc, v);
           const uint32_t slot = nchunk & 1u;
           if (E::BWD) {
-            if (cc + 64 < p.BN) fetch(c, cc + 64, slot ^ 1u, true);  // next chunk of this tile
-            else fetch(decode_tile<PAIR>(p, t + tile_step, rank), half * 32, slot ^ 1u, t + tile_step < p.num_tiles);  // first chunk of the next tile
+            fetch(cc + 64, slot ^ 1u);
             cp_async_wait<1>();  // this chunk's group (the next chunk's may still be in flight)
           }
           if (lane == 0) tma_store_wait_read();  // the previous store has read the staging tile
