@@ -290,7 +290,7 @@ def run_b200(args):
     G = networks.get_network("generator", "unet").to(dev).train()  # reference default: dropout ON
     D = networks.PatchGANDiscriminator(sigmoid=(kind != "wgan"), imagedim=R).to(dev).train()
     tr = InpaintingTrainer(kind, G, D, recon=recon, distributed=(world > 1 and not infer), bucket_mb=args.bucket_mb, graph=not args.no_graph, rank=rank,
-                           comm_sms=args.comm_sms)
+                           comm_sms=args.comm_sms, wire_bf16=(None if args.grad_wire is None else args.grad_wire == "bf16"))
 
     def sync_all():
         torch.cuda.synchronize()
@@ -499,6 +499,7 @@ def run_b200(args):
                    "recipe": args.recipe, "res": R, "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                    "dropout": not infer, "l2": "no flush: one step streams several GB of activations/gradients, far larger than the 126 MB L2",
                    "bn": "running statistics (eval)" if infer else "per-replica batch statistics", "bucket_mb": args.bucket_mb,
+                   "grad_wire": ("bf16" if getattr(tr, "wire_bf16", False) else "fp32") if world > 1 else None,
                    "comm_sms": (args.comm_sms if args.comm_sms is not None else int(os.environ.get("B200_COMM_SMS", "0"))) if world > 1 else 0,
                    "launch": "eager (one ctypes call per kernel)" if (args.no_graph or infer) else "whole step replayed as one CUDA graph"},
         "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
@@ -526,6 +527,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=4, help="images per step of the bounded CPU sample")
     ap.add_argument("--bucket-mb", type=float, default=25.0)
     ap.add_argument("--comm-sms", type=int, default=None, help="SMs kept free for the gradient all-reduces while they are in flight (default: B200_COMM_SMS or 0 = none)")
+    ap.add_argument("--grad-wire", default=None, choices=["fp32", "bf16"], help="dtype of the gradient buckets on the wire (default: B200_GRAD_WIRE or fp32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the short D-only / inference measurements of the default run")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying the captured step graph")

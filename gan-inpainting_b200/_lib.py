@@ -63,6 +63,7 @@ SIGNATURES = {
     "b200_step_inc": [P, S],
     "b200_adam_step": [P, P, P, P, L, F, F, F, F, P, S],
     "b200_clamp": [P, L, F, F, S],
+    "b200_cast_grads": [P, P, L, I, S],
     "b200_absmean": [P, P, I, P, S],
     # ---- SSIM metric (csrc/ssim.cu)
     "b200_ssim": [P, P, I, I, I, I, POINTER(c_float), I, P, P, S],

@@ -90,6 +90,24 @@ __global__ void __launch_bounds__(256) clamp_kernel(float* __restrict__ p, long 
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) p[i] = fminf(fmaxf(p[i], lo), hi);
 }
 
+// Gradient buckets on the wire in bf16 (optional, data-parallel all-reduce): fp32 -> bf16 before the collective, bf16 -> fp32 after.
+// n % 4 == 0 (the flat gradient buffer aligns every tensor to 4 elements); 128-bit loads / 64-bit stores and vice versa.
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n4) {
+  b200::pdl_enter();
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    reinterpret_cast<uint2*>(dst)[i] = make_uint2(b200::pack_bf16x2(v.x, v.y), b200::pack_bf16x2(v.z, v.w));
+  }
+}
+__global__ void __launch_bounds__(256) cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, long long n4) {
+  b200::pdl_enter();
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    const uint2 u = reinterpret_cast<const uint2*>(src)[i];
+    const float2 a = b200::unpack_bf16x2(u.x), b = b200::unpack_bf16x2(u.y);
+    reinterpret_cast<float4*>(dst)[i] = make_float4(a.x, a.y, b.x, b.y);
+  }
+}
+
 // out[t] = mean |g[off[t] .. off[t+1])|  — one block per tensor (deterministic)
 __global__ void __launch_bounds__(256) absmean_kernel(const float* __restrict__ g, const long long* __restrict__ off, float* __restrict__ out) {
   b200::pdl_enter();
@@ -149,6 +167,19 @@ int b200_adam_step(float* p, const float* g, float* m, float* v, long long n, fl
 
 int b200_clamp(float* p, long long n, float lo, float hi, cudaStream_t stream) {
   B200_LAUNCH((clamp_kernel), opt_grid(n * 4), 256, 0, stream, p, n, lo, hi);
+  B200_CHECK_LAUNCH();
+  return B200_OK;
+}
+
+// to_bf16 != 0: dst (bf16) = src (fp32); else dst (fp32) = src (bf16).  n elements, n % 4 == 0, both pointers 16-byte aligned.
+int b200_cast_grads(const void* src, void* dst, long long n, int to_bf16, cudaStream_t stream) {
+  if (n < 0 || (n & 3)) {
+    b200_set_error("cast_grads: n must be a multiple of 4");
+    return B200_ERR_ARG;
+  }
+  if (n == 0) return B200_OK;
+  if (to_bf16) B200_LAUNCH((cast_f32_bf16_kernel), opt_grid(n * 4), 256, 0, stream, (const float*)src, (__nv_bfloat16*)dst, n / 4);
+  else B200_LAUNCH((cast_bf16_f32_kernel), opt_grid(n * 4), 256, 0, stream, (const __nv_bfloat16*)src, (float*)dst, n / 4);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

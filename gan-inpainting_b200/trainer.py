@@ -45,7 +45,7 @@ class GradBucketer:
     """Bucketed, overlapped gradient all-reduce over a flat gradient buffer whose tensors complete in descending
     address order during backward (decoder outermost..innermost, then encoder innermost..outermost)."""
 
-    def __init__(self, group: optim.FlatGroup, bucket_mb: float = 25.0, process_group=None, comm_sms: int = 0):
+    def __init__(self, group: optim.FlatGroup, bucket_mb: float = 25.0, process_group=None, comm_sms: int = 0, wire_bf16: bool = False):
         import torch.distributed as dist
 
         self.dist = dist
@@ -56,6 +56,10 @@ class GradBucketer:
         # launched on 148 - comm_sms SMs from the first bucket until finish(), so that NCCL's CTAs never hold an SM a persistent
         # CTA was counting on (a late-starting CTA stretches its whole launch — the 0.4-0.7 ms a step lost at 2-8 GPUs in round 1)
         self.comm_sms = int(comm_sms)
+        # wire_bf16: the buckets travel as bf16 (cast kernels on the communication stream before / after the collective): half the
+        # NVLink bytes and half the time NCCL's CTAs compete with the backward GEMMs; the averaged gradient then carries one bf16
+        # rounding (rel 2^-9 per element) — the same storage precision as every activation gradient of the step
+        self.wire = torch.empty(group.numel, dtype=torch.bfloat16, device=group.grads.device) if (wire_bf16 and group.grads.is_cuda) else None
         self.bucket_elems = max(1, int(bucket_mb * (1 << 20) / 4))
         self.cuda = group.grads.is_cuda
         self.comm = torch.cuda.Stream() if self.cuda else None
@@ -93,7 +97,14 @@ class GradBucketer:
             ev.record(torch.cuda.current_stream())
             with torch.cuda.stream(self.comm):
                 self.comm.wait_event(ev)
-                self._reduce(bucket)
+                if self.wire is not None:
+                    w = self.wire[lo : self.hi]
+                    cs = ctypes_ptr(self.group.grads, lo), ctypes_ptr(self.wire, lo)
+                    call("b200_cast_grads", cs[0], cs[1], self.hi - lo, 1, stream())
+                    self._reduce(w)
+                    call("b200_cast_grads", cs[1], cs[0], self.hi - lo, 0, stream())
+                else:
+                    self._reduce(bucket)
         else:
             self._reduce(bucket)
         self.hi = lo
@@ -114,7 +125,7 @@ class GradBucketer:
 class InpaintingTrainer:
     def __init__(self, recipe: str, net_G, net_D, net_D_local=None, recon: str = "l1", lambdas=(300.0, 300.0), clip: float = 0.01,
                  distributed: bool = False, bucket_mb: float = 25.0, log_grad_means: bool = False, graph: bool = False, rank: Optional[int] = None,
-                 comm_sms: Optional[int] = None, bucket_mb_d: float = 4.0):
+                 comm_sms: Optional[int] = None, bucket_mb_d: float = 4.0, wire_bf16: Optional[bool] = None):
         if recipe not in ("wgan", "minimax", "global_local"):
             raise ValueError(recipe)
         if recipe == "global_local" and net_D_local is None:
@@ -155,12 +166,16 @@ class InpaintingTrainer:
             self.rank = dist.get_rank()
             if comm_sms is None:
                 comm_sms = int(os.environ.get("B200_COMM_SMS", "0"))
+            if wire_bf16 is None:
+                wire_bf16 = os.environ.get("B200_GRAD_WIRE", "fp32").lower() == "bf16"
+            self.wire_bf16 = bool(wire_bf16)
             for fg in (self.fG, self.fD, self.fDl):
                 if fg is not None:
                     dist.broadcast(fg.params, src=0)
                     # the discriminators' 11 MB of gradients use small buckets: their all-reduce then overlaps the rest of the D
                     # backward pass instead of starting after it
-                    self.buckets[id(fg)] = GradBucketer(fg, bucket_mb if fg is self.fG else min(bucket_mb, bucket_mb_d), comm_sms=comm_sms)
+                    self.buckets[id(fg)] = GradBucketer(fg, bucket_mb if fg is self.fG else min(bucket_mb, bucket_mb_d), comm_sms=comm_sms,
+                                                        wire_bf16=self.wire_bf16)
             for net in (net_G, net_D, net_D_local):
                 if net is not None:
                     for b in net.buffers():

@@ -211,6 +211,9 @@ int b200_step_inc(int* step_count, b200_stream_t stream);
 int b200_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps, const int* step_count,
                    b200_stream_t stream);
 int b200_clamp(float* p, long long n, float lo, float hi, b200_stream_t stream);
+/* Gradient buckets on the wire in bf16 (data-parallel all-reduce, optional; the reference is single-GPU):
+ * to_bf16 != 0: dst (bf16) = src (fp32), else dst (fp32) = src (bf16).  n % 4 == 0, 16-byte aligned pointers. */
+int b200_cast_grads(const void* src, void* dst, long long n, int to_bf16, b200_stream_t stream);
 /* out[t] = mean |g[offsets[t] .. offsets[t+1])|, t < ntensors (offsets: int64[ntensors+1]) */
 int b200_absmean(const float* g, const long long* offsets, int ntensors, float* out, b200_stream_t stream);
 

@@ -1,9 +1,7 @@
 #!/bin/bash
-# One gpurun call of round 2 (kept for reproducibility): full GPU suite incl. the headline-shape parity tests, parity table, bench, launch list.
+# One gpurun --gpus 2 call of round 2 (kept for reproducibility): gradient buckets on the wire in fp32 vs bf16.
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_full.log 2>&1; tail -5 gpurun_out/pytest_gpu_full.log
-python -m tests.parity_report --out gpurun_out/parity_r2.json > gpurun_out/parity.log 2>&1; tail -2 gpurun_out/parity.log | cut -c1-300
-python bench.py --steps 30 --warmup 5 > gpurun_out/bench_pf.json 2> gpurun_out/bench_pf.err; cut -c1-260 gpurun_out/bench_pf.json; tail -2 gpurun_out/bench_pf.err
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 1300 --csv --log-file gpurun_out/launches_pf.csv \
-  python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-graph --no-also > gpurun_out/ncu.log 2>&1
-tail -1 gpurun_out/ncu.log | cut -c 1-200
+python bench.py --gpus 2 --steps 30 --warmup 5 > gpurun_out/b2_fp32.json 2> gpurun_out/b2_fp32.err; cut -c1-240 gpurun_out/b2_fp32.json
+python bench.py --gpus 2 --steps 30 --warmup 5 --grad-wire bf16 > gpurun_out/b2_bf16.json 2> gpurun_out/b2_bf16.err; cut -c1-240 gpurun_out/b2_bf16.json; tail -2 gpurun_out/b2_bf16.err
+B200_GRAD_WIRE=bf16 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29612 tests/ddp_oracle_check.py > gpurun_out/ddp_oracle_check_bf16.log 2>&1; tail -1 gpurun_out/ddp_oracle_check_bf16.log
+python bench.py --gpus 2 --steps 30 --warmup 5 --grad-wire bf16 --bucket-mb 50 > gpurun_out/b2_bf16_b50.json 2> gpurun_out/b2_bf16_b50.err; cut -c1-240 gpurun_out/b2_bf16_b50.json
