@@ -1,7 +1,11 @@
 #!/bin/bash
-# One gpurun --gpus 2 call of round 2 (kept for reproducibility): gradient buckets on the wire in fp32 vs bf16.
+# One gpurun call of round 2 (kept for reproducibility): final evidence — GPU suite, smoke, bench line, ncu launch list, ncu --set full of the top kernel.
 mkdir -p gpurun_out
-python bench.py --gpus 2 --steps 30 --warmup 5 > gpurun_out/b2_fp32.json 2> gpurun_out/b2_fp32.err; cut -c1-240 gpurun_out/b2_fp32.json
-python bench.py --gpus 2 --steps 30 --warmup 5 --grad-wire bf16 > gpurun_out/b2_bf16.json 2> gpurun_out/b2_bf16.err; cut -c1-240 gpurun_out/b2_bf16.json; tail -2 gpurun_out/b2_bf16.err
-B200_GRAD_WIRE=bf16 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29612 tests/ddp_oracle_check.py > gpurun_out/ddp_oracle_check_bf16.log 2>&1; tail -1 gpurun_out/ddp_oracle_check_bf16.log
-python bench.py --gpus 2 --steps 30 --warmup 5 --grad-wire bf16 --bucket-mb 50 > gpurun_out/b2_bf16_b50.json 2> gpurun_out/b2_bf16_b50.err; cut -c1-240 gpurun_out/b2_bf16_b50.json
+python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_gpu.log 2>&1; tail -3 gpurun_out/r2_pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_smoke.log 2>&1; tail -1 gpurun_out/r2_smoke.log | cut -c1-400
+python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err; cut -c1-200 gpurun_out/r2_bench_n1.json; tail -2 gpurun_out/r2_bench_n1.err
+python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/r2_bench_reference.json 2> gpurun_out/r2_bench_reference.err; cut -c1-200 gpurun_out/r2_bench_reference.json
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 1300 --csv --log-file gpurun_out/r2_bench_launches_ncu.csv \
+  python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-graph --no-also > gpurun_out/ncu.log 2>&1
+python tools/one_layer.py convt 64 32 512 128 3 1 > gpurun_out/ol.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:igemm -s 3 -c 1 -f -o gpurun_out/r2_prof_u3 python tools/one_layer.py convt 64 32 512 128 3 1 > gpurun_out/ncu_u3.log 2>&1
+tail -1 gpurun_out/ncu_u3.log
