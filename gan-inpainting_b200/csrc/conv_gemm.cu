@@ -96,10 +96,14 @@ constexpr int kThreads = 64 + 32 * kEpiWarps;      // warp 0 = TMA, warp 1 = MMA
 constexpr int kATileBytes = 128 * 128;  // 128 rows x 64 bf16 (K-major) or 2 x (64 px x 64 ch) (MN-major)
 // window operand staging: a pixel tile is 8 wide x 16 high; its halo window is 9 x 17 pixels x 64 channels = 153 rows of 128 bytes
 constexpr int kWinTw = 8, kWinTh = 16;
-constexpr int kWinRows = (kWinTw + 1) * (kWinTh + 1);
-constexpr int kWinBytes = kWinRows * 128;              // 19584
-constexpr int kWinSlotBytes = 20 * 1024;               // slot pitch (1024-byte aligned: SWIZZLE_128B)
-constexpr int kWinSbo = (kWinTw + 1) * 128;            // byte distance of consecutive 8-pixel row groups inside a window
+// WIN = 1: one parity plane (conv) / one phase (convT): halo of 1 pixel on one side per axis -> 17 x 9 window, 4 taps.
+// WIN = 4: ALL FOUR phases of a transposed convolution from one window: halo of 1 pixel on both sides -> 18 x 10 window, 16
+//          (phase, tap) descriptors, four TMEM accumulators (N <= 64).  0: legacy (one TMA box per tap).
+__host__ __device__ constexpr int win_pitch(int win) { return win == 4 ? kWinTw + 2 : kWinTw + 1; }                  // pixel rows per window row
+__host__ __device__ constexpr int win_bytes(int win) { return win_pitch(win) * (win == 4 ? kWinTh + 2 : kWinTh + 1) * 128; }  // 23040 / 19584
+__host__ __device__ constexpr int win_slot_bytes(int win) { return win == 4 ? 24 * 1024 : 20 * 1024; }              // slot pitch (1024-aligned)
+__host__ __device__ constexpr int win_sbo(int win) { return win_pitch(win) * 128; }                                 // byte distance of 8-pixel row groups
+__host__ __device__ constexpr int win_taps(int win) { return win == 4 ? 16 : 4; }                                   // descriptors per window
 constexpr int kBarrierBytes = 1024;                    // mbarriers + TMEM pointer behind the operand rings (keeps the epilogue tiles 1024-byte aligned)
 constexpr int kStatTileBytes = 4096 + 2048;           // per epilogue warp: 32 x 32 fp32 of dz + 32 x 32 bf16 of y (forward: 32 x 32 bf16 only)
 
@@ -368,7 +372,7 @@ __device__ __forceinline__ void column_sums_f32(const uint8_t* ztile, const uint
 // core applies the 128-byte swizzle to absolute shared-memory addresses, so a descriptor may start at any 128-byte row of a
 // TMA-written window (tools/umma_probe.cu checks exactly this on the hardware).  Activation bytes per MMA drop 3.3x; the
 // weights ride in their own ring (`tpb` taps per stage) because the two operands now arrive at different rates.
-template <class E, bool PAIR, bool WIN>
+template <class E, bool PAIR, int WIN>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
              const __grid_constant__ CUtensorMap tmZ, const IGemmParams p) {
@@ -379,7 +383,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int b_bytes = (PAIR ? p.BN / 2 : p.BN) * 128;  // per CTA
   // WIN: [sa window slots][stages weight stages of tpb boxes]; else [stages of kpb (A tile + B tile)]
   const int stage_bytes = WIN ? p.tpb * b_bytes : p.kpb * (kATileBytes + b_bytes);
-  uint8_t* smem_b = smem + (WIN ? p.sa * kWinSlotBytes : 0);
+  uint8_t* smem_b = smem + (WIN ? p.sa * win_slot_bytes(WIN) : 0);
   const int rank = PAIR ? (int)(blockIdx.x & 1u) : 0;  // == %cluster_ctarank for 2 x 1 x 1 clusters; read from blockIdx it is provably warp-uniform (the MMA / TMA loops then compile to the uniform datapath)
   const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // first work item of this CTA (pair)
   const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -438,7 +442,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const uint32_t tmem_base = role_begin();
     if (WIN) {
     // ===================== TMA producer, window operand staging =====================
-    const uint32_t a_tx = (uint32_t)kWinBytes * (PAIR ? 2u : 1u);
+    const uint32_t a_tx = (uint32_t)win_bytes(WIN) * (PAIR ? 2u : 1u);
     const uint32_t b_tx = (uint32_t)stage_bytes * (PAIR ? 2u : 1u);
     const int nB = PAIR ? rank * (p.BN / 2) : 0;
     const int planes = (p.mode == MODE_CONV_S2) ? 4 : 1;
@@ -452,8 +456,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int cc = 0; cc < p.cpt; ++cc) {
           mbar_wait(&emptyA_bar[sa], para ^ 1u);
           if (!PAIR || rank == 0) mbar_arrive_expect_tx_w(&fullA_bar[sa], a_tx);
-          uint8_t* sW = smem + sa * kWinSlotBytes;
-          if (p.mode == MODE_CONV_S2) {
+          uint8_t* sW = smem + sa * win_slot_bytes(WIN);
+          if (WIN == 4) {
+            // all four phases: input pixels (i - 1 .. i + 16, j - 1 .. j + 8) of the tile
+            if (PAIR) tma2_load_4d_w(sW, &tmA, &fullA_bar[sa], cc * 64, c.w0 - 1, c.h0 - 1, c.b0);
+            else tma_load_4d_w(sW, &tmA, &fullA_bar[sa], cc * 64, c.w0 - 1, c.h0 - 1, c.b0);
+          } else if (p.mode == MODE_CONV_S2) {
             // plane (pr, pc) holds input rows 2*h2 + pr: taps kh = 2*eh + 1 - pr read h2 = oh + eh - pr, so the window starts at h0 - pr
             if (PAIR) tma2_load_5d_w(sW, &tmA, &fullA_bar[sa], pc * p.C_k + cc * 64, c.w0 - pc, pr, c.h0 - pr, c.b0);
             else tma_load_5d_w(sW, &tmA, &fullA_bar[sa], pc * p.C_k + cc * 64, c.w0 - pc, pr, c.h0 - pr, c.b0);
@@ -462,14 +470,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (PAIR) tma2_load_4d_w(sW, &tmA, &fullA_bar[sa], cc * 64, c.w0 + ph_q - 1, c.h0 + ph_p - 1, c.b0);
             else tma_load_4d_w(sW, &tmA, &fullA_bar[sa], cc * 64, c.w0 + ph_q - 1, c.h0 + ph_p - 1, c.b0);
           }
-          for (int tg = 0; tg < 4; tg += p.tpb) {
+          for (int tg = 0; tg < win_taps(WIN); tg += p.tpb) {
             mbar_wait(&empty_bar[sb], parb ^ 1u);
             if (!PAIR || rank == 0) mbar_arrive_expect_tx_w(&full_bar[sb], b_tx);
             for (int u = 0; u < p.tpb; ++u) {
-              const int j = tg + u, eh = j >> 1, ew = j & 1;
+              const int j = tg + u, eh = (j >> 1) & 1, ew = j & 1;
               uint8_t* sB = smem_b + sb * stage_bytes + u * b_bytes;
               int kb, row;
-              if (p.mode == MODE_CONV_S2) {
+              if (WIN == 4) {  // j = phase * 4 + tap
+                kb = ((j & 3) << p.cpt_sh) + cc;
+                row = (j >> 2) * p.Cout + c.n0 + nB;
+              } else if (p.mode == MODE_CONV_S2) {
                 const int kh = 2 * eh + 1 - pr, kw = 2 * ew + 1 - pc;
                 kb = ((kh * 4 + kw) << p.cpt_sh) + cc;
                 row = c.n0 + nB;
@@ -572,29 +583,35 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (rank == 0) {
       const uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, p.BN, 0, 0);
       const int nwin = ((p.mode == MODE_CONV_S2) ? 4 : 1) * p.cpt;
+      const int acc_cols = (WIN == 4 ? 4 : 1) * p.BN;  // TMEM columns of one accumulator buffer
       int sa = 0, sb = 0, lt = 0;
       uint32_t para = 0, parb = 0;
       for (int t = tile0; t < p.num_tiles; t += tile_step, ++lt) {
         const int buf = lt & 1;
         mbar_wait(&tmem_empty_bar[buf], (uint32_t)(((lt >> 1) & 1) ^ 1));  // the epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t d_addr = tmem_base + (uint32_t)(buf * p.BN);
+        const uint32_t d_addr = tmem_base + (uint32_t)(buf * acc_cols);
         for (int wi = 0; wi < nwin; ++wi) {
           mbar_wait(&fullA_bar[sa], para);
           tc_fence_after();
-          const uint32_t w_lo = desc_lo(smem_u32(smem + sa * kWinSlotBytes), 16u);
-          for (int tg = 0; tg < 4; tg += p.tpb) {
+          const uint32_t w_lo = desc_lo(smem_u32(smem + sa * win_slot_bytes(WIN)), 16u);
+          for (int tg = 0; tg < win_taps(WIN); tg += p.tpb) {
             mbar_wait(&full_bar[sb], parb);
             tc_fence_after();
             const uint32_t b_lo0 = desc_lo(smem_u32(smem_b + sb * stage_bytes), 16u);
             for (int u = 0; u < p.tpb; ++u) {
               const int j = tg + u;
-              const uint32_t a_lo = w_lo + (uint32_t)(((j >> 1) * (kWinTw + 1) + (j & 1)) * 8);  // tap (eh, ew) = window row eh * 9 + ew (128 B = 8 units)
+              // WIN 1: tap (eh, ew) = window row eh * 9 + ew.  WIN 4: phase (p, q), tap (a, b) = window row (p + a) * 10 + (q + b), accumulator
+              // of phase 2p + q (one window row = 128 bytes = 8 descriptor units)
+              const int ph = WIN == 4 ? (j >> 2) : 0, tp = WIN == 4 ? (j & 3) : j;
+              const int wr = WIN == 4 ? ((ph >> 1) + (tp >> 1)) * win_pitch(WIN) + (ph & 1) + (tp & 1) : (tp >> 1) * win_pitch(WIN) + (tp & 1);
+              const uint32_t a_lo = w_lo + (uint32_t)(wr * 8);
               const uint32_t b_lo = b_lo0 + (uint32_t)u * ((uint32_t)b_bytes >> 4);
+              const uint32_t d_ph = d_addr + (uint32_t)(ph * p.BN);
 #pragma unroll
               for (int k = 0; k < 4; ++k)  // K = 16 slices: 32 bytes = 2 descriptor units apart
-                umma_bf16_lo_w<kDescHiSw128 | (kWinSbo >> 4), kDescHiSw128 | (1024 >> 4), PAIR>(d_addr, a_lo + 2 * k, b_lo + 2 * k, idesc,
-                                                                                                   (wi > 0 || j > 0 || k > 0) ? 1u : 0u);
+                umma_bf16_lo_w<kDescHiSw128 | (win_sbo(WIN) >> 4), kDescHiSw128 | (1024 >> 4), PAIR>(d_ph, a_lo + 2 * k, b_lo + 2 * k, idesc,
+                                                                                                        (wi > 0 || tp > 0 || k > 0) ? 1u : 0u);
             }
             if (PAIR) umma_commit_2cta_w(&empty_bar[sb]);
             else umma_commit_w(&empty_bar[sb]);
@@ -695,25 +712,25 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int frow = lane >> 2, fch = lane & 3;  // cp.async mapping: pixel of the image row, 16-byte channel chunk
       const bool convt = (p.mode == MODE_CONVT);
       uint32_t nchunk = 0;
+      constexpr int NPH = WIN == 4 ? 4 : 1;  // phases of a transposed convolution handled per tile
+      const int acc_cols = NPH * p.BN;       // TMEM columns of one accumulator buffer
       for (int t = tile0; t < p.num_tiles; t += tile_step, ++lt) {
         const TileCoord c = decode_tile<PAIR>(p, t, rank);
         const int buf = lt & 1;
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.BN);
-        const int ph_p = c.phase >> 1, ph_q = c.phase & 1;
-        auto pixel = [&](int hl, int wl) -> size_t {
+        auto pixel = [&](int phase, int hl, int wl) -> size_t {
           if (!convt) return ((size_t)c.b0 * p.Hs + (c.h0 + hl)) * p.Ws + (c.w0 + wl);
-          return ((size_t)c.b0 * (2 * p.Hs) + (2 * (c.h0 + hl) + ph_p)) * (size_t)(2 * p.Ws) + (2 * (c.w0 + wl) + ph_q);
+          return ((size_t)c.b0 * (2 * p.Hs) + (2 * (c.h0 + hl) + (phase >> 1))) * (size_t)(2 * p.Ws) + (2 * (c.w0 + wl) + (phase & 1));
         };
-        const size_t pix = pixel(r >> 3, r & 7);  // this lane's own accumulator row
         const int sp = (p.stat_parity == 2) ? (lt & 1) : 0;
         float* st = stat_smem + (sp * 4 + quad) * 2 * p.BN;
-        auto fetch = [&](int cc, uint32_t slot) {  // one cp.async group per call (empty when the chunk needs nothing)
+        // one cp.async group per call (empty when the chunk needs nothing): the y / skip-gradient slices of chunk (phase, cc)
+        auto fetch = [&](int phase, int cc, uint32_t slot, bool live) {
           const int cb = c.n0 + cc - p.bwd.col0;
-          if (cb >= 0 && cc < p.BN) {
+          if (live && cb >= 0 && cc < p.BN) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int row = 8 * i + frow;
-              const size_t fp = pixel(hq + i, frow);
+              const size_t fp = pixel(phase, hq + i, frow);
               const int off = (int)slot * 2048 + row * 64 + ((fch ^ ((row >> 1) & 3)) * 16);
               cp_async16(ybuf + off, p.bwd.y + fp * p.bwd.ldy + cb + fch * 8);
               if (E::G2) cp_async16(gbuf + off, p.bwd.g2 + fp * p.bwd.ldg2 + p.bwd.offg2 + cb + fch * 8);
@@ -721,15 +738,24 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
           cp_async_commit();
         };
-        if (E::BWD) fetch(half * 32, nchunk & 1u);  // the first chunk's operands travel while the tile's MMAs are still running
+        const int phase0 = WIN == 4 ? 0 : c.phase;
+        if (E::BWD) fetch(phase0, half * 32, nchunk & 1u, true);  // the first chunk's operands travel while the tile's MMAs are still running
         mbar_wait(&tmem_full_bar[buf], (uint32_t)((lt >> 1) & 1));
         tc_fence_after();
+#pragma unroll 1
+        for (int ph = 0; ph < NPH; ++ph) {
+        const int phase = WIN == 4 ? ph : c.phase;
+        const int ph_p = phase >> 1, ph_q = phase & 1;
+        const size_t pix = pixel(phase, r >> 3, r & 7);  // this lane's own accumulator row
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * acc_cols + ph * p.BN);
+        const bool first_ph = (ph == 0);
         for (int cc = half * 32; cc < p.BN; cc += 64, ++nchunk) {
           uint32_t v[32];
           tmem_ld_32x32(taddr + cc, v);
           const uint32_t slot = nchunk & 1u;
           if (E::BWD) {
-            fetch(cc + 64, slot ^ 1u);
+            if (cc + 64 < p.BN) fetch(phase, cc + 64, slot ^ 1u, true);         // next chunk of this phase
+            else fetch(phase + 1, half * 32, slot ^ 1u, ph + 1 < NPH);         // first chunk of the next phase of this tile (if any)
             cp_async_wait<1>();  // this chunk's group (the next chunk's may still be in flight)
           }
           if (lane == 0) tma_store_wait_read();  // the previous store has read the staging tile
@@ -782,8 +808,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (lane < 8) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                st[cc + lane * 4 + k] = cs[k];
-                st[p.BN + cc + lane * 4 + k] = cq[k];
+                float* s0 = st + cc + lane * 4 + k;
+                s0[0] = first_ph ? cs[k] : s0[0] + cs[k];
+                s0[p.BN] = first_ph ? cq[k] : s0[p.BN] + cq[k];
               }
             }
           } else {
@@ -799,21 +826,25 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               tma_store_commit();
             }
             if (E::STATS && E::BWD) {  // unfused columns of a fused-backward GEMM carry no statistics
-              st[cc + lane] = 0.f;
-              st[p.BN + cc + lane] = 0.f;
+              if (first_ph) {
+                st[cc + lane] = 0.f;
+                st[p.BN + cc + lane] = 0.f;
+              }
             } else if (E::STATS) {     // per-channel sums of the values as stored
               float cs[8], cq[8];
               column_sums_bf16(zbuf, lane, cs, cq);
               if (lane < 4) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                  st[cc + lane * 8 + k] = cs[k];
-                  st[p.BN + cc + lane * 8 + k] = cq[k];
+                  float* s0 = st + cc + lane * 8 + k;
+                  s0[0] = first_ph ? cs[k] : s0[0] + cs[k];
+                  s0[p.BN] = first_ph ? cq[k] : s0[p.BN] + cq[k];
                 }
               }
             }
           }
           __syncwarp();  // every lane is done with the staging tiles of this chunk
+        }
         }
         tc_fence_before();  // the accumulator has been read: hand the TMEM buffer back before the cross-warp statistics
         __syncwarp();
@@ -1140,7 +1171,7 @@ static int ilog2(int v) {
 struct StoreMaps {
   CUtensorMap out, dz;  // window-mode epilogue: bf16 output tensor, fp32 dz tensor of a fused BatchNorm backward (zeroed when unused)
 };
-template <class E, bool WIN>
+template <class E, int WIN>
 static void launch_variant_w(const CUtensorMap& a, const CUtensorMap& b, const StoreMaps& sm, const IGemmParams& p, int grid, size_t smem,
                              cudaStream_t stream) {
   if (p.pair) {
@@ -1182,8 +1213,9 @@ static void launch_variant_w(const CUtensorMap& a, const CUtensorMap& b, const S
 template <class E>
 static void launch_variant(const CUtensorMap& a, const CUtensorMap& b, const StoreMaps& sm, const IGemmParams& p, int grid, size_t smem,
                            cudaStream_t stream) {
-  if (p.win) launch_variant_w<E, true>(a, b, sm, p, grid, smem, stream);
-  else launch_variant_w<E, false>(a, b, sm, p, grid, smem, stream);
+  if (p.win == 4) launch_variant_w<E, 4>(a, b, sm, p, grid, smem, stream);
+  else if (p.win) launch_variant_w<E, 1>(a, b, sm, p, grid, smem, stream);
+  else launch_variant_w<E, 0>(a, b, sm, p, grid, smem, stream);
 }
 
 // Window operand staging applies to the fprop / dgrad modes when an image holds at least one 16 x 8-pixel tile and K is not
@@ -1256,13 +1288,14 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const StoreMaps& s
     p.tpb = b_bytes * 4 <= 32 * 1024 ? 4 : (b_bytes * 2 <= 32 * 1024 ? 2 : 1);
     if (tpb_env == 1 || tpb_env == 2 || tpb_env == 4) p.tpb = tpb_env;
     stage_bytes = p.tpb * b_bytes;
-    const int per_window = (4 / p.tpb) * stage_bytes;  // weight bytes one window consumes
-    auto fits = [&](int ex, int sa) { return (227 * 1024 - ex - sa * kWinSlotBytes) / stage_bytes; };
+    const int taps = win_taps(p.win), slot = win_slot_bytes(p.win);
+    const int per_window = (taps / p.tpb) * stage_bytes;  // weight bytes one window consumes
+    auto fits = [&](int ex, int sa) { return (227 * 1024 - ex - sa * slot) / stage_bytes; };
     extra = layout(2);
     if (has_stats && fits(extra, 3) * stage_bytes < 2 * per_window) extra = layout(1);
-    p.sa = sa_env > 0 ? sa_env : (fits(extra, 4) * stage_bytes >= 2 * per_window ? 4 : 3);
+    p.sa = sa_env > 0 ? sa_env : ((p.win != 4 && fits(extra, 4) * stage_bytes >= 2 * per_window) ? 4 : 3);
     while (p.sa > 2 && fits(extra, p.sa) < 2) --p.sa;
-    ring_a = p.sa * kWinSlotBytes;
+    ring_a = p.sa * slot;
     p.stages = fits(extra, p.sa);
     if (p.stages > 12) p.stages = 12;
     if (2 * p.sa + 2 * p.stages + 4 > (kBarrierBytes - 16) / 8) {
@@ -1287,7 +1320,7 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const StoreMaps& s
     return B200_ERR_ARG;
   }
   uint32_t cols = 32;
-  while ((int)cols < 2 * p.BN) cols <<= 1;
+  while ((int)cols < 2 * (p.win == 4 ? 4 : 1) * p.BN) cols <<= 1;  // two accumulator buffers (of four phases each in WIN 4)
   p.tmem_cols = cols;
   const size_t smem = (size_t)p.stages * stage_bytes + ring_a + extra;
   const int sms = b200_sm_limit();  // all 148, or fewer while a trainer keeps SMs free for gradient all-reduces
@@ -1467,6 +1500,11 @@ int b200_convt_s2_gemm(const void* z, int B, int Hi, int Wi, int Cin, int ldz, c
   p.C_k = Cin;
   p.cpt = Cin / 64;
   p.kb_per_tile = p.kb_total = 4 * p.cpt;
+  // narrow layers (N <= 64: the last decoder level, the data gradients into 64-channel layers): all four phases per tile from ONE
+  // 18 x 10 window into four TMEM accumulators — a 256 x 64 pair tile is otherwise bound by the L2 -> SM operand stream
+  // (B200_WIN4=0: one phase per work item)
+  static const bool win4_enabled = env_int("B200_WIN4", 1) != 0;
+  const bool win4 = p.win && win4_enabled && pick_bn(Cout, bn_hint) <= 64;
   p.BN = pick_bn(Cout, bn_hint);
   if (Cout % p.BN || p.BN % 32 || p.BN > 256 || (stats && Cout > 1024)) {
     b200_set_error("convt_s2_gemm: bad N tile");
@@ -1477,9 +1515,10 @@ int b200_convt_s2_gemm(const void* z, int B, int Hi, int Wi, int Cin, int ldz, c
   p.out = y;
   p.stages = stages;
   p.n_tiles = Cout / p.BN;
-  p.phases = 4;
+  p.phases = win4 ? 1 : 4;
+  if (win4) p.win = 4;
   p.m_tiles = 1;
-  p.num_tiles = p.num_ptiles * p.n_tiles * 4;
+  p.num_tiles = p.num_ptiles * p.n_tiles * p.phases;
   p.stats = stats;
   int rc;
   if ((rc = set_bwd(p, bwd, Cout, "convt_s2_gemm"))) return rc;
@@ -1487,7 +1526,8 @@ int b200_convt_s2_gemm(const void* z, int B, int Hi, int Wi, int Cin, int ldz, c
   p.pair = want_pair(p, ksplit) ? 1 : 0;
   if (p.pair) p.num_tiles /= 2;
   CUtensorMap ta, tb;
-  if ((rc = map_nhwc(&ta, z, B, Hi, Wi, Cin, ldz, p.tw + p.win, p.th + p.win, p.nb))) return rc;
+  const int halo = p.win == 4 ? 2 : (p.win ? 1 : 0);
+  if ((rc = map_nhwc(&ta, z, B, Hi, Wi, Cin, ldz, p.tw + halo, p.th + halo, p.nb))) return rc;
   if ((rc = map_weights(&tb, wpk, 4 * Cout, 4 * Cin, p.pair ? p.BN / 2 : p.BN))) return rc;
   StoreMaps sm{};
   if (p.win) {

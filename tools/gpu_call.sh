@@ -1,11 +1,13 @@
 #!/bin/bash
-# One gpurun call of round 2 (kept for reproducibility): final evidence — GPU suite, smoke, bench line, ncu launch list, ncu --set full of the top kernel.
+# One gpurun call of round 2 (kept for reproducibility): 4-phase window mode (WIN 4) validation and A/B.
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_gpu.log 2>&1; tail -3 gpurun_out/r2_pytest_gpu.log
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_smoke.log 2>&1; tail -1 gpurun_out/r2_smoke.log | cut -c1-400
-python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err; cut -c1-200 gpurun_out/r2_bench_n1.json; tail -2 gpurun_out/r2_bench_n1.err
-python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/r2_bench_reference.json 2> gpurun_out/r2_bench_reference.err; cut -c1-200 gpurun_out/r2_bench_reference.json
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 1300 --csv --log-file gpurun_out/r2_bench_launches_ncu.csv \
-  python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-graph --no-also > gpurun_out/ncu.log 2>&1
-python tools/one_layer.py convt 64 32 512 128 3 1 > gpurun_out/ol.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:igemm -s 3 -c 1 -f -o gpurun_out/r2_prof_u3 python tools/one_layer.py convt 64 32 512 128 3 1 > gpurun_out/ncu_u3.log 2>&1
-tail -1 gpurun_out/ncu_u3.log
+python -m pytest tests -m gpu -x -q --deselect tests/test_headline_gpu.py > gpurun_out/pytest_gpu.log 2>&1; tail -6 gpurun_out/pytest_gpu.log
+for w4 in 1 0; do
+B200_WIN4=$w4 python tools/one_layer.py convt 64 64 256 64 10 0
+B200_WIN4=$w4 python tools/one_layer.py convt 64 64 256 64 10 1
+B200_WIN4=$w4 python tools/one_layer.py convt 64 64 128 64 10 0
+B200_WIN4=$w4 python tools/one_layer.py convt 128 128 256 64 5 0
+done > gpurun_out/one_layer_w4.log 2>&1; cat gpurun_out/one_layer_w4.log
+python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-also > gpurun_out/bench_w4.json 2> gpurun_out/bench_w4.err; cut -c1-200 gpurun_out/bench_w4.json; tail -2 gpurun_out/bench_w4.err
+B200_WIN4=0 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-also > gpurun_out/bench_w4off.json 2> gpurun_out/bench_w4off.err; cut -c1-200 gpurun_out/bench_w4off.json
+python bench.py --recipe inference --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_inf_w4.json 2> gpurun_out/bench_inf_w4.err; cut -c1-200 gpurun_out/bench_inf_w4.json
