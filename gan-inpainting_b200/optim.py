@@ -9,6 +9,7 @@ are still handled (one launch per tensor).
 """
 from __future__ import annotations
 
+import weakref
 from typing import Dict, List, Optional
 
 import torch
@@ -40,7 +41,9 @@ class FlatGroup:
             p.data = self.params[o : o + p.numel()].view(p.shape)
             p.grad = self.grads[o : o + p.numel()].view(p.shape)
         self.grad_views = [p.grad for p in ps]
-        _FLAT.update({id(p): self for p in ps})
+        module._b200_flat_group = self  # the module owns its flat group; the registry below only holds weak references
+        ref = weakref.ref(self)
+        _FLAT.update({id(p): ref for p in ps})
 
     def grad_of(self, p) -> torch.Tensor:
         return self.grad_views[self._index(p)]
@@ -54,8 +57,25 @@ class FlatGroup:
     def grad_map(self) -> Dict[int, torch.Tensor]:
         return {id(p): g for p, g in zip(self.members, self.grad_views)}
 
+    def check_alias(self):
+        """The parameters must still BE the views into ``params``: ``net.to(other device / dtype)`` or
+        ``load_state_dict(assign=True)`` replaces ``p.data``, after which the fused optimizer, the WGAN clip and the all-reduce
+        buckets would update a buffer the module no longer reads — training would silently stop.  Cheap (one pointer compare per
+        parameter); re-homes a detached parameter when only its storage moved (same device, dtype and shape), raises otherwise."""
+        esz = self.params.element_size()
+        for p, o in zip(self.members, self.offsets):
+            if p.data_ptr() != self.params.data_ptr() + o * esz:
+                if p.device != self.params.device or p.dtype != self.params.dtype:
+                    raise _lib.B200Error("a flattened parameter was moved to another device / dtype (net.to(...) after flatten_parameters): "
+                                         "re-create the optimizer / trainer after moving the network")
+                view = self.params[o : o + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                _lib.WEIGHT_EPOCH += 1
+
     def rebind_grads(self):
         """Bring ``p.grad`` back to the flat views (after ``zero_grad(set_to_none=True)`` or an autograd re-allocation)."""
+        self.check_alias()
         for p, g in zip(self.members, self.grad_views):
             if p.grad is None:
                 g.zero_()
@@ -80,13 +100,23 @@ class FlatGroup:
         return names, spans
 
 
-_FLAT: Dict[int, FlatGroup] = {}
+_FLAT: Dict[int, "weakref.ref[FlatGroup]"] = {}
+
+
+def _flat_of(p) -> Optional[FlatGroup]:
+    ref = _FLAT.get(id(p))
+    g = ref() if ref is not None else None
+    if g is None or not any(q is p for q in g.members):  # dead group, or a recycled id()
+        return None
+    return g
 
 
 def flatten_parameters(module: torch.nn.Module) -> FlatGroup:
     ps = list(module.parameters())
-    if ps and id(ps[0]) in _FLAT and _FLAT[id(ps[0])].members == ps:
-        return _FLAT[id(ps[0])]
+    g = _flat_of(ps[0]) if ps else None
+    if g is not None and len(g.members) == len(ps) and all(a is b for a, b in zip(g.members, ps)):
+        g.check_alias()
+        return g
     return FlatGroup(module)
 
 
@@ -95,7 +125,7 @@ def _plan(params: List[torch.nn.Parameter]):
     groups, loose, seen = [], [], set()
     ids = {id(p) for p in params}
     for p in params:
-        g = _FLAT.get(id(p))
+        g = _flat_of(p)
         if g is not None and all(id(q) in ids for q in g.members):
             if id(g) not in seen:
                 seen.add(id(g))

@@ -272,3 +272,29 @@ def test_gpu_load_transform_tap_tables_match_the_oracle():
     t = data.GpuLoadTransform(128, "cpu")
     for h, w in [(300, 260), (260, 300), (128, 128), (64, 200)]:
         assert t.output_size(h, w) == preprocess.resize_output_size(h, w, 128)
+
+
+def test_flat_group_detects_and_repairs_a_detached_parameter():
+    """optim.FlatGroup re-homes parameters into one flat buffer; if something replaces ``p.data`` afterwards (``load_state_dict(assign=True)``,
+    a manual ``p.data = ...``) the fused optimizer would update a buffer the module no longer reads.  ``check_alias`` (run by every
+    optimizer step via ``rebind_grads`` and by ``flatten_parameters``) copies the new value back into the flat view and re-binds it."""
+    import gc
+
+    from gan_inpainting_b200 import optim
+
+    lin = torch.nn.Linear(8, 4)
+    fg = optim.flatten_parameters(lin)
+    assert optim.flatten_parameters(lin) is fg and lin.weight.data_ptr() == fg.params.data_ptr()
+    new_w = torch.full((4, 8), 3.0)
+    lin.weight.data = new_w  # detaches the parameter from the flat buffer
+    assert lin.weight.data_ptr() != fg.params.data_ptr()
+    fg.check_alias()
+    assert lin.weight.data_ptr() == fg.params.data_ptr() and float(fg.params[:32].min()) == 3.0
+    fg.params.mul_(2.0)  # what a fused optimizer kernel does: the module must see it
+    assert float(lin.weight.min()) == 6.0
+    # the registry holds the group weakly: dropping the module frees it
+    import weakref
+    r = weakref.ref(fg)
+    del fg, lin
+    gc.collect()
+    assert r() is None
