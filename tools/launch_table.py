@@ -40,7 +40,7 @@ def short(name):
         e = [x.strip() for x in m.group(1).split(",")]
         tag = "".join(("S" if e[0] == "1" else "-", "B" if e[1] == "1" else "-", {"0": "-", "1": "L", "2": "R"}[e[2].strip()], "G" if e[3] == "1" else "-",
                        "N" if e[4] == "1" else "-"))
-        return f"igemm[{tag}{' pair' if m.group(2) == '1' else ''}{' win' if m.group(3) == '1' else ''}]"
+        return f"igemm[{tag}{' pair' if m.group(2) == '1' else ''}{' win' if m.group(3) == '1' else (' win4' if m.group(3) == '4' else '')}]"
     return n.split("<")[0].split("(")[0]
 
 
