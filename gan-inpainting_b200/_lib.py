@@ -67,6 +67,14 @@ SIGNATURES = {
     "b200_absmean": [P, P, I, P, S],
     # ---- SSIM metric (csrc/ssim.cu)
     "b200_ssim": [P, P, I, I, I, I, POINTER(c_float), I, P, P, S],
+    # ---- VGG19 feature losses (csrc/conv_gemm.cu conv3 / gram modes, csrc/vgg.cu)
+    "b200_conv3_gemm": [P, I, I, I, I, I, P, P, I, P, I, I, S],
+    "b200_pack_conv3": [P, I, I, P, S],
+    "b200_conv3_c1_fwd": [P, I, I, I, P, P, I, P, S],
+    "b200_maxpool2": [P, I, I, I, I, P, S],
+    "b200_gram_gemm": [P, I, I, I, I, I, P, S],
+    "b200_sqdiff_bf16": [P, P, L, ctypes.c_double, P, P, I, S],
+    "b200_sqdiff_gram": [P, P, I, I, I, I, F, ctypes.c_double, P, P, I, S],
     # ---- input pipeline: greyscale + resize + ToTensor (csrc/preprocess.cu)
     "b200_preprocess": [P, I, I, I, I, I, I, P, P, P, I, P, P, P, I, P, P, S],
     # ---- total-variation loss (csrc/tv.cu)
@@ -86,6 +94,8 @@ VALUE_FUNCS = {
     "b200_wgrad_c1_blocks": (c_int, []),
     "b200_recon_scratch_floats": (c_int, []),
     "b200_ssim_partials": (c_longlong, [I, I, I, I]),
+    "b200_sqdiff_blocks": (c_int, []),
+    "b200_gram_splits": (c_int, [I, I, I, I]),
 }
 
 

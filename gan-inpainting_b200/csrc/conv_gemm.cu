@@ -25,7 +25,10 @@
 
 namespace b200 {
 
-enum { MODE_CONV_S2 = 0, MODE_CONVT = 1, MODE_WGRAD = 2 };
+//   MODE_CONV3    y[b,h,w,:] = relu(sum_{kh,kw,ci} x[b,h+kh-1,w+kw-1,ci] * W[:,kh,kw,ci] + bias)
+//                 (Conv2d k3 s1 p1 + ReLU: the VGG19 feature extractor of the perceptual / style losses, lib/models/loss.py:49-115,
+//                 networks.py:367-389; window mode only)
+enum { MODE_CONV_S2 = 0, MODE_CONVT = 1, MODE_WGRAD = 2, MODE_CONV3 = 3 };
 
 // Optional backward-of-activation epilogue of the data-gradient GEMMs (mirrors b200_epi_bwd in include/b200_inpaint.h).
 // Output columns >= col0 are gradients w.r.t. act(dropout(bn(y)))[:, col - col0]; the epilogue turns them into the gradient
@@ -84,6 +87,10 @@ struct IGemmParams {
                          // that read it are four shared-memory descriptors into that window instead of four TMA boxes
   int sa;                // window slots of the activation ring (win)
   int tpb;               // filter taps (weight boxes) per stage of the weight ring (win); `stages` counts the weight stages
+  const float* bias;     // MODE_CONV3: per-output-channel bias added before the ReLU of the epilogue
+  int gram;              // MODE_WGRAD without taps: the second operand is read at the SAME pixels as the first (tmB is a plain NHWC map),
+                         // G[cs][cl] = sum_pixels S[pix][cs] * L[pix][cl]; one split per image gives the per-image Gram matrices of
+                         // lib/models/loss.py:117-136
   float* stats;          // optional (fprop modes): per-CTA column sums of the stored bf16 outputs,
                          // [gridDim.x][2][Cout] (sum, sum of squares) for the BatchNorm that follows;
                          // with `bwd`: (sum dz, sum dz*y) of the fused columns instead
@@ -99,16 +106,18 @@ constexpr int kWinTw = 8, kWinTh = 16;
 // WIN = 1: one parity plane (conv) / one phase (convT): halo of 1 pixel on one side per axis -> 17 x 9 window, 4 taps.
 // WIN = 4: ALL FOUR phases of a transposed convolution from one window: halo of 1 pixel on both sides -> 18 x 10 window, 16
 //          (phase, tap) descriptors, four TMEM accumulators (N <= 64).  0: legacy (one TMA box per tap).
-__host__ __device__ constexpr int win_pitch(int win) { return win == 4 ? kWinTw + 2 : kWinTw + 1; }                  // pixel rows per window row
-__host__ __device__ constexpr int win_bytes(int win) { return win_pitch(win) * (win == 4 ? kWinTh + 2 : kWinTh + 1) * 128; }  // 23040 / 19584
-__host__ __device__ constexpr int win_slot_bytes(int win) { return win == 4 ? 24 * 1024 : 20 * 1024; }              // slot pitch (1024-aligned)
+// WIN = 3: the 9 taps of a 3x3 / stride-1 / pad-1 convolution from the same 18 x 10 window (tap (kh, kw) = window row kh * 10 + kw).
+__host__ __device__ constexpr bool win_wide(int win) { return win == 4 || win == 3; }                               // halo on both sides
+__host__ __device__ constexpr int win_pitch(int win) { return win_wide(win) ? kWinTw + 2 : kWinTw + 1; }            // pixel rows per window row
+__host__ __device__ constexpr int win_bytes(int win) { return win_pitch(win) * (win_wide(win) ? kWinTh + 2 : kWinTh + 1) * 128; }  // 23040 / 19584
+__host__ __device__ constexpr int win_slot_bytes(int win) { return win_wide(win) ? 24 * 1024 : 20 * 1024; }         // slot pitch (1024-aligned)
 __host__ __device__ constexpr int win_sbo(int win) { return win_pitch(win) * 128; }                                 // byte distance of 8-pixel row groups
-__host__ __device__ constexpr int win_taps(int win) { return win == 4 ? 16 : 4; }                                   // descriptors per window
+__host__ __device__ constexpr int win_taps(int win) { return win == 4 ? 16 : (win == 3 ? 9 : 4); }                  // descriptors per window
 constexpr int kBarrierBytes = 1024;                    // mbarriers + TMEM pointer behind the operand rings (keeps the epilogue tiles 1024-byte aligned)
 constexpr int kStatTileBytes = 4096 + 2048;           // per epilogue warp: 32 x 32 fp32 of dz + 32 x 32 bf16 of y (forward: 32 x 32 bf16 only)
 
 // Epilogue variants (compile-time: the per-element code has no branches and each variant is a small kernel)
-enum { ACT_BWD_NONE = 0, ACT_BWD_LEAKY = 1, ACT_BWD_RELU = 2 };
+enum { ACT_BWD_NONE = 0, ACT_BWD_LEAKY = 1, ACT_BWD_RELU = 2, ACT_FWD_BIAS_RELU = 3 };  // (3: forward epilogue of MODE_CONV3, BWD = false)
 template <bool STATS_, bool BWD_, int ACT_, bool G2_, bool BN_>
 struct Epi {
   static constexpr bool STATS = STATS_, BWD = BWD_, G2 = G2_, BN = BN_;
@@ -457,8 +466,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           mbar_wait(&emptyA_bar[sa], para ^ 1u);
           if (!PAIR || rank == 0) mbar_arrive_expect_tx_w(&fullA_bar[sa], a_tx);
           uint8_t* sW = smem + sa * win_slot_bytes(WIN);
-          if (WIN == 4) {
-            // all four phases: input pixels (i - 1 .. i + 16, j - 1 .. j + 8) of the tile
+          if (WIN == 4 || WIN == 3) {
+            // all four phases / all nine taps: input pixels (i - 1 .. i + 16, j - 1 .. j + 8) of the tile
             if (PAIR) tma2_load_4d_w(sW, &tmA, &fullA_bar[sa], cc * 64, c.w0 - 1, c.h0 - 1, c.b0);
             else tma_load_4d_w(sW, &tmA, &fullA_bar[sa], cc * 64, c.w0 - 1, c.h0 - 1, c.b0);
           } else if (p.mode == MODE_CONV_S2) {
@@ -480,6 +489,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               if (WIN == 4) {  // j = phase * 4 + tap
                 kb = ((j & 3) << p.cpt_sh) + cc;
                 row = (j >> 2) * p.Cout + c.n0 + nB;
+              } else if (WIN == 3) {  // j = kh * 3 + kw
+                kb = (j << p.cpt_sh) + cc;
+                row = c.n0 + nB;
               } else if (p.mode == MODE_CONV_S2) {
                 const int kh = 2 * eh + 1 - pr, kw = 2 * ew + 1 - pc;
                 kb = ((kh * 4 + kw) << p.cpt_sh) + cc;
@@ -552,6 +564,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const int nsub = p.BN >> 6;
             for (int j = 0; j < nsub; ++j) {
               const int nidx = c.n0 + 64 * j;
+              if (p.gram) {
+                tma_load_4d_w(sB + j * 8192, &tmB, &full_bar[s], nidx, pw0, ph0, pb0);
+                continue;
+              }
               const int tap = nidx >> p.ck_sh, c0 = nidx & (p.C_k - 1);
               const int kh = tap >> 2, kw = tap & 3;
               tma_load_5d_w(sB + j * 8192, &tmB, &full_bar[s], ((kw + 1) & 1) * p.C_k + c0, pw0 + ((kw + 1) >> 1) - 1, (kh + 1) & 1,
@@ -604,7 +620,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               // WIN 1: tap (eh, ew) = window row eh * 9 + ew.  WIN 4: phase (p, q), tap (a, b) = window row (p + a) * 10 + (q + b), accumulator
               // of phase 2p + q (one window row = 128 bytes = 8 descriptor units)
               const int ph = WIN == 4 ? (j >> 2) : 0, tp = WIN == 4 ? (j & 3) : j;
-              const int wr = WIN == 4 ? ((ph >> 1) + (tp >> 1)) * win_pitch(WIN) + (ph & 1) + (tp & 1) : (tp >> 1) * win_pitch(WIN) + (tp & 1);
+              const int wr = WIN == 4   ? ((ph >> 1) + (tp >> 1)) * win_pitch(WIN) + (ph & 1) + (tp & 1)
+                             : WIN == 3 ? (tp / 3) * win_pitch(WIN) + tp % 3
+                                        : (tp >> 1) * win_pitch(WIN) + (tp & 1);
               const uint32_t a_lo = w_lo + (uint32_t)(wr * 8);
               const uint32_t b_lo = b_lo0 + (uint32_t)u * ((uint32_t)b_bytes >> 4);
               const uint32_t d_ph = d_addr + (uint32_t)(ph * p.BN);
@@ -683,6 +701,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     constexpr int kEpiThreads = 32 * kEpiWarps;
     if (E::STATS) {
       for (int e = et; e < 2 * p.Cout; e += kEpiThreads) stat_acc[e] = 0.f;
+    }
+    if (!E::BWD && E::ACT == ACT_FWD_BIAS_RELU) {  // MODE_CONV3: the bias vector (bn_ss doubles as its staging area)
+      for (int e = et; e < p.Cout; e += kEpiThreads) bn_ss[e] = p.bias ? __ldg(p.bias + e) : 0.f;
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
     }
     if (E::BWD && E::BN) {
       for (int e = et; e < p.bwd.Cy; e += kEpiThreads) {
@@ -814,6 +836,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               }
             }
           } else {
+            if (!E::BWD && E::ACT == ACT_FWD_BIAS_RELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaxf(__uint_as_float(v[j]) + bn_ss[c.n0 + cc + j], 0.f));
+            }
             uint32_t o[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) o[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
@@ -1271,7 +1297,7 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const StoreMaps& s
     p.off_acc = off;
     off += has_stats ? 2 * p.Cout * 4 : 0;
     p.off_ss = off;
-    off += (has_bwd && p.bwd.scale) ? 2 * p.bwd.Cy * 4 : 0;
+    off += (has_bwd && p.bwd.scale) ? 2 * p.bwd.Cy * 4 : (p.mode == MODE_CONV3 ? p.Cout * 4 : 0);
     off = (off + 15) & ~15;
     if (p.win) off = (off + 1023) & ~1023;  // TMA-swizzled tiles
     p.off_tile = off;
@@ -1287,6 +1313,7 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const StoreMaps& s
     static const int tpb_env = env_int("B200_WIN_TPB", 0), sa_env = env_int("B200_WIN_SA", 0);
     p.tpb = b_bytes * 4 <= 32 * 1024 ? 4 : (b_bytes * 2 <= 32 * 1024 ? 2 : 1);
     if (tpb_env == 1 || tpb_env == 2 || tpb_env == 4) p.tpb = tpb_env;
+    if (p.win == 3) p.tpb = b_bytes * 3 <= 48 * 1024 ? 3 : 1;  // nine taps per window
     stage_bytes = p.tpb * b_bytes;
     const int taps = win_taps(p.win), slot = win_slot_bytes(p.win);
     const int per_window = (taps / p.tpb) * stage_bytes;  // weight bytes one window consumes
@@ -1328,7 +1355,9 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const StoreMaps& s
   if (grid_out) *grid_out = grid;
   const bool bn = p.bwd.scale != nullptr, g2 = p.bwd.g2 != nullptr;
   const int act = p.bwd.act;
-  if (!has_bwd) {
+  if (p.mode == MODE_CONV3) {
+    launch_variant_w<Epi<false, false, ACT_FWD_BIAS_RELU, false, false>, 3>(a, b, sm, p, grid, smem, stream);
+  } else if (!has_bwd) {
     if (has_stats) launch_variant<Epi<true, false, 0, false, false>>(a, b, sm, p, grid, smem, stream);
     else launch_variant<Epi<false, false, 0, false, false>>(a, b, sm, p, grid, smem, stream);
   } else if (act == ACT_BWD_LEAKY && bn && g2 && has_stats) {
@@ -1537,6 +1566,57 @@ int b200_convt_s2_gemm(const void* z, int B, int Hi, int Wi, int Cin, int ldz, c
   return launch(ta, tb, sm, p, stream, stat_rows);
 }
 
+// y[B,H,W,ldy] (bf16) = relu(conv3x3/s1/p1(x[B,H,W,Cin] (pixel stride ldx), wpk[Cout][9*Cin] bf16 with k = (kh*3+kw)*Cin + ci) + bias)
+// (relu == 0: no activation is not offered — every VGG19 convolution is followed by ReLU(inplace), loss.py:61-66).
+int b200_conv3_gemm(const void* x, int B, int H, int W, int Cin, int ldx, const void* wpk, const float* bias, int Cout, void* y, int ldy, int bn_hint,
+                    cudaStream_t stream) {
+  if (!is_pow2(H) || !is_pow2(W) || H < kWinTh || W < kWinTw || Cin % 64 || Cout % 32 || ldy % 8 || ldx % 8 || B < 1) {
+    b200_set_error("conv3_gemm: needs power-of-two H >= 16, W >= 8, Cin % 64 == 0, Cout % 32 == 0");
+    return B200_ERR_ARG;
+  }
+  IGemmParams p{};
+  p.mode = MODE_CONV3;
+  p.B = B;
+  p.Hs = H;
+  p.Ws = W;
+  p.win = 3;
+  p.tw = kWinTw, p.th = kWinTh, p.nb = 1;
+  p.tiles_w = p.Ws / p.tw;
+  p.tiles_h = p.Hs / p.th;
+  p.num_ptiles = p.tiles_w * p.tiles_h * B;
+  p.C_k = Cin;
+  p.cpt = Cin / 64;
+  p.kb_per_tile = p.kb_total = 9 * p.cpt;
+  p.BN = pick_bn(Cout, bn_hint);
+  if (Cout % p.BN || p.BN % 32 || p.BN > 256) {
+    b200_set_error("conv3_gemm: bad N tile");
+    return B200_ERR_ARG;
+  }
+  p.Cout = Cout;
+  p.ldc = ldy;
+  p.out = y;
+  p.stages = 0;
+  p.n_tiles = Cout / p.BN;
+  p.phases = 1;
+  p.m_tiles = 1;
+  p.num_tiles = p.num_ptiles * p.n_tiles;
+  p.stats = nullptr;
+  p.bias = bias;
+  p.bwd = EpiBwd{};
+  p.ksplit = 1;
+  p.partial = nullptr;
+  p.P_total = (long long)B * H * W;
+  p.pair = want_pair(p, 1) ? 1 : 0;
+  if (p.pair) p.num_tiles /= 2;
+  CUtensorMap ta, tb;
+  int rc;
+  if ((rc = map_nhwc(&ta, x, B, H, W, Cin, ldx, p.tw + 2, p.th + 2, p.nb))) return rc;
+  if ((rc = map_weights(&tb, wpk, Cout, 9 * Cin, p.pair ? p.BN / 2 : p.BN))) return rc;
+  StoreMaps sm{};
+  if ((rc = map_store(&sm.out, y, B, H, W, ldy, 2, false))) return rc;
+  return launch(ta, tb, sm, p, stream, nullptr);
+}
+
 // partial[splits][Cs][16*Cl] (fp32): per-split sums of S[b,i,j,cs] * L[b,2i+kh-1,2j+kw-1,cl], column = (kh*4+kw)*Cl + cl.
 // S: [B,Hs,Ws,Cs] (pixel stride lds), L: [B,2Hs,2Ws,Cl] dense.  Returns the split count actually used in *splits_io.
 int b200_wgrad_gemm(const void* S, int B, int Hs, int Ws, int Cs, int lds, const void* L, int Cl, void* partial, int* splits_io, int bn_hint, int stages,
@@ -1586,6 +1666,63 @@ int b200_wgrad_gemm(const void* S, int B, int Hs, int Ws, int Cs, int lds, const
   int rc;
   if ((rc = map_nhwc(&ta, S, B, Hs, Ws, Cs, lds, p.tw, p.th, p.nb))) return rc;
   if ((rc = map_nhwc_parity(&tb, L, B, 2 * Hs, 2 * Ws, Cl, p.tw, p.th, p.nb))) return rc;
+  return launch(ta, tb, StoreMaps{}, p, stream, nullptr);
+}
+
+// Splits per image of b200_gram_gemm.  Two reasons to split the pixel sum: (1) the tensor cores add into the fp32 accumulator with
+// truncation, so a sum of non-negative products (post-ReLU features) drifts low by ~0.6e-7 per accumulation step — 4096 steps for a
+// 256x256 map (measured 1.4e-4 low); bounding a split at 64 pixel tiles (256 steps) keeps that under 2e-5, the partial sums are then
+// added in round-to-nearest fp32 by the consumer; (2) B x (C/128) x (C/BN) tiles alone do not fill 148 SMs for the shallow layers.
+int b200_gram_splits(int B, int H, int W, int C) {
+  if (B < 1 || H < 1 || W < 1 || C < 64 || H * W < 64) return 1;
+  const int tiles = H * W / 64;
+  const int mn = ((C < 128 ? 128 : C) / 128) * (C / (C >= 256 ? 256 : C));
+  int s = 1;
+  while (tiles / s > 64) s <<= 1;
+  while (s < tiles && tiles / s > 8 && (long long)B * mn * s < kNumSMs) s <<= 1;
+  return s;
+}
+
+// Per-image Gram matrices of a feature map (lib/models/loss.py:117-136, `gram_matrix` before its division): F [B,H,W,C] bf16
+// (pixel stride ldf) -> G [B][S][Cp][C] fp32, sum_s G[b][s][c][c'] = sum_pixels F[b,pix,c] * F[b,pix,c'], S = b200_gram_splits(...),
+// Cp = max(C, 128) rows per matrix (rows >= C are zero).  The weight-gradient GEMM without taps: both operands are the same tensor.
+int b200_gram_gemm(const void* F, int B, int H, int W, int C, int ldf, float* G, cudaStream_t stream) {
+  if (!is_pow2(H) || !is_pow2(W) || H * W < 64 || C % 64 || ldf % 8 || B < 1) {
+    b200_set_error("gram_gemm: needs power-of-two H, W with H*W >= 64 and C % 64 == 0");
+    return B200_ERR_ARG;
+  }
+  IGemmParams p{};
+  p.mode = MODE_WGRAD;
+  p.gram = 1;
+  p.B = B;
+  p.Hs = H;
+  p.Ws = W;
+  pixel_box(H, W, 64, &p.tw, &p.th, &p.nb);
+  if (p.nb != 1) {
+    b200_set_error("gram_gemm: a 64-pixel tile must lie inside one image");
+    return B200_ERR_ARG;
+  }
+  const int S = b200_gram_splits(B, H, W, C);
+  p.tiles_w = W / p.tw;
+  p.tiles_h = H / p.th;
+  p.num_ptiles = p.tiles_w * p.tiles_h * B;
+  p.C_k = C;
+  p.cpt = C / 64;
+  p.BN = C >= 256 ? 256 : C;
+  p.kb_total = p.num_ptiles;
+  p.kb_per_tile = p.tiles_w * p.tiles_h / S;  // S splits per image, image-major: split index = b * S + s
+  p.Cout = C < 128 ? 128 : C;                 // accumulator rows: 128-row MMA tiles (channels beyond C are TMA zero fill)
+  p.ldc = C;
+  p.out = G;
+  p.stages = 0;
+  p.m_tiles = p.Cout / 128;
+  p.n_tiles = C / p.BN;
+  p.phases = 1;
+  p.num_tiles = p.m_tiles * p.n_tiles * B * S;
+  CUtensorMap ta, tb;
+  int rc;
+  if ((rc = map_nhwc(&ta, F, B, H, W, C, ldf, p.tw, p.th, p.nb))) return rc;
+  if ((rc = map_nhwc(&tb, F, B, H, W, C, ldf, p.tw, p.th, p.nb))) return rc;
   return launch(ta, tb, StoreMaps{}, p, stream, nullptr);
 }
 

@@ -608,3 +608,99 @@ class DiscriminatorEngine:
             dx = _empty((B, 1, R, R), f32, dev)
             call("b200_convt_c1_fwd", ptr(dz), B, R // 2, R // 2, 64, 64, ptr(self.convs[0].weight.data), None, ACT_NONE, None, ptr(c.xmul), ptr(dx), None, stream())
         return dx
+
+
+# ================================================================================================
+# VGG19 feature extractor of the perceptual / style losses (config 4)
+# ================================================================================================
+VGG_FEATURE_LAYERS = (1, 6, 11, 20, 29)  # relu1_1 .. relu5_1 (lib/models/loss.py:54)
+
+
+class VggFeatureEngine:
+    """``vgg19.features[0..29]`` (networks.py:367-389: torchvision VGG19 inside ``VGG19Wrapper``) on 1-channel images that the loss
+    functions feed as ``img.repeat(1, 3, 1, 1)`` (lib/models/loss.py:55-56).  Forward only — the reference evaluates these losses
+    under ``torch.no_grad()`` on detached tensors.  Layers 30..36 of ``features`` are executed by the reference's
+    loop but none of their outputs is used; they are skipped.
+
+    Every 3x3 convolution (+ bias + ReLU) except the first runs on the tcgen05 window kernel (``b200_conv3_gemm``); the first one
+    (3 identical input channels == 1 channel with channel-summed filters) is a direct kernel; max-pools are their own pass."""
+
+    def __init__(self, features: torch.nn.Sequential):
+        self.features = features
+        self.plan = []  # ("conv", index) | ("pool",)
+        for i, m in enumerate(features):
+            if i > max(VGG_FEATURE_LAYERS):
+                break
+            if isinstance(m, torch.nn.Conv2d):
+                if m.kernel_size != (3, 3) or m.stride != (1, 1) or m.padding != (1, 1):
+                    raise _lib.B200Error("VggFeatureEngine expects 3x3 / stride 1 / pad 1 convolutions")
+                self.plan.append(("conv", i))
+            elif isinstance(m, torch.nn.MaxPool2d):
+                self.plan.append(("pool", i))
+            elif isinstance(m, torch.nn.ReLU):
+                self.plan.append(("relu", i))
+            else:
+                raise _lib.B200Error(f"unexpected module in vgg19.features: {type(m).__name__}")
+        self.packed: Dict[int, torch.Tensor] = {}
+        self.w1 = None
+        self._versions = None
+
+    def refresh_weights(self):
+        convs = [self.features[i] for kind, i in self.plan if kind == "conv"]
+        ver = tuple((c.weight._version, c.weight.data_ptr()) for c in convs)
+        if ver == self._versions:
+            return
+        first = True
+        for kind, i in self.plan:
+            if kind != "conv":
+                continue
+            c = self.features[i]
+            w = c.weight.data.float().contiguous()
+            if first:  # Conv2d(3, 64): the three input channels carry the same image
+                if w.shape[0] != 64 or w.shape[1] != 3:
+                    raise _lib.B200Error("VggFeatureEngine expects features[0] = Conv2d(3, 64, 3, 1, 1)")
+                self.w1 = w.sum(dim=1).reshape(64, 9).contiguous()
+                first = False
+                continue
+            cout, cin = w.shape[:2]
+            pk = self.packed.get(i)
+            if pk is None or pk.device != w.device:
+                pk = _empty((cout, 9 * cin), bf16, w.device)
+                self.packed[i] = pk
+            call("b200_pack_conv3", ptr(w), cout, cin, ptr(pk), stream())
+        self._versions = ver
+
+    @torch.no_grad()
+    def features_of(self, x: torch.Tensor) -> List[torch.Tensor]:
+        """x: fp32 [B,1,H,W] (or [B,H,W]) -> the five NHWC bf16 feature maps relu1_1 .. relu5_1."""
+        if not x.is_cuda:
+            raise _lib.B200Error("the VGG feature losses run on CUDA tensors only; there is no CPU fallback")
+        x = x.detach().contiguous().float()
+        B, H, W = x.shape[0], x.shape[-2], x.shape[-1]
+        if x.numel() != B * H * W:
+            raise _lib.B200Error(f"the VGG feature losses expect 1-channel images, got {tuple(x.shape)}")
+        self.refresh_weights()
+        outs, h, first = [], None, True
+        C = 0
+        for kind, i in self.plan:
+            if kind == "conv":
+                c = self.features[i]
+                bias = c.bias.data.float() if c.bias is not None else None
+                if first:
+                    h = _empty((B, H, W, 64), bf16, x.device)
+                    call("b200_conv3_c1_fwd", ptr(x), B, H, W, ptr(self.w1), ptr(bias), 64, ptr(h), stream())
+                    C, first = 64, False
+                else:
+                    cout = c.out_channels
+                    y = _empty((B, H, W, cout), bf16, x.device)
+                    mt = B * (H // 16) * (W // 8)
+                    call("b200_conv3_gemm", ptr(h), B, H, W, C, C, ptr(self.packed[i]), ptr(bias), cout, ptr(y), cout, pick_bn(mt, cout), stream())
+                    h, C = y, cout
+            elif kind == "pool":
+                y = _empty((B, H // 2, W // 2, C), bf16, x.device)
+                call("b200_maxpool2", ptr(h), B, H, W, C, ptr(y), stream())
+                h, H, W = y, H // 2, W // 2
+            # "relu": fused into the convolution epilogue (ReLU(inplace=True) overwrites the conv output in the reference as well)
+            if i in VGG_FEATURE_LAYERS:
+                outs.append(h)
+        return outs

@@ -2,8 +2,10 @@
 reductions with hand-written backward kernels (csrc/losses.cu).
 
 ``tv_loss`` (loss.py:138-151, part of g_loss in config 4) is a fused stencil + reduction with its own backward kernel
-(csrc/tv.cu).  The perceptual / style losses of loss.py:49-115 need downloaded VGG19 weights and contribute no gradient (they run
-under ``no_grad`` on detached tensors); they are the not-yet-built part of SURVEY.md §8f row 1.
+(csrc/tv.cu).  ``perceptual_loss`` / ``style_loss`` / ``perceptual_and_style_loss`` / ``gram_matrix`` (loss.py:49-136) run the VGG19
+feature extractor on the tcgen05 3x3 window kernel (``engine.VggFeatureEngine``); like the reference they contribute no gradient
+(``torch.no_grad()`` on detached tensors).  The reference builds its VGG at import time with downloaded weights
+(loss.py:4-5); here it is built lazily with random initialisation unless ``set_vgg`` installs one.
 """
 from __future__ import annotations
 
@@ -133,3 +135,87 @@ def tv_loss(img, tv_weight):
     """loss.py:138-151: ``tv_weight * (mean((img[..., :-1] - img[..., 1:])**2) + mean((img[..., :-1, :] - img[..., 1:, :])**2))``;
     differentiable w.r.t. ``img`` (it is part of ``g_loss``, wgan_perceptual_style_faceparsing.py:219-221)."""
     return _TvFunction.apply(img, tv_weight)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# VGG19 perceptual / style losses (loss.py:49-136)
+# ------------------------------------------------------------------------------------------------------------------
+vgg = None  # the reference's module-level ``vgg = VGG19Wrapper().to(device)`` (loss.py:4-5), built on first use
+
+
+def set_vgg(wrapper):
+    """Install the ``networks.VGG19Wrapper`` the feature losses use (e.g. one loaded with trained torchvision weights)."""
+    global vgg
+    vgg = wrapper
+    return wrapper
+
+
+def _vgg(device):
+    global vgg
+    if vgg is None:
+        from . import networks
+
+        vgg = networks.VGG19Wrapper().to(device)
+        vgg.eval()
+    return vgg
+
+
+def _feature_losses(output, target, want_p: bool, want_s: bool):
+    """(sum over the five layers of mean((f_o - f_t)^2), sum of mean((gram(f_o) - gram(f_t))^2)) as device scalars."""
+    eng = _vgg(output.device)._get_engine()
+    B = output.shape[0]
+    with torch.no_grad():
+        # one pass over [output; target]: the weights are read once per layer
+        feats = eng.features_of(torch.cat([output.detach().reshape(B, 1, *output.shape[-2:]), target.detach().reshape(B, 1, *target.shape[-2:])], 0).float())
+        dev = output.device
+        out = torch.zeros(2, dtype=torch.float32, device=dev)
+        part = torch.empty(_lib.value("b200_sqdiff_blocks"), dtype=torch.float32, device=dev)
+        for f in feats:
+            _, H, W, C = f.shape
+            fo, ft = f[:B], f[B:]
+            n = fo.numel()
+            if want_p:
+                call("b200_sqdiff_bf16", ptr(fo), ptr(ft), n, 1.0 / n, ptr(part), ptr(out), 1, stream())
+            if want_s:
+                Cp, S = max(C, 128), _lib.value("b200_gram_splits", 2 * B, H, W, C)
+                G = torch.empty((2 * B, S, Cp, C), dtype=torch.float32, device=dev)
+                call("b200_gram_gemm", ptr(f), 2 * B, H, W, C, C, ptr(G), stream())
+                call("b200_sqdiff_gram", ptr(G[:B]), ptr(G[B:]), B, S, Cp, C, 1.0 / (H * W * C), 1.0 / (B * C * C), ptr(part), ctypes_ptr(out, 1), 1, stream())
+    return out
+
+
+def ctypes_ptr(t, index):
+    import ctypes
+
+    return ctypes.c_void_p(t.data_ptr() + index * t.element_size())
+
+
+def perceptual_loss(output, target, weight=0.05):
+    """loss.py:49-69: ``weight * sum_l mean((vgg_l(output) - vgg_l(target))^2)`` over relu{1..5}_1; no gradient."""
+    return weight * _feature_losses(output, target, True, False)[0]
+
+
+def style_loss(output, target, weight=0.1):
+    """loss.py:71-91: ``weight * sum_l mean((gram(vgg_l(output)) - gram(vgg_l(target)))^2)``; no gradient."""
+    return weight * _feature_losses(output, target, False, True)[1]
+
+
+def perceptual_and_style_loss(output, target, weight_p=0.05, weight_s=100):
+    """loss.py:93-115 (called with weight_p = weight_s = 0.01 at wgan_perceptual_style_faceparsing.py:216): both losses from ONE
+    pass of the feature extractor over [output; target]."""
+    v = _feature_losses(output, target, True, True)
+    return weight_p * v[0], weight_s * v[1]
+
+
+def gram_matrix(features, normalize=True):
+    """loss.py:117-136: ``features`` [N,C,H,W] -> [N,C,C] Gram matrices (divided by H*W*C when ``normalize``), on the tensor cores.
+    C must be a multiple of 64 and H*W >= 64 (every VGG19 layer the losses use)."""
+    if not features.is_cuda:
+        raise _lib.B200Error("gram_matrix runs on CUDA tensors only; there is no CPU fallback")
+    N, C, H, W = features.shape
+    f = features.detach().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    Cp, S = max(C, 128), _lib.value("b200_gram_splits", N, H, W, C)
+    G = torch.empty((N, S, Cp, C), dtype=torch.float32, device=features.device)
+    call("b200_gram_gemm", ptr(f), N, H, W, C, C, ptr(G), stream())
+    g = G[:, :, :C, :].sum(1)
+    return g / (H * W * C) if normalize else g

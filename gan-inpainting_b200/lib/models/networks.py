@@ -286,3 +286,33 @@ class PatchGANDiscriminator(nn.Module):
             raise _lib.B200Error(f"expected NCHW input with 1 channel, got {tuple(x.shape)}")
         output = _PatchGANFunction.apply(x, self, *self.parameters())
         return output.view(-1, 1)
+
+
+class VGG19Wrapper(nn.Module):
+    """networks.py:367-389: a torchvision VGG19 whose relu{1..5}_1 activations feed the perceptual / style losses
+    (lib/models/loss.py:49-115).  The reference loads ``vgg19(pretrained=True)`` (a download); there is no network here, so the
+    default is random initialisation (``pretrained=False``) — pass a ``state_dict`` of torchvision's VGG19 to use trained weights.
+    ``forward`` (the full classifier, never called by the reference's losses) is not built; the losses use
+    ``lib.models.loss.perceptual_and_style_loss``, which runs ``features[0..29]`` on the sm_100a kernels."""
+
+    def __init__(self, pretrained: bool = False, state_dict=None):
+        super().__init__()
+        from torchvision import models
+
+        if pretrained and state_dict is None:
+            raise _lib.B200Error("VGG19Wrapper(pretrained=True) needs a download; pass state_dict=<torchvision vgg19 weights> instead")
+        self.feature_maps = {}
+        self.vgg19 = models.vgg19(weights=None)
+        if state_dict is not None:
+            self.vgg19.load_state_dict(state_dict)
+        self._engine = None
+
+    def _get_engine(self):
+        from ...engine import VggFeatureEngine
+
+        if self._engine is None:
+            self._engine = VggFeatureEngine(self.vgg19.features)
+        return self._engine
+
+    def forward(self, x):
+        raise NotImplementedError("the VGG19 classifier head is not on the hot path (the reference's losses only walk vgg19.features)")

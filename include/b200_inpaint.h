@@ -238,6 +238,37 @@ int b200_tv_loss_bwd(const float* img, long long planes, int H, int W, float wei
                      b200_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
+ * VGG19 feature losses of config 4 (csrc/conv_gemm.cu MODE_CONV3 / gram mode, csrc/vgg.cu) — lib/models/loss.py:49-136
+ * (`perceptual_loss`, `style_loss`, `perceptual_and_style_loss`, `gram_matrix`) over networks.py:367-389 (`VGG19Wrapper`), called at
+ * experiment_list/wgan_perceptual_style_faceparsing.py:216.  Forward only: the reference evaluates them under torch.no_grad() on
+ * detached tensors.
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* nn.Conv2d(Cin, Cout, 3, 1, 1) + ReLU(inplace) of vgg19.features (window operand staging: the nine taps are descriptors into one
+ * 18 x 10-pixel halo window per 64-channel block).  x [B,H,W,Cin] bf16 (pixel stride ldx), wpk [Cout][9*Cin] from b200_pack_conv3,
+ * bias [Cout] fp32 or NULL; y [B,H,W,*] (pixel stride ldy).  H >= 16, W >= 8, powers of two; Cin % 64 == 0; Cout % 32 == 0. */
+int b200_conv3_gemm(const void* x, int B, int H, int W, int Cin, int ldx, const void* wpk, const float* bias, int Cout, void* y, int ldy, int bn_hint,
+                    b200_stream_t stream);
+/* fp32 [Cout][Cin][3][3] (torch layout) -> bf16 [Cout][(kh*3+kw)*Cin + ci] */
+int b200_pack_conv3(const float* w, int Cout, int Cin, void* out, b200_stream_t stream);
+/* vgg19.features[0..1] on `img.repeat(1,3,1,1)` (loss.py:55-56): x fp32 [B,H,W], w1 [64][9] = the filters summed over their 3 input
+ * channels, bias [64] -> y [B,H,W,64] bf16 = relu(conv + bias). */
+int b200_conv3_c1_fwd(const float* x, int B, int H, int W, const float* w1, const float* bias, int C, void* y, b200_stream_t stream);
+/* nn.MaxPool2d(2, 2) on NHWC bf16 */
+int b200_maxpool2(const void* x, int B, int H, int W, int C, void* y, b200_stream_t stream);
+/* gram_matrix (loss.py:117-136) before its division: F [B,H,W,C] bf16 -> G [B][S][max(C,128)][C] fp32 with
+ * sum_s G[b][s][c][c'] = sum_pix F[b,pix,c] F[b,pix,c'] and S = b200_gram_splits(B,H,W,C) partial sums per image (short tensor-core
+ * accumulation chains: see csrc/conv_gemm.cu; the consumer adds the S partials). */
+int b200_gram_splits(int B, int H, int W, int C);
+int b200_gram_gemm(const void* F, int B, int H, int W, int C, int ldf, float* G, b200_stream_t stream);
+/* out[0] (+)= scale * sum (a - b)^2: two bf16 tensors (torch.mean(torch.pow(f_o - f_t, 2)), loss.py:65) / two Gram stacks
+ * [B][S][Cp][C] from b200_gram_gemm, their S partials added and scaled by gscale first (loss.py:85).  partial: b200_sqdiff_blocks()
+ * floats. */
+int b200_sqdiff_blocks(void);
+int b200_sqdiff_bf16(const void* a, const void* b, long long n, double scale, float* partial, float* out, int accumulate, b200_stream_t stream);
+int b200_sqdiff_gram(const float* ga, const float* gb, int B, int S, int Cp, int C, float gscale, double scale, float* partial, float* out, int accumulate,
+                     b200_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
  * Input pipeline (csrc/preprocess.cu) — what the reference does to every decoded image on the host, for a batch on the GPU:
  * lib/data/dataset.py:6-12 (`Image.open(f).convert('L')`) and train.py:69-72 (`transforms.Resize(size)` + `transforms.ToTensor()`).
  * src: uint8 [B,H,W,channels] (3 = RGB, 1 = L); out: fp32 [B,1,outH,outW] in [0,1]; tmp: B*H*outW bytes.  Bit-exact with

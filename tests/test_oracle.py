@@ -180,3 +180,25 @@ def test_preprocess_oracle_matches_pillow_torchvision_golden():
     img = rng.integers(0, 256, (64, 64), dtype=np.uint8)
     assert np.array_equal(preprocess.load_transform(img, 64)[0], img.astype(np.float32) / np.float32(255))
     assert preprocess.load_transform(rng.integers(0, 256, (512, 512, 3), dtype=np.uint8), 4).shape == (1, 4, 4)
+
+
+def test_vgg_loss_oracle_matches_reference_golden():
+    """oracle/vgg_losses.py against the values the reference's own perceptual / style loss functions returned for the same seeded
+    random-initialised VGG19 (oracle/pin_vgg_against_reference.py)."""
+    import os
+
+    from oracle import vgg_losses
+
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_vgg.pt"))
+    feats = vgg_losses.seeded_vgg_features(gold["seed"])
+    wsum = float(sum(p.detach().double().sum() for p in feats.parameters()))
+    assert abs(wsum - gold["weight_sum"]) < 1e-6 * max(1.0, abs(gold["weight_sum"])), "torchvision's seeded VGG19 initialisation changed"
+    for c in gold["cases"][:2]:
+        p, s = vgg_losses.perceptual_and_style_loss(feats, c["output"], c["target"], 0.01, 0.01)
+        assert torch.allclose(p, c["p"], rtol=1e-5, atol=0) and torch.allclose(s, c["s"], rtol=1e-5, atol=0)
+    c = gold["cases"][2]
+    assert torch.allclose(vgg_losses.perceptual_loss(feats, c["output"], c["target"]), c["p_default"], rtol=1e-5, atol=0)
+    assert torch.allclose(vgg_losses.style_loss(feats, c["output"], c["target"]), c["s_default"], rtol=1e-5, atol=0)
+    # the bf16-storage emulation stays close to fp32 (it bounds what the CUDA path may differ by)
+    pe, se = vgg_losses.perceptual_and_style_loss(feats, c["output"], c["target"], 0.01, 0.01, bf16=True)
+    assert abs(float(pe) - float(c["p"])) < 5e-2 * float(c["p"]) and abs(float(se) - float(c["s"])) < 1e-1 * float(c["s"])

@@ -1,10 +1,5 @@
 #!/bin/bash
-# One gpurun call of round 2 (kept for reproducibility): final evidence — GPU suite, smoke, bench line + reference arm, ncu launch list.
+# One gpurun call of round 2 (kept for reproducibility): VGG perceptual / style loss kernels — tests and per-layer timing.
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_gpu.log 2>&1; tail -3 gpurun_out/r2_pytest_gpu.log
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_smoke.log 2>&1; tail -1 gpurun_out/r2_smoke.log | cut -c1-300
-python bench.py --steps 20 --warmup 5 > gpurun_out/r2_bench_n1.json 2> gpurun_out/r2_bench_n1.err; cut -c1-200 gpurun_out/r2_bench_n1.json; tail -2 gpurun_out/r2_bench_n1.err
-python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/r2_bench_reference.json 2> gpurun_out/r2_bench_reference.err; cut -c1-200 gpurun_out/r2_bench_reference.json
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 1300 --csv --log-file gpurun_out/r2_bench_launches_ncu.csv \
-  python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-graph --no-also > gpurun_out/ncu.log 2>&1
-tail -1 gpurun_out/ncu.log | cut -c1-120
+timeout 600 python -m pytest tests/test_vgg_gpu.py -q > gpurun_out/r2_vgg_tests.log 2>&1; echo rc=$?; tail -15 gpurun_out/r2_vgg_tests.log
+timeout 300 python tools/vgg_table.py > gpurun_out/r2_vgg_table.txt 2>&1; cat gpurun_out/r2_vgg_table.txt | tail -50
