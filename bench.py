@@ -50,10 +50,14 @@ RECIPES = {
     "wgan_rmse": ("wgan", "rmse"),
     "minimaxgan_rmse": ("minimax", "rmse"),
     "minimaxgan_l1": ("minimax", "l1"),
+    # config 4 (wgan_perceptual_style_faceparsing.py:197-225) without its face-parsing term (needs a trained segmentation network):
+    # WGAN + RMSE + local (masked MSE) + TV + VGG19 perceptual / style losses
+    "wgan_perceptual_style": ("wgan", "rmse"),
     "wgan_d_only": ("wgan", "l1"),     # the D-only batches of the WGAN schedule (update_g=False)
     "inference": ("wgan", "l1"),       # config 5: trainer.inpaint, no discriminator work
 }
-DEFAULT_SHAPE = {"inference": (512, 128)}  # (res, batch per GPU); everything else 256x256, batch 64 (BASELINE configs[1])
+CONFIG4 = dict(tv_weight=1.0, feature_weights=(0.01, 0.01), local_recon="mse")  # :209-219
+DEFAULT_SHAPE = {"inference": (512, 128), "wgan_perceptual_style": (256, 32)}  # (res, batch per GPU); everything else 256x256, batch 64 (BASELINE configs[1])
 
 
 def metric_name(recipe: str, res: int) -> str:
@@ -83,6 +87,16 @@ def conv_flops(res: int):
     return g, d
 
 
+def vgg_flops(res: int) -> float:
+    """Tensor-core FLOPs per image of ONE pass of vgg19.features[0..29] (conv1_2 .. conv5_1; conv1_1 runs as a direct kernel) plus
+    the five Gram matrices (loss.py:117-136)."""
+    cfg = [(64, 64, 0), (64, 128, 1), (128, 128, 1), (128, 256, 2), (256, 256, 2), (256, 256, 2), (256, 256, 2), (256, 512, 3), (512, 512, 3), (512, 512, 3),
+           (512, 512, 3), (512, 512, 4)]
+    f = sum(2.0 * (res >> lv) ** 2 * 9 * cin * cout for cin, cout, lv in cfg)
+    f += sum(2.0 * (res >> lv) ** 2 * c * c for lv, c in enumerate((64, 128, 256, 512, 512)))
+    return f
+
+
 def flops_per_image(res: int, recipe: str) -> dict:
     """Algorithmic conv FLOPs (2*MAC) per image, SURVEY.md §8(d): full step = 3*G + 8*D."""
     g, d = conv_flops(res)
@@ -98,6 +112,9 @@ def flops_per_image(res: int, recipe: str) -> dict:
         return dict(total=g + 6 * d, tensor=g_tc + 6 * d_tc)
     # G: fwd + dgrad + wgrad (d2's dgrad to a1 IS needed; d1 has none).  D: 2 fwd + 2*(dgrad+wgrad) in the D step
     # (c2's dgrad is needed for c1's wgrad) + 1 fwd + 1 dgrad in the G step.
+    if recipe == "wgan_perceptual_style":  # + two feature-extractor passes (inpainted, ground) per image; its first conv is not tensor-core work
+        v = 2 * vgg_flops(res)
+        return dict(total=3 * g + 8 * d + v + 2 * 2.0 * res * res * 27 * 64, tensor=3 * g_tc + 8 * d_tc + v)
     return dict(total=3 * g + 8 * d, tensor=3 * g_tc + 8 * d_tc)
 
 
@@ -178,7 +195,13 @@ def cpu_step_runner(recipe: str, res: int, batch: int):
     G, D = steps.enable_grad(nets.init_unet(0)), steps.enable_grad(nets.init_patchgan(1, res=res))
     if kind == "wgan":
         go, do = steps.make_optimizer("rmsprop", G), steps.make_optimizer("rmsprop", D)
-        fn = lambda g, m: steps.wgan_step(G, D, go, do, g, m, recon=recon, update_g=(recipe != "wgan_d_only"))
+        extra = {}
+        if recipe == "wgan_perceptual_style":
+            from oracle import vgg_losses
+
+            extra = dict(tv_weight=CONFIG4["tv_weight"], vgg_features=vgg_losses.seeded_vgg_features(0), feature_weights=CONFIG4["feature_weights"],
+                         local_recon=CONFIG4["local_recon"])
+        fn = lambda g, m: steps.wgan_step(G, D, go, do, g, m, recon=recon, update_g=(recipe != "wgan_d_only"), **extra)
     else:
         go, do = steps.make_optimizer("adam", G), steps.make_optimizer("adam", D)
         fn = lambda g, m: steps.minimax_step(G, D, go, do, g, m, recon=recon)
@@ -199,6 +222,9 @@ def time_cpu(recipe: str, res: int, batch: int, steps_n: int, warmup: int):
 def workload_name(recipe: str, res: int, batch: int, what: str) -> str:
     if recipe == "inference":
         return f"inference (config 5): ceil(mask) -> mask-out -> U-Net generator (eval) -> composite, {res}x{res}, batch {batch} {what}"
+    if recipe == "wgan_perceptual_style":
+        return (f"wgan_perceptual_style_faceparsing without its face-parsing term: U-Net generator + PatchGAN global D full train step, g_loss = adversarial + "
+                f"RMSE + local MSE + TV + VGG19 perceptual/style (random-init VGG19), {res}x{res}, batch {batch} {what}")
     if recipe == "wgan_d_only":
         return f"wgan_l1 D-only batch (G forward + composite + D update, no G update; wgan_l1.py:157-163), {res}x{res}, batch {batch} {what}"
     return f"{recipe}: U-Net generator + PatchGAN global D, full train step (D update + G update), {res}x{res}, batch {batch} {what}"
@@ -290,7 +316,8 @@ def run_b200(args):
     G = networks.get_network("generator", "unet").to(dev).train()  # reference default: dropout ON
     D = networks.PatchGANDiscriminator(sigmoid=(kind != "wgan"), imagedim=R).to(dev).train()
     tr = InpaintingTrainer(kind, G, D, recon=recon, distributed=(world > 1 and not infer), bucket_mb=args.bucket_mb, graph=not args.no_graph, rank=rank,
-                           comm_sms=args.comm_sms, wire_bf16=(None if args.grad_wire is None else args.grad_wire == "bf16"))
+                           comm_sms=args.comm_sms, wire_bf16=(None if args.grad_wire is None else args.grad_wire == "bf16"),
+                           **(CONFIG4 if args.recipe == "wgan_perceptual_style" else {}))
 
     def sync_all():
         torch.cuda.synchronize()
@@ -342,7 +369,7 @@ def run_b200(args):
             return step, e2e, 2 * ground_h.numel() * 4, res_h.numel() * 4
         upd = recipe != "wgan_d_only"
         step = lambda: tr.step(ground, mask, update_g=upd)
-        out_h = torch.empty(16, dtype=torch.float32).pin_memory()
+        out_h = torch.empty(tr.scalars.numel(), dtype=torch.float32).pin_memory()
 
         def e2e(n):
             """n steps through the public API: DevicePrefetcher (pinned host -> device copy of EVERY step's inputs, overlapped with
@@ -456,7 +483,7 @@ def run_b200(args):
         return
     peaks = measured_peaks()
     fl = flops_per_image(R, args.recipe)
-    gemm_names = ("b200_conv_s2_gemm", "b200_convt_s2_gemm", "b200_wgrad_gemm")
+    gemm_names = ("b200_conv_s2_gemm", "b200_convt_s2_gemm", "b200_wgrad_gemm", "b200_conv3_gemm", "b200_gram_gemm")
     gemm_ms = sum(kernel_ms.get(k, 0.0) for k in gemm_names)
     gemm_calls = sum(len(prof.get(k, [])) for k in gemm_names)
     achieved = fl["tensor"] * B / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None

@@ -24,9 +24,11 @@ __global__ void __launch_bounds__(256) pack_conv3_kernel(const float* __restrict
   }
 }
 
-// thread = (8-channel group, pixel pair): the 72 filter taps of its channel group live in registers for the whole grid-stride loop
-// (the loop stride is a multiple of 8, so a thread never changes group); per pair of horizontally adjacent pixels 12 image loads
-// (broadcast across the 8 threads of the pair), 144 FMAs, two 16-byte stores.  C == 64, W even.
+// thread = (8-channel group, run of 8 pixels of one row): the 72 filter taps of its channel group live in registers for the whole
+// grid-stride loop (the loop stride is a multiple of 8, so a thread never changes group); per run 12 image loads (3 rows x {left
+// neighbour, two float4, right neighbour}, broadcast across the 8 threads that share the run), 576 FMAs and eight 16-byte stores —
+// the index arithmetic is paid once per 8 pixels, which is what makes the kernel FMA-bound instead of issue-bound.
+// C == 64, W % 8 == 0, x 16-byte aligned, B*H*W < 2^31.
 __global__ void __launch_bounds__(256) conv3_c1_fwd_kernel(const float* __restrict__ x, int B, int H, int W, const float* __restrict__ w1 /*[64][9]*/,
                                                            const float* __restrict__ bias, __nv_bfloat16* __restrict__ y) {
   pdl_enter();
@@ -38,41 +40,45 @@ __global__ void __launch_bounds__(256) conv3_c1_fwd_kernel(const float* __restri
 #pragma unroll
     for (int t = 0; t < 9; ++t) wr[t][k] = __ldg(w1 + (cg + k) * 9 + t);
   }
-  const int Wh = W >> 1;
-  const long long pairs = (long long)B * H * Wh;
-  for (long long pr = ((long long)blockIdx.x * 256 + threadIdx.x) >> 3; pr < pairs; pr += ((long long)gridDim.x * 256) >> 3) {
-    const int wq = (int)(pr % Wh) * 2;
-    const long long r = pr / Wh;  // b * H + hq
-    const int hq = (int)(r % H);
-    const float* xr = x + r * W;  // row hq of image b
-    float v[3][4];
+  const unsigned Wr = (unsigned)W >> 3, runs = (unsigned)B * H * Wr;
+  for (unsigned run = (blockIdx.x * 256u + threadIdx.x) >> 3; run < runs; run += (gridDim.x * 256u) >> 3) {
+    const unsigned r = run / Wr;  // b * H + hq
+    const int wq = (int)(run - r * Wr) * 8;
+    const int hq = (int)(r % (unsigned)H);
+    const float* xr = x + (size_t)r * W + wq;
+    float v[3][10];
 #pragma unroll
     for (int dh = 0; dh < 3; ++dh) {
       const int hh = hq + dh - 1;
       const bool rv = hh >= 0 && hh < H;
-      const float* xp = xr + (long long)(dh - 1) * W + wq;
+      const float* xp = xr + (ptrdiff_t)(dh - 1) * W;
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 m0 = rv ? __ldg(reinterpret_cast<const float4*>(xp)) : z, m1 = rv ? __ldg(reinterpret_cast<const float4*>(xp) + 1) : z;
       v[dh][0] = (rv && wq > 0) ? __ldg(xp - 1) : 0.f;
-      const float2 m = rv ? __ldg(reinterpret_cast<const float2*>(xp)) : make_float2(0.f, 0.f);
-      v[dh][1] = m.x, v[dh][2] = m.y;
-      v[dh][3] = (rv && wq + 2 < W) ? __ldg(xp + 2) : 0.f;
+      v[dh][1] = m0.x, v[dh][2] = m0.y, v[dh][3] = m0.z, v[dh][4] = m0.w;
+      v[dh][5] = m1.x, v[dh][6] = m1.y, v[dh][7] = m1.z, v[dh][8] = m1.w;
+      v[dh][9] = (rv && wq + 8 < W) ? __ldg(xp + 8) : 0.f;
     }
-    float a0[8], a1[8];
+    __nv_bfloat16* yp = y + ((size_t)r * W + wq) * 64 + cg;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) a0[k] = a1[k] = br[k];
+    for (int px = 0; px < 8; px += 2) {
+      float a0[8], a1[8];
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const float v0 = v[t / 3][t % 3], v1 = v[t / 3][t % 3 + 1];
+      for (int k = 0; k < 8; ++k) a0[k] = a1[k] = br[k];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        a0[k] = fmaf(v0, wr[t][k], a0[k]);
-        a1[k] = fmaf(v1, wr[t][k], a1[k]);
+      for (int t = 0; t < 9; ++t) {
+        const float v0 = v[t / 3][px + t % 3], v1 = v[t / 3][px + t % 3 + 1];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          a0[k] = fmaf(v0, wr[t][k], a0[k]);
+          a1[k] = fmaf(v1, wr[t][k], a1[k]);
+        }
       }
+      *reinterpret_cast<uint4*>(yp + px * 64) = make_uint4(pack_bf16x2(fmaxf(a0[0], 0.f), fmaxf(a0[1], 0.f)), pack_bf16x2(fmaxf(a0[2], 0.f), fmaxf(a0[3], 0.f)),
+                                                           pack_bf16x2(fmaxf(a0[4], 0.f), fmaxf(a0[5], 0.f)), pack_bf16x2(fmaxf(a0[6], 0.f), fmaxf(a0[7], 0.f)));
+      *reinterpret_cast<uint4*>(yp + px * 64 + 64) = make_uint4(pack_bf16x2(fmaxf(a1[0], 0.f), fmaxf(a1[1], 0.f)), pack_bf16x2(fmaxf(a1[2], 0.f), fmaxf(a1[3], 0.f)),
+                                                                pack_bf16x2(fmaxf(a1[4], 0.f), fmaxf(a1[5], 0.f)), pack_bf16x2(fmaxf(a1[6], 0.f), fmaxf(a1[7], 0.f)));
     }
-    __nv_bfloat16* yp = y + (r * W + wq) * 64 + cg;
-    *reinterpret_cast<uint4*>(yp) = make_uint4(pack_bf16x2(fmaxf(a0[0], 0.f), fmaxf(a0[1], 0.f)), pack_bf16x2(fmaxf(a0[2], 0.f), fmaxf(a0[3], 0.f)),
-                                               pack_bf16x2(fmaxf(a0[4], 0.f), fmaxf(a0[5], 0.f)), pack_bf16x2(fmaxf(a0[6], 0.f), fmaxf(a0[7], 0.f)));
-    *reinterpret_cast<uint4*>(yp + 64) = make_uint4(pack_bf16x2(fmaxf(a1[0], 0.f), fmaxf(a1[1], 0.f)), pack_bf16x2(fmaxf(a1[2], 0.f), fmaxf(a1[3], 0.f)),
-                                                    pack_bf16x2(fmaxf(a1[4], 0.f), fmaxf(a1[5], 0.f)), pack_bf16x2(fmaxf(a1[6], 0.f), fmaxf(a1[7], 0.f)));
   }
 }
 
@@ -207,11 +213,11 @@ int b200_pack_conv3(const float* w, int Cout, int Cin, void* out, cudaStream_t s
 }
 
 int b200_conv3_c1_fwd(const float* x, int B, int H, int W, const float* w1, const float* bias, int C, void* y, cudaStream_t stream) {
-  if (C != 64 || B < 1 || H < 1 || W < 2 || (W & 1) || ((uintptr_t)x & 7)) {
-    b200_set_error("conv3_c1_fwd: C must be 64 (VGG19 features[0]), W even, x 8-byte aligned");
+  if (C != 64 || B < 1 || H < 1 || W < 8 || (W & 7) || ((uintptr_t)x & 15) || (long long)B * H * W >= (1LL << 31)) {
+    b200_set_error("conv3_c1_fwd: C must be 64 (VGG19 features[0]), W a multiple of 8, x 16-byte aligned, B*H*W < 2^31");
     return B200_ERR_ARG;
   }
-  B200_LAUNCH((conv3_c1_fwd_kernel), grid_for((long long)B * H * W * 4), 256, 0, stream, x, B, H, W, w1, bias, (__nv_bfloat16*)y);
+  B200_LAUNCH((conv3_c1_fwd_kernel), grid_for((long long)B * H * W), 256, 0, stream, x, B, H, W, w1, bias, (__nv_bfloat16*)y);
   B200_CHECK_LAUNCH();
   return B200_OK;
 }

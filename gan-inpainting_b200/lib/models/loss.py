@@ -160,27 +160,29 @@ def _vgg(device):
     return vgg
 
 
-def _feature_losses(output, target, want_p: bool, want_s: bool):
-    """(sum over the five layers of mean((f_o - f_t)^2), sum of mean((gram(f_o) - gram(f_t))^2)) as device scalars."""
+def _feature_losses(output, target, want_p: bool, want_s: bool, dst=None, weights=(1.0, 1.0)):
+    """weights x (sum over the five layers of mean((f_o - f_t)^2), sum of mean((gram(f_o) - gram(f_t))^2)) as two device scalars
+    (written into ``dst`` when given: a contiguous fp32 view of 2 elements)."""
     eng = _vgg(output.device)._get_engine()
     B = output.shape[0]
     with torch.no_grad():
         # one pass over [output; target]: the weights are read once per layer
         feats = eng.features_of(torch.cat([output.detach().reshape(B, 1, *output.shape[-2:]), target.detach().reshape(B, 1, *target.shape[-2:])], 0).float())
         dev = output.device
-        out = torch.zeros(2, dtype=torch.float32, device=dev)
+        out = torch.zeros(2, dtype=torch.float32, device=dev) if dst is None else dst.zero_()
+        wp, ws = float(weights[0]), float(weights[1])
         part = torch.empty(_lib.value("b200_sqdiff_blocks"), dtype=torch.float32, device=dev)
         for f in feats:
             _, H, W, C = f.shape
             fo, ft = f[:B], f[B:]
             n = fo.numel()
             if want_p:
-                call("b200_sqdiff_bf16", ptr(fo), ptr(ft), n, 1.0 / n, ptr(part), ptr(out), 1, stream())
+                call("b200_sqdiff_bf16", ptr(fo), ptr(ft), n, wp / n, ptr(part), ptr(out), 1, stream())
             if want_s:
                 Cp, S = max(C, 128), _lib.value("b200_gram_splits", 2 * B, H, W, C)
                 G = torch.empty((2 * B, S, Cp, C), dtype=torch.float32, device=dev)
                 call("b200_gram_gemm", ptr(f), 2 * B, H, W, C, C, ptr(G), stream())
-                call("b200_sqdiff_gram", ptr(G[:B]), ptr(G[B:]), B, S, Cp, C, 1.0 / (H * W * C), 1.0 / (B * C * C), ptr(part), ctypes_ptr(out, 1), 1, stream())
+                call("b200_sqdiff_gram", ptr(G[:B]), ptr(G[B:]), B, S, Cp, C, 1.0 / (H * W * C), ws / (B * C * C), ptr(part), ctypes_ptr(out, 1), 1, stream())
     return out
 
 

@@ -23,7 +23,7 @@ past a bucket, so the transfer overlaps the remaining backward kernels.  BatchNo
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional
+from typing import Dict, List, Optional, Tuple
 
 import torch
 
@@ -37,8 +37,9 @@ RECON_L1, RECON_RMSE, RECON_LOCAL_L1, RECON_LOCAL_MSE, RECON_MASKED_RMSE = 0, 1,
 # slots of the per-step scalar vector
 SLOTS = ["d_loss_real", "d_loss_fake", "g_adv", "g_adv_local", "d_loss_real_local", "d_loss_fake_local"]
 RECON_SLOT = 8      # 4 floats: loss, denom, exact count (2 words)
-RECON2_SLOT = 12    # second reconstruction term (global_local)
-NSCALARS = 16
+RECON2_SLOT = 12    # second reconstruction term (global_local; config 4's local term)
+TV_SLOT, PERCEPTUAL_SLOT, STYLE_SLOT = 16, 17, 18  # config 4's extra generator loss terms (already weighted)
+NSCALARS = 20
 
 
 class GradBucketer:
@@ -125,9 +126,19 @@ class GradBucketer:
 class InpaintingTrainer:
     def __init__(self, recipe: str, net_G, net_D, net_D_local=None, recon: str = "l1", lambdas=(300.0, 300.0), clip: float = 0.01,
                  distributed: bool = False, bucket_mb: float = 25.0, log_grad_means: bool = False, graph: bool = False, rank: Optional[int] = None,
-                 comm_sms: Optional[int] = None, bucket_mb_d: float = 4.0, wire_bf16: Optional[bool] = None):
+                 comm_sms: Optional[int] = None, bucket_mb_d: float = 4.0, wire_bf16: Optional[bool] = None, tv_weight: float = 0.0,
+                 feature_weights: Optional[Tuple[float, float]] = None, local_recon: Optional[str] = None):
+        """``tv_weight`` / ``feature_weights=(weight_p, weight_s)`` / ``local_recon`` ("l1" | "mse") add the generator loss terms of
+        wgan_perceptual_style_faceparsing.py:208-221 to the ``wgan`` / ``minimax`` recipes: ``tv_loss(inpainted, tv_weight)`` (with
+        its gradient), the VGG19 perceptual + style losses (numbers only: the reference computes them under ``no_grad``, SURVEY.md
+        D11) and ``LocalLoss(base)(ground, inpainted, mask)``.  That script's face-parsing term is not built."""
         if recipe not in ("wgan", "minimax", "global_local"):
             raise ValueError(recipe)
+        if recipe == "global_local" and (tv_weight or feature_weights or local_recon):
+            raise ValueError("the extra generator loss terms belong to the wgan / minimax recipes")
+        self.tv_weight = float(tv_weight)
+        self.feature_weights = tuple(float(w) for w in feature_weights) if feature_weights is not None else None
+        self.local_recon = {None: -1, "l1": RECON_LOCAL_L1, "mse": RECON_LOCAL_MSE}[local_recon]
         if recipe == "global_local" and net_D_local is None:
             raise ValueError("global_local needs a local discriminator")
         self.recipe, self.recon = recipe, {"l1": RECON_L1, "rmse": RECON_RMSE}[recon]
@@ -325,11 +336,23 @@ class InpaintingTrainer:
             cA = eD.forward(inpainted, True, self.sigmoid)
             dadv = eD.backward(cA, self._adv(cA, 1.0, 1.0, "g_adv"), None, input_grad=True)
             call("b200_recon_loss", self.recon, ptr(ground), ptr(inpainted), None, n, 1e-16, ptr(sc.recon), self._slot(RECON_SLOT), stream())
+            if self.local_recon >= 0:  # wgan_perceptual_style_faceparsing.py:209
+                call("b200_recon_loss", self.local_recon, ptr(ground), ptr(inpainted), ptr(mask_c), n, 1e-16, ptr(sc.recon), self._slot(RECON2_SLOT), stream())
+            if self.tv_weight:  # :219 — value into its slot, gradient added to d g_loss / d inpainted
+                R = ground.shape[-1]
+                part = torch.empty(2 * B * ground.shape[-2], dtype=torch.float32, device=dev)
+                call("b200_tv_loss", ptr(inpainted), B, ground.shape[-2], R, self.tv_weight, ptr(part), self._slot(TV_SLOT), stream())
+                call("b200_tv_loss_bwd", ptr(inpainted), B, ground.shape[-2], R, self.tv_weight, None, ptr(dadv), 1, stream())
+            if self.feature_weights is not None:  # :216 — no gradient
+                from .lib.models import loss as _loss
+
+                _loss._feature_losses(inpainted, ground, True, True, dst=self.scalars[PERCEPTUAL_SLOT:STYLE_SLOT + 1], weights=self.feature_weights)
             dpre = torch.empty_like(ground)
             gG = self.fG.grad_map()
             bias = eG.uc[0].bias
-            call("b200_gstep_seed", ptr(ground), ptr(inpainted), ptr(cG.g_out), ptr(mask_c), ptr(dadv), None, self.recon, 1.0, self._slot(RECON_SLOT), -1, 0.0,
-                 None, None, 1, n, ptr(dpre), None, ptr(sc.recon), ptr(gG[id(bias)]), 0, stream())
+            call("b200_gstep_seed", ptr(ground), ptr(inpainted), ptr(cG.g_out), ptr(mask_c), ptr(dadv), None, self.recon, 1.0, self._slot(RECON_SLOT),
+                 self.local_recon, 1.0 if self.local_recon >= 0 else 0.0, self._slot(RECON2_SLOT) if self.local_recon >= 0 else None, None, 1, n, ptr(dpre),
+                 None, ptr(sc.recon), ptr(gG[id(bias)]), 0, stream())
             hook = self.buckets.get(id(self.fG))
             if hook:
                 hook.ready(bias)
@@ -402,7 +425,14 @@ class InpaintingTrainer:
             out["g_loss"] = out["g_adv"] + out["g_adv_local"] + self.lambdas[0] * out["recon"] + self.lambdas[1] * out["recon_local"]
             out["d_loss"] = out["d_loss_real"] + out["d_loss_fake"] + out["d_loss_real_local"] + out["d_loss_fake_local"]
         else:
+            out["g_tv"], out["g_perceptual"], out["g_style"] = v[TV_SLOT], v[PERCEPTUAL_SLOT], v[STYLE_SLOT]
             out["g_loss"] = out["g_adv"] + out["recon"]
+            if self.local_recon >= 0:
+                out["g_loss"] += out["recon_local"]
+            if self.tv_weight:
+                out["g_loss"] += out["g_tv"]
+            if self.feature_weights is not None:
+                out["g_loss"] += out["g_perceptual"] + out["g_style"]
             out["d_loss"] = out["d_loss_real"] - out["d_loss_fake"] if self.recipe == "wgan" else out["d_loss_real"] + out["d_loss_fake"]
         return out
 

@@ -128,10 +128,18 @@ def wgan_step(
     clip: float = 0.01,
     policy=None,
     after_d_step=None,
+    tv_weight: float = 0.0,
+    vgg_features=None,
+    feature_weights=(0.01, 0.01),
+    local_recon: Optional[str] = None,
 ):
     """wgan_l1.py:110-186 (recon='l1') / wgan_rmse.py (recon='rmse').
 
-    ``update_g`` stands for the schedule test at wgan_l1.py:157-163."""
+    ``update_g`` stands for the schedule test at wgan_l1.py:157-163.  ``tv_weight`` / ``vgg_features`` (+ ``feature_weights``) /
+    ``local_recon`` add the generator loss terms of wgan_perceptual_style_faceparsing.py:208-221 — ``tv_loss(inpainted, 1)``,
+    ``perceptual_and_style_loss(inpainted, ground, 0.01, 0.01)`` (no gradient, D11) and the local reconstruction term — as that
+    script intends them (it does not run: ``recon_loss`` :221 is undefined and ``LocalLoss(RMSELoss())`` :63 cannot be constructed;
+    the usable ``LocalLoss`` bases are L1 / MSE).  Its face-parsing term needs a trained segmentation network and is not restated."""
     out = {}
     mask, masked = prepare(ground, mask)
     _scope(policy, "G")
@@ -168,6 +176,21 @@ def wgan_step(
         g_adv = d_gen.mean().view(1)
         rec = _recon(recon, ground, inpainted)
         g_loss = g_adv + rec
+        if local_recon is not None:  # :209
+            loc = losses.local_loss(inpainted, ground, mask, local_recon)
+            g_loss = g_loss + loc
+            out["recon_local"] = loc.item()
+        if tv_weight:  # :219
+            tv = losses.tv_loss(inpainted, tv_weight)
+            g_loss = g_loss + tv
+            out["g_tv"] = tv.item()
+        if vgg_features is not None:  # :216
+            from . import vgg_losses
+
+            with torch.no_grad():
+                p, s = vgg_losses.perceptual_and_style_loss(vgg_features, inpainted, ground, feature_weights[0], feature_weights[1], bf16=policy is not None)
+            g_loss = g_loss + p + s
+            out["g_perceptual"], out["g_style"] = p.item(), s.item()
         g_loss.backward()
         out["g_adv"], out["recon"], out["g_loss"] = g_adv.item(), rec.item(), g_loss.item()
         out["g_grads"] = grads_of(G)

@@ -159,6 +159,48 @@ def test_wgan_step(dev, recon):
     assert abs(float(D.state_dict()["model.3.weight"].mean()) - 0.01) < 1e-6
 
 
+def test_wgan_step_with_config4_loss_terms(dev):
+    """The generator loss of wgan_perceptual_style_faceparsing.py:208-221 without its face-parsing term: adversarial + RMSE + local
+    (masked, micro-averaged MSE) + TV (with gradient) + VGG19 perceptual / style (numbers only) at 256x256 — teacher-forced."""
+    trainer, nets, steps, synth = _imports()
+    from gan_inpainting_b200.lib.models import loss, networks
+    from oracle import vgg_losses
+
+    R, B = 256, 4
+    ground, mask = synth.make_batch(B, R, seed=31, soft_edge=True)
+    gp, dp = nets.init_unet(0), nets.init_patchgan(1, res=R)
+    G, D = make_G(dev, gp).train(), make_D(dev, dp, R, False).train()
+    feats = vgg_losses.seeded_vgg_features(11)
+    w = networks.VGG19Wrapper()
+    w.vgg19.features.load_state_dict(feats.state_dict())
+    loss.set_vgg(w.to(dev).eval())
+    try:
+        tr = trainer.InpaintingTrainer("wgan", G, D, recon="rmse", tv_weight=1.0, feature_weights=(0.01, 0.01), local_recon="mse")
+        tr.step(ground.to(dev), mask.to(dev), update_g=True)
+        s = tr.read_scalars()
+    finally:
+        loss.set_vgg(None)
+    cl = lambda p: steps.enable_grad({k: v.clone() for k, v in p.items()})
+    pol = forced_policy(tr, nets)
+    G_, D_ = cl(gp), cl(dp)
+    d_post = {}
+    o = steps.wgan_step(G_, D_, steps.make_optimizer("rmsprop", G_), steps.make_optimizer("rmsprop", D_), ground, mask, recon="rmse", policy=pol,
+                        after_d_step=adopt_params(D, d_post), tv_weight=1.0, vgg_features=feats, feature_weights=(0.01, 0.01), local_recon="mse")
+    assert rel(tr.last["inpainted"], o["inpainted"]) < 1e-4
+    for k in ("g_adv", "recon", "recon_local", "g_tv", "g_loss"):
+        assert close(s[k], o[k], 2e-3), (k, s[k], o[k])
+    for k in ("g_perceptual", "g_style"):  # bf16 storage through 13 convolutions; the oracle emulates it under a policy
+        assert s[k] > 0 and close(s[k], o[k], 2e-2, floor=0.0), (k, s[k], o[k])
+    assert abs(s["g_loss"] - (s["g_adv"] + s["recon"] + s["recon_local"] + s["g_tv"] + s["g_perceptual"] + s["g_style"])) < 1e-5 * max(1.0, abs(s["g_loss"]))
+    check_grads(tr.fG, o["g_grads"], what="G grads with TV + local terms (teacher-forced)")
+    check_params(G, G_, RMSPROP_STEP, what="G after RMSprop")
+    # the extra terms really reach the gradient: the same step without them gives different G gradients
+    G2, D2 = make_G(dev, gp).train(), make_D(dev, dp, R, False).train()
+    tr2 = trainer.InpaintingTrainer("wgan", G2, D2, recon="rmse")
+    tr2.step(ground.to(dev), mask.to(dev), update_g=True)
+    assert rel(tr2.fG.grads, tr.fG.grads) > 1e-3
+
+
 def test_wgan_d_only_step(dev):
     """4 of 5 steady-state batches skip the G update (wgan_l1.py:157-163)."""
     trainer, nets, steps, synth = _imports()
