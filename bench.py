@@ -298,7 +298,9 @@ def run_b200(args):
     if world > 1:
         import torch.distributed as dist
 
-        dist.init_process_group("nccl", device_id=dev)
+        from gan_inpainting_b200.trainer import nccl_group_options
+
+        dist.init_process_group("nccl", device_id=dev, pg_options=nccl_group_options(args.nccl_ctas))
     from gan_inpainting_b200 import _lib, build
     from gan_inpainting_b200.lib.models import networks
     from gan_inpainting_b200.data import DevicePrefetcher, synthetic_batch
@@ -527,6 +529,7 @@ def run_b200(args):
                    "dropout": not infer, "l2": "no flush: one step streams several GB of activations/gradients, far larger than the 126 MB L2",
                    "bn": "running statistics (eval)" if infer else "per-replica batch statistics", "bucket_mb": args.bucket_mb,
                    "grad_wire": ("bf16" if getattr(tr, "wire_bf16", False) else "fp32") if world > 1 else None,
+                   "nccl_ctas": (args.nccl_ctas if args.nccl_ctas is not None else int(os.environ.get("B200_NCCL_CTAS", "0"))) if world > 1 else 0,
                    "comm_sms": (args.comm_sms if args.comm_sms is not None else int(os.environ.get("B200_COMM_SMS", "0"))) if world > 1 else 0,
                    "launch": "eager (one ctypes call per kernel)" if (args.no_graph or infer) else "whole step replayed as one CUDA graph"},
         "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / args.steps},
@@ -554,6 +557,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=4, help="images per step of the bounded CPU sample")
     ap.add_argument("--bucket-mb", type=float, default=25.0)
     ap.add_argument("--comm-sms", type=int, default=None, help="SMs kept free for the gradient all-reduces while they are in flight (default: B200_COMM_SMS or 0 = none)")
+    ap.add_argument("--nccl-ctas", type=int, default=None, help="cap on NCCL's thread blocks per collective (default: B200_NCCL_CTAS or 0 = NCCL's own choice)")
     ap.add_argument("--grad-wire", default=None, choices=["fp32", "bf16"], help="dtype of the gradient buckets on the wire (default: B200_GRAD_WIRE or fp32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the short D-only / inference measurements of the default run")

@@ -68,7 +68,7 @@ SIGNATURES = {
     # ---- SSIM metric (csrc/ssim.cu)
     "b200_ssim": [P, P, I, I, I, I, POINTER(c_float), I, P, P, S],
     # ---- VGG19 feature losses (csrc/conv_gemm.cu conv3 / gram modes, csrc/vgg.cu)
-    "b200_conv3_gemm": [P, I, I, I, I, I, P, P, I, P, I, I, S],
+    "b200_conv3_gemm": [P, I, I, I, I, I, P, P, I, P, I, I, I, S],
     "b200_pack_conv3": [P, I, I, P, S],
     "b200_conv3_c1_fwd": [P, I, I, I, P, P, I, P, S],
     "b200_maxpool2": [P, I, I, I, I, P, S],

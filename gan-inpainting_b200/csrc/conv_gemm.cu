@@ -88,6 +88,7 @@ struct IGemmParams {
   int sa;                // window slots of the activation ring (win)
   int tpb;               // filter taps (weight boxes) per stage of the weight ring (win); `stages` counts the weight stages
   const float* bias;     // MODE_CONV3: per-output-channel bias added before the ReLU of the epilogue
+  int pool;              // MODE_CONV3: 2 x 2 max-pool fused into the epilogue (the output tensor is [B, Hs/2, Ws/2, ldc])
   int gram;              // MODE_WGRAD without taps: the second operand is read at the SAME pixels as the first (tmB is a plain NHWC map),
                          // G[cs][cl] = sum_pixels S[pix][cs] * L[pix][cl]; one split per image gives the per-image Gram matrices of
                          // lib/models/loss.py:117-136
@@ -296,6 +297,11 @@ __device__ __forceinline__ void igemm_teardown(bool tmem_owner, uint32_t tmem_ba
 // 128-bit LDS / STS), the transposed column sums, the cp.async operand loads and the TMA store.
 //   bf16 tile: 32 rows x 64 B, 16-byte chunk j of row r at  r * 64 + ((j ^ ((r >> 1) & 3)) * 16)       (SWIZZLE_64B)
 //   fp32 tile: 32 rows x 128 B, chunk j of row r at         r * 128 + ((j ^ (r & 7)) * 16)            (SWIZZLE_128B)
+__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
 __device__ __forceinline__ void stage_bf16_row(uint8_t* tile, const uint32_t (&o)[16], int lane) {
   const int sw = (lane >> 1) & 3;
   uint4* rowp = reinterpret_cast<uint4*>(tile + lane * 64);
@@ -843,6 +849,23 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             uint32_t o[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) o[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+            if (!E::BWD && E::ACT == ACT_FWD_BIAS_RELU && p.pool) {
+              // MaxPool2d(2, 2) of the layer's output without the output ever reaching memory: a warp's 32 accumulator rows are
+              // 4 image rows x 8 pixels (lane = 8 * row + column), so the 2 x 2 window of a pooled pixel is lanes {l, l^1, l^8, l^9};
+              // the 2 x 4 pooled pixels of the warp are staged as an 8-row tile and leave through one TMA store
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const uint32_t t = max_bf16x2(o[j], __shfl_xor_sync(0xffffffffu, o[j], 1));
+                o[j] = max_bf16x2(t, __shfl_xor_sync(0xffffffffu, t, 8));
+              }
+              if (!(lane & 9)) stage_bf16_row(zbuf, o, ((lane >> 4) << 2) | ((lane & 7) >> 1));
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_4d(&tmO, zbuf, c.n0 + cc, c.w0 >> 1, (c.h0 + hq) >> 1, c.b0);
+                tma_store_commit();
+              }
+            } else {
             stage_bf16_row(zbuf, o, lane);
             fence_proxy_async();
             __syncwarp();
@@ -850,6 +873,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               if (convt) tma_store_5d(&tmO, zbuf, ph_q * p.ldc + c.n0 + cc, c.w0, ph_p, c.h0 + hq, c.b0);
               else tma_store_4d(&tmO, zbuf, c.n0 + cc, c.w0, c.h0 + hq, c.b0);
               tma_store_commit();
+            }
             }
             if (E::STATS && E::BWD) {  // unfused columns of a fused-backward GEMM carry no statistics
               if (first_ph) {
@@ -1151,14 +1175,14 @@ static int map_nhwc_parity(CUtensorMap* m, const void* base, int B, int H, int W
 // `ld` channels per pixel and elements of `esize` bytes (2: bf16 tile, SWIZZLE_64B; 4: fp32 tile, SWIZZLE_128B).
 //   plain:  [ld, W, H, B], box [32, 8, 4, 1]           (stride-2 convolution: output pixel = accumulator row)
 //   parity: [2 ld, W/2, 2, H/2, B], box [32, 8, 1, 4, 1] (transposed convolution: accumulator row (i, j) of phase (p, q) is pixel (2i+p, 2j+q))
-static int map_store(CUtensorMap* m, const void* base, int B, int H, int W, int ld, int esize, bool parity) {
+static int map_store(CUtensorMap* m, const void* base, int B, int H, int W, int ld, int esize, bool parity, bool pooled = false) {
   const CUtensorMapDataType dt = esize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   const CUtensorMapSwizzle sw = esize == 4 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   const cuuint64_t e = (cuuint64_t)esize;
   if (!parity) {
     cuuint64_t dims[4] = {(cuuint64_t)ld, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t st[3] = {(cuuint64_t)ld * e, (cuuint64_t)W * ld * e, (cuuint64_t)H * W * ld * e};
-    cuuint32_t box[4] = {32, 8, 4, 1};
+    cuuint32_t box[4] = {32, pooled ? 4u : 8u, pooled ? 2u : 4u, 1};  // pooled: the 2 x 4 pooled pixels of a warp's 4 x 8 pixels
     return encode(m, base, 4, dims, st, box, dt, sw);
   }
   cuuint64_t dims[5] = {(cuuint64_t)2 * ld, (cuuint64_t)W / 2, 2, (cuuint64_t)H / 2, (cuuint64_t)B};
@@ -1568,8 +1592,9 @@ int b200_convt_s2_gemm(const void* z, int B, int Hi, int Wi, int Cin, int ldz, c
 
 // y[B,H,W,ldy] (bf16) = relu(conv3x3/s1/p1(x[B,H,W,Cin] (pixel stride ldx), wpk[Cout][9*Cin] bf16 with k = (kh*3+kw)*Cin + ci) + bias)
 // (relu == 0: no activation is not offered — every VGG19 convolution is followed by ReLU(inplace), loss.py:61-66).
-int b200_conv3_gemm(const void* x, int B, int H, int W, int Cin, int ldx, const void* wpk, const float* bias, int Cout, void* y, int ldy, int bn_hint,
-                    cudaStream_t stream) {
+// pool != 0: y [B,H/2,W/2,ldy] = MaxPool2d(2, 2) of that result, fused into the epilogue (vgg19.features' conv -> ReLU -> MaxPool runs).
+int b200_conv3_gemm(const void* x, int B, int H, int W, int Cin, int ldx, const void* wpk, const float* bias, int Cout, void* y, int ldy, int pool,
+                    int bn_hint, cudaStream_t stream) {
   if (!is_pow2(H) || !is_pow2(W) || H < kWinTh || W < kWinTw || Cin % 64 || Cout % 32 || ldy % 8 || ldx % 8 || B < 1) {
     b200_set_error("conv3_gemm: needs power-of-two H >= 16, W >= 8, Cin % 64 == 0, Cout % 32 == 0");
     return B200_ERR_ARG;
@@ -1602,6 +1627,7 @@ int b200_conv3_gemm(const void* x, int B, int H, int W, int Cin, int ldx, const 
   p.num_tiles = p.num_ptiles * p.n_tiles;
   p.stats = nullptr;
   p.bias = bias;
+  p.pool = pool ? 1 : 0;
   p.bwd = EpiBwd{};
   p.ksplit = 1;
   p.partial = nullptr;
@@ -1613,7 +1639,7 @@ int b200_conv3_gemm(const void* x, int B, int H, int W, int Cin, int ldx, const 
   if ((rc = map_nhwc(&ta, x, B, H, W, Cin, ldx, p.tw + 2, p.th + 2, p.nb))) return rc;
   if ((rc = map_weights(&tb, wpk, Cout, 9 * Cin, p.pair ? p.BN / 2 : p.BN))) return rc;
   StoreMaps sm{};
-  if ((rc = map_store(&sm.out, y, B, H, W, ldy, 2, false))) return rc;
+  if ((rc = pool ? map_store(&sm.out, y, B, H / 2, W / 2, ldy, 2, false, true) : map_store(&sm.out, y, B, H, W, ldy, 2, false))) return rc;
   return launch(ta, tb, sm, p, stream, nullptr);
 }
 

@@ -644,6 +644,7 @@ class VggFeatureEngine:
         self.packed: Dict[int, torch.Tensor] = {}
         self.w1 = None
         self._versions = None
+        self.fuse_pool = True  # tests switch it off to compare with the separate max-pool kernel
 
     def refresh_weights(self):
         convs = [self.features[i] for kind, i in self.plan if kind == "conv"]
@@ -682,7 +683,8 @@ class VggFeatureEngine:
         self.refresh_weights()
         outs, h, first = [], None, True
         C = 0
-        for kind, i in self.plan:
+        fused_pools = set()
+        for n, (kind, i) in enumerate(self.plan):
             if kind == "conv":
                 c = self.features[i]
                 bias = c.bias.data.float() if c.bias is not None else None
@@ -692,11 +694,17 @@ class VggFeatureEngine:
                     C, first = 64, False
                 else:
                     cout = c.out_channels
-                    y = _empty((B, H, W, cout), bf16, x.device)
+                    # conv -> ReLU -> MaxPool whose un-pooled activation nobody reads: the pool runs in the GEMM epilogue
+                    pool = (n + 2 < len(self.plan) and self.plan[n + 1][0] == "relu" and self.plan[n + 2][0] == "pool"
+                            and self.plan[n + 1][1] not in VGG_FEATURE_LAYERS and self.fuse_pool)
+                    Ho, Wo = (H // 2, W // 2) if pool else (H, W)
+                    y = _empty((B, Ho, Wo, cout), bf16, x.device)
                     mt = B * (H // 16) * (W // 8)
-                    call("b200_conv3_gemm", ptr(h), B, H, W, C, C, ptr(self.packed[i]), ptr(bias), cout, ptr(y), cout, pick_bn(mt, cout), stream())
-                    h, C = y, cout
-            elif kind == "pool":
+                    call("b200_conv3_gemm", ptr(h), B, H, W, C, C, ptr(self.packed[i]), ptr(bias), cout, ptr(y), cout, int(pool), pick_bn(mt, cout), stream())
+                    h, C, H, W = y, cout, Ho, Wo
+                    if pool:
+                        fused_pools.add(self.plan[n + 2][1])
+            elif kind == "pool" and i not in fused_pools:
                 y = _empty((B, H // 2, W // 2, C), bf16, x.device)
                 call("b200_maxpool2", ptr(h), B, H, W, C, ptr(y), stream())
                 h, H, W = y, H // 2, W // 2

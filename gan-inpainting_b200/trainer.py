@@ -123,6 +123,29 @@ class GradBucketer:
         return n
 
 
+def nccl_group_options(max_ctas: Optional[int] = None):
+    """``pg_options`` for ``torch.distributed.init_process_group("nccl", ...)`` that cap the thread blocks NCCL may use per
+    collective (``B200_NCCL_CTAS`` when ``max_ctas`` is None; 0 / unset = NCCL's default).
+
+    Why: the persistent tcgen05 GEMMs own all 227 KB of shared memory of every SM they run on, so an all-reduce block and a GEMM
+    block never share an SM — whichever is resident first keeps it.  With a static tile schedule a GEMM whose block has to wait for
+    an all-reduce block (100+ us per 25 MB bucket) is stretched by that wait.  Capping NCCL at k blocks and keeping k SMs out of the
+    GEMM grids (``comm_sms=k`` -> ``b200_set_sm_limit``) gives each side its own SMs; the 178 MB of gradients per step need only
+    ~30 GB/s to stay hidden behind the backward pass."""
+    import os
+
+    import torch.distributed as dist
+
+    if max_ctas is None:
+        max_ctas = int(os.environ.get("B200_NCCL_CTAS", "0"))
+    if max_ctas <= 0:
+        return None
+    opts = dist.ProcessGroupNCCL.Options()
+    opts.config.max_ctas = int(max_ctas)
+    opts.config.min_ctas = 1
+    return opts
+
+
 class InpaintingTrainer:
     def __init__(self, recipe: str, net_G, net_D, net_D_local=None, recon: str = "l1", lambdas=(300.0, 300.0), clip: float = 0.01,
                  distributed: bool = False, bucket_mb: float = 25.0, log_grad_means: bool = False, graph: bool = False, rank: Optional[int] = None,

@@ -245,9 +245,11 @@ int b200_tv_loss_bwd(const float* img, long long planes, int H, int W, float wei
  * ------------------------------------------------------------------------------------------------------------------ */
 /* nn.Conv2d(Cin, Cout, 3, 1, 1) + ReLU(inplace) of vgg19.features (window operand staging: the nine taps are descriptors into one
  * 18 x 10-pixel halo window per 64-channel block).  x [B,H,W,Cin] bf16 (pixel stride ldx), wpk [Cout][9*Cin] from b200_pack_conv3,
- * bias [Cout] fp32 or NULL; y [B,H,W,*] (pixel stride ldy).  H >= 16, W >= 8, powers of two; Cin % 64 == 0; Cout % 32 == 0. */
-int b200_conv3_gemm(const void* x, int B, int H, int W, int Cin, int ldx, const void* wpk, const float* bias, int Cout, void* y, int ldy, int bn_hint,
-                    b200_stream_t stream);
+ * bias [Cout] fp32 or NULL; y [B,H,W,*] (pixel stride ldy).  H >= 16, W >= 8, powers of two; Cin % 64 == 0; Cout % 32 == 0.
+ * pool != 0: the nn.MaxPool2d(2, 2) that follows the ReLU is fused into the epilogue and y is [B,H/2,W/2,*] — the full-resolution
+ * output never reaches memory. */
+int b200_conv3_gemm(const void* x, int B, int H, int W, int Cin, int ldx, const void* wpk, const float* bias, int Cout, void* y, int ldy, int pool,
+                    int bn_hint, b200_stream_t stream);
 /* fp32 [Cout][Cin][3][3] (torch layout) -> bf16 [Cout][(kh*3+kw)*Cin + ci] */
 int b200_pack_conv3(const float* w, int Cout, int Cin, void* out, b200_stream_t stream);
 /* vgg19.features[0..1] on `img.repeat(1,3,1,1)` (loss.py:55-56): x fp32 [B,H,W], w1 [64][9] = the filters summed over their 3 input

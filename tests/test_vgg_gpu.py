@@ -55,11 +55,31 @@ def test_conv3_bias_relu(dev, B, H, W, Cin, Cout):
     y = torch.full((B, H, W, Cout), float("nan"), dtype=torch.bfloat16, device=dev)
     for hint in (0, eng.pick_bn(B * (H // 16) * (W // 8), Cout)):
         y.fill_(float("nan"))
-        lib.call("b200_conv3_gemm", lib.ptr(xh), B, H, W, Cin, Cin, lib.ptr(_pack3(w)), lib.ptr(b), Cout, lib.ptr(y), Cout, hint, lib.stream())
+        lib.call("b200_conv3_gemm", lib.ptr(xh), B, H, W, Cin, Cin, lib.ptr(_pack3(w)), lib.ptr(b), Cout, lib.ptr(y), Cout, 0, hint, lib.stream())
         got = nchw(y).float()
         assert torch.isfinite(got).all()
         assert rel(got, ref) < BF16_TOL, (hint, rel(got, ref))
         assert (got >= 0).all()
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 256, 256, 64, 64), (3, 64, 64, 128, 128), (2, 32, 32, 256, 256), (5, 16, 8, 512, 512), (64, 32, 32, 512, 512)])
+def test_conv3_fused_maxpool_equals_separate_kernels(dev, B, H, W, Cin, Cout):
+    """conv -> bias -> ReLU -> MaxPool2d(2, 2) in one launch: bit-identical to the un-pooled launch followed by b200_maxpool2 (max of
+    bf16-rounded values == bf16 rounding of the max: rounding is monotonic)."""
+    lib, eng = _api()
+    torch.manual_seed(Cin + H)
+    x = bf(torch.randn(B, H, W, Cin, device=dev))
+    w = torch.randn(Cout, Cin, 3, 3, device=dev) * (2.0 / (9 * Cin)) ** 0.5
+    b = torch.randn(Cout, device=dev) * 0.2
+    pk = _pack3(w)
+    full = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device=dev)
+    lib.call("b200_conv3_gemm", lib.ptr(x), B, H, W, Cin, Cin, lib.ptr(pk), lib.ptr(b), Cout, lib.ptr(full), Cout, 0, 0, lib.stream())
+    ref = torch.empty(B, H // 2, W // 2, Cout, dtype=torch.bfloat16, device=dev)
+    lib.call("b200_maxpool2", lib.ptr(full), B, H, W, Cout, lib.ptr(ref), lib.stream())
+    for hint in (0, 64, eng.pick_bn(B * (H // 16) * (W // 8), Cout)):
+        got = torch.full_like(ref, float("nan"))
+        lib.call("b200_conv3_gemm", lib.ptr(x), B, H, W, Cin, Cin, lib.ptr(pk), lib.ptr(b), Cout, lib.ptr(got), Cout, 1, hint, lib.stream())
+        assert torch.equal(got, ref), (hint, float((got.float() - ref.float()).abs().max()))
 
 
 def test_conv3_strided_input_and_output(dev):
@@ -71,7 +91,7 @@ def test_conv3_strided_input_and_output(dev):
     w = torch.randn(Cout, Cin, 3, 3, device=dev) * 0.06
     b = torch.zeros(Cout, device=dev)
     out = torch.zeros(B, H, W, 192, dtype=torch.bfloat16, device=dev)
-    lib.call("b200_conv3_gemm", lib.ptr(buf), B, H, W, Cin, 128, lib.ptr(_pack3(w)), lib.ptr(b), Cout, lib.ptr(out), 192, 0, lib.stream())
+    lib.call("b200_conv3_gemm", lib.ptr(buf), B, H, W, Cin, 128, lib.ptr(_pack3(w)), lib.ptr(b), Cout, lib.ptr(out), 192, 0, 0, lib.stream())
     ref = torch.relu(F.conv2d(nchw(buf[..., :64]).float(), bf(w).float(), b, padding=1))
     assert rel(nchw(out[..., :64]).float(), ref) < BF16_TOL
     assert float(out[..., 64:].abs().max()) == 0.0
@@ -81,7 +101,7 @@ def test_conv3_rejects_unsupported_shapes(dev):
     lib, _ = _api()
     x = torch.zeros(1, 8, 8, 64, dtype=torch.bfloat16, device=dev)
     with pytest.raises(lib.B200Error):
-        lib.call("b200_conv3_gemm", lib.ptr(x), 1, 8, 8, 64, 64, lib.ptr(x), lib.ptr(x), 64, lib.ptr(x), 64, 0, lib.stream())
+        lib.call("b200_conv3_gemm", lib.ptr(x), 1, 8, 8, 64, 64, lib.ptr(x), lib.ptr(x), 64, lib.ptr(x), 64, 0, 0, lib.stream())
 
 
 @pytest.mark.parametrize("B,H,W", [(2, 256, 256), (3, 32, 64), (1, 16, 8)])
@@ -185,6 +205,10 @@ def test_vgg_feature_maps_match_oracle(dev):
     w = _wrapper(dev)
     out, _ = _images(dev, 2, 256, 3)
     feats = w._get_engine().features_of(out)
+    w._get_engine().fuse_pool = False  # the separate max-pool kernel gives the same bits
+    for a, b in zip(feats, w._get_engine().features_of(out)):
+        assert torch.equal(a, b)
+    w._get_engine().fuse_pool = True
     ref = vgg_losses.feature_maps(w.vgg19.features, out)
     emu = vgg_losses.feature_maps(w.vgg19.features, out, bf16=True)
     assert len(feats) == 5
