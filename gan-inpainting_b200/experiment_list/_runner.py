@@ -66,7 +66,8 @@ def _logger(title: str, log_dir: str, to_file: bool = True) -> logging.Logger:
 
 
 def run(state: dict, loaders: dict, title: str, recipe: str, recon: str, schedule: Callable[[int, int], bool], local_d: bool = False,
-        lambdas=(300.0, 300.0)) -> Dict[str, object]:
+        lambdas=(300.0, 300.0), loss_terms: Optional[dict] = None) -> Dict[str, object]:
+    """``loss_terms``: extra generator loss terms for ``InpaintingTrainer`` (``tv_weight``, ``feature_weights``, ``local_recon``)."""
     state = state.copy()
     state.update({"title": title})
     train_loader, test_loader = loaders["train"], loaders.get("test")
@@ -93,7 +94,7 @@ def run(state: dict, loaders: dict, title: str, recipe: str, recon: str, schedul
     net_D = networks.PatchGANDiscriminator(sigmoid=sigmoid, imagedim=R).to(device)
     net_Dl = networks.PatchGANDiscriminator(sigmoid=sigmoid, imagedim=R).to(device) if local_d else None
     tr = InpaintingTrainer(recipe, net_G, net_D, net_Dl, recon=recon, lambdas=lambdas, distributed=distributed,
-                           bucket_mb=float(state.get("bucket_mb", 25.0)), log_grad_means=True, graph=bool(state.get("graph", True)))
+                           bucket_mb=float(state.get("bucket_mb", 25.0)), log_grad_means=True, graph=bool(state.get("graph", True)), **(loss_terms or {}))
     g_names = [n for n, _ in net_G.named_parameters() if "bias" not in n]
     d_names = [n for n, _ in net_D.named_parameters() if "bias" not in n]
     evaluate_fn: Optional[Callable] = state.get("evaluate_fn")
@@ -107,6 +108,8 @@ def run(state: dict, loaders: dict, title: str, recipe: str, recon: str, schedul
     for epoch in range(num_epochs + 1):
         start = time.time()
         eg = {"total": 0.0, "recon": 0.0, "adv": 0.0, "update_count": 0}
+        if loss_terms:  # wgan_perceptual_style_faceparsing.py logs every term of g_loss
+            eg.update({"recon_local": 0.0, "tv": 0.0, "perceptual": 0.0, "style": 0.0})
         ed = {"total": 0.0, "adv_real": 0.0, "adv_fake": 0.0, "update_count": 0}
         gh = {"avg_g": {n: 0.0 for n in g_names}, "avg_d": {n: 0.0 for n in d_names}}
         ssim_acc, n_images = torch.zeros((), dtype=torch.float32, device=device), 0  # experiment1_global_local_D.py:135,209
@@ -128,6 +131,11 @@ def run(state: dict, loaders: dict, title: str, recipe: str, recon: str, schedul
                 eg["recon"] += s["recon"]
                 eg["adv"] += s["g_adv"] + (s["g_adv_local"] if local_d else 0.0)
                 eg["update_count"] += 1
+                if loss_terms:
+                    eg["recon_local"] += s["recon_local"]
+                    eg["tv"] += s["g_tv"]
+                    eg["perceptual"] += s["g_perceptual"]
+                    eg["style"] += s["g_style"]
                 for n, v in tr.grad_means_host("g").items():
                     if n in gh["avg_g"]:
                         gh["avg_g"][n] += v
@@ -140,12 +148,12 @@ def run(state: dict, loaders: dict, title: str, recipe: str, recon: str, schedul
                 if n in gh["avg_d"]:
                     gh["avg_d"][n] += v
         if eg["update_count"]:
-            for k in ("total", "recon", "adv"):
+            for k in [k for k in eg if k != "update_count"]:
                 eg[k] /= eg["update_count"]
             for n in g_names:
                 gh["avg_g"][n] /= eg["update_count"]
         else:  # generator never updated in this epoch
-            for k in ("total", "recon", "adv"):
+            for k in [k for k in eg if k != "update_count"]:
                 eg[k] = SENTINEL
             for n in g_names:
                 gh["avg_g"][n] = SENTINEL

@@ -45,7 +45,9 @@ def calculate_metric(device, loader, net, fid_stats=None, mode="test", inception
         if is_flip_mask:  # evaluate.py:131-132
             m = 1.0 - m
             call("b200_mask_prepare", ptr(ground), ptr(m), n, 0, None, ptr(masked), stream())
-        out = eng.forward(masked, net.training, comp_base=masked, comp_mul=m, keep=False).comp
+        # the reference never calls .eval(): in train mode every batch draws its own dropout masks
+        seed = net._next_seed() if (net.training and hasattr(net, "_next_seed")) else 0
+        out = eng.forward(masked, net.training, comp_base=masked, comp_mul=m, seed=seed, keep=False).comp
         for i, kind in enumerate((RECON_RMSE, RECON_L1, RECON_LOCAL_MSE, RECON_LOCAL_L1)):
             call("b200_recon_loss", kind, ptr(ground), ptr(out), ptr(m) if kind >= RECON_LOCAL_L1 else None, n, float(eps), ptr(sc.recon), ptr(slot[i]), stream())
         vals = slot[:, 0].clone()

@@ -3,6 +3,7 @@ step of the CUDA path against the pure-fp32 oracle (oracle.steps, restating wgan
 experiment1_global_local_D.py:139-200), at BASELINE.json's configs:
 
     C1  experiment1_global_local_D  128x128, batch 8        C2  wgan_l1  256x256, batch 64      C3  minimaxgan_rmse  256x256, batch 64
+    C4  wgan + RMSE + local MSE + TV + VGG19 perceptual / style (random-init VGG19), 256x256, batch 32
 
     python -m tests.parity_report [--out profiles/parity_r2.json] [--cases C1,C2,C3,...]
 
@@ -36,7 +37,10 @@ CASES = {
     "C1w": ("wgan", "l1", 128, 8, 21),
     "C2": ("wgan", "l1", 256, 64, 31),
     "C3": ("minimax", "rmse", 256, 64, 33),
+    # config 4's generator loss without its face-parsing term (wgan_perceptual_style_faceparsing.py:208-221)
+    "C4": ("wgan", "rmse", 256, 32, 35, dict(tv_weight=1.0, feature_weights=(0.01, 0.01), local_recon="mse")),
 }
+VGG_SEED = 11
 
 
 def _rel(a, b):
@@ -73,9 +77,10 @@ def _recording(nets, base=None):
     return RecordingPolicy()
 
 
-def _run_oracle(steps, recipe, recon, params, ground, mask, policy, hooks=None):
+def _run_oracle(steps, recipe, recon, params, ground, mask, policy, hooks=None, extras=None):
     cl = lambda p: steps.enable_grad({k: v.clone() for k, v in p.items()})
     hooks = hooks or {}
+    extras = extras or {}
     if recipe == "global_local":
         G, Dg, Dl = cl(params["G"]), cl(params["D"]), cl(params["Dl"])
         o = steps.global_local_step(G, Dg, Dl, steps.make_optimizer("adam", G), steps.make_optimizer("adam", Dl, Dg), ground, mask, policy=policy)
@@ -84,7 +89,7 @@ def _run_oracle(steps, recipe, recon, params, ground, mask, policy, hooks=None):
     G, D = cl(params["G"]), cl(params["D"])
     if recipe == "wgan":
         o = steps.wgan_step(G, D, steps.make_optimizer("rmsprop", G), steps.make_optimizer("rmsprop", D), ground, mask, recon=recon, policy=policy,
-                            after_d_step=hooks.get("after_d_step"))
+                            after_d_step=hooks.get("after_d_step"), **extras)
     else:
         o = steps.minimax_step(G, D, steps.make_optimizer("adam", G), steps.make_optimizer("adam", D), ground, mask, recon=recon, policy=policy,
                                after_d_step=hooks.get("after_d_step"))
@@ -95,8 +100,9 @@ LOSS_KEYS = {"wgan": ("d_loss_real", "d_loss_fake", "g_adv", "recon", "g_loss"),
              "global_local": ("g_adv", "g_adv_local", "recon", "recon_local", "g_loss", "d_loss")}
 
 
-def parity_case(dev, recipe, recon, R, B, seed, with_forced=True):
-    """One train step of the CUDA path and up to three oracle runs on the same inputs / weights.  Returns the table (dict)."""
+def parity_case(dev, recipe, recon, R, B, seed, extras=None, with_forced=True):
+    """One train step of the CUDA path and up to three oracle runs on the same inputs / weights.  Returns the table (dict).
+    ``extras``: the extra generator loss terms of config 4 (``InpaintingTrainer`` keywords)."""
     from gan_inpainting_b200 import trainer
     from oracle import nets, steps, synth
     from tests.test_networks_gpu import make_D, make_G
@@ -111,10 +117,23 @@ def parity_case(dev, recipe, recon, R, B, seed, with_forced=True):
     if recipe == "global_local":
         params["Dl"] = nets.init_patchgan(2, res=R)
         Dl = make_D(dev, params["Dl"], R, True).train()
-    tr = trainer.InpaintingTrainer(recipe, G, D, Dl, recon=recon)
+    oextras, loss_keys = {}, LOSS_KEYS[recipe]
+    if extras:
+        from gan_inpainting_b200.lib.models import loss, networks
+        from oracle import vgg_losses
+
+        feats = vgg_losses.seeded_vgg_features(VGG_SEED)
+        w = networks.VGG19Wrapper()
+        w.vgg19.features.load_state_dict(feats.state_dict())
+        loss.set_vgg(w.to(dev).eval())
+        oextras = dict(tv_weight=extras["tv_weight"], vgg_features=feats, feature_weights=extras["feature_weights"], local_recon=extras["local_recon"])
+        loss_keys = loss_keys + ("recon_local", "g_tv", "g_perceptual", "g_style")
+    tr = trainer.InpaintingTrainer(recipe, G, D, Dl, recon=recon, **(extras or {}))
     tr.step(ground.to(dev), mask.to(dev))
     s = tr.read_scalars()
     torch.cuda.synchronize()
+    if extras:
+        loss.set_vgg(None)
 
     stored = {}
     for scope, c in tr.last["ctx"].items():
@@ -129,10 +148,10 @@ def parity_case(dev, recipe, recon, R, B, seed, with_forced=True):
 
     t0 = time.time()
     p32 = _recording(nets)
-    o32, _ = _run_oracle(steps, recipe, recon, params, ground, mask, p32)
+    o32, _ = _run_oracle(steps, recipe, recon, params, ground, mask, p32, extras=oextras)
     t_oracle = time.time() - t0
     pem = _recording(nets, nets.Bf16Policy())
-    oem, _ = _run_oracle(steps, recipe, recon, params, ground, mask, pem)
+    oem, _ = _run_oracle(steps, recipe, recon, params, ground, mask, pem, extras=oextras)
 
     def grads_of(o):
         g = {"G": o["g_grads"], "D": o["d_grads"]}
@@ -141,12 +160,13 @@ def parity_case(dev, recipe, recon, R, B, seed, with_forced=True):
         return g
 
     g32, gem = grads_of(o32), grads_of(oem)
-    table = dict(recipe=recipe, recon=recon, res=R, batch=B, seed=seed, oracle_step_s=round(t_oracle, 2), activations={}, losses={}, grads={})
+    table = dict(recipe=recipe, recon=recon, res=R, batch=B, seed=seed, oracle_step_s=round(t_oracle, 2), activations={}, losses={}, grads={},
+                 extras={k: (list(v) if isinstance(v, tuple) else v) for k, v in (extras or {}).items()})
     table["image"] = dict(cuda=_rel(inpainted, o32["inpainted"]), emulated=_rel(oem["inpainted"], o32["inpainted"]))
     for k in sorted(p32.rec):
         if k in stored:
             table["activations"][k] = dict(cuda=_rel(stored[k], p32.rec[k]), emulated=_rel(pem.rec[k], p32.rec[k]))
-    for k in LOSS_KEYS[recipe]:
+    for k in loss_keys:
         ref = o32[k]
         table["losses"][k] = dict(value_cuda=s[k], value_fp32=ref, value_emulated=oem[k], cuda=abs(s[k] - ref) / max(abs(ref), 1e-30),
                                   emulated=abs(oem[k] - ref) / max(abs(ref), 1e-30))
@@ -166,11 +186,11 @@ def parity_case(dev, recipe, recon, R, B, seed, with_forced=True):
         hooks = {}
         if recipe != "global_local":
             hooks["after_d_step"] = adopt_params(D, {})
-        of, _ = _run_oracle(steps, recipe, recon, params, ground, mask, pol, hooks)
+        of, _ = _run_oracle(steps, recipe, recon, params, ground, mask, pol, hooks, extras=oextras)
         gf = grads_of(of)
         for k, e in pol.errors.items():
             table["activations"].setdefault(k, {})["forced"] = e
-        for k in LOSS_KEYS[recipe]:
+        for k in loss_keys:
             table["losses"][k]["forced"] = abs(s[k] - of[k]) / max(abs(of[k]), 1e-30)
             table["losses"][k]["value_forced"] = of[k]
         for net in gf:
@@ -195,7 +215,8 @@ def markdown(tables):
            "bf16 rounding at the CUDA path's storage points (what bf16 NHWC tiles + fp32 accumulation cost in ANY implementation), `forced` = teacher-forced",
            "(one-layer error / error against the exact fp32 VJP of the CUDA forward).  Full per-tensor numbers: `parity_r2.json`.", ""]
     for name, t in tables.items():
-        out.append(f"## {name}: {t['recipe']} ({t['recon']}), {t['res']}x{t['res']}, batch {t['batch']} — fp32 oracle step {t['oracle_step_s']} s on the host")
+        ex = " + local MSE + TV + VGG19 perceptual / style (random-init VGG19, seeded)" if t.get("extras") else ""
+        out.append(f"## {name}: {t['recipe']} ({t['recon']}){ex}, {t['res']}x{t['res']}, batch {t['batch']} — fp32 oracle step {t['oracle_step_s']} s on the host")
         out.append("")
         out.append("| quantity | cuda max (median) | emulated max (median) | forced max (median) | worst tensor (cuda) |")
         out.append("|---|---|---|---|---|")
@@ -214,7 +235,7 @@ def markdown(tables):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "parity_r2.json"))
-    ap.add_argument("--cases", default="C1,C1w,C2,C3")
+    ap.add_argument("--cases", default="C1,C1w,C2,C3,C4")
     args = ap.parse_args()
     from gan_inpainting_b200 import build
 
@@ -224,9 +245,8 @@ def main():
     dev = torch.device("cuda:0")
     tables = {}
     for name in args.cases.split(","):
-        recipe, recon, R, B, seed = CASES[name]
         t0 = time.time()
-        tables[name] = parity_case(dev, recipe, recon, R, B, seed)
+        tables[name] = parity_case(dev, *CASES[name])
         print(f"[parity] {name}: {json.dumps(tables[name]['summary'])}  ({time.time() - t0:.0f} s)", flush=True)
         torch.cuda.empty_cache()
     os.makedirs(os.path.dirname(args.out), exist_ok=True)

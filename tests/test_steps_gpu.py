@@ -400,6 +400,23 @@ def test_begin_call_surface(dev, tmp_path):
     from gan_inpainting_b200.experiment_list import experiment1_global_local_D
     out = experiment1_global_local_D.begin(dict(state, numepoch=0), {"train": batches, "test": batches, "extra": batches})
     assert 0.0 < out["history"][0]["g"]["ssim"] <= 1.0  # lib.pytorch_ssim per batch (experiment1_global_local_D.py:209)
+    # config 4 (wgan_perceptual_style_faceparsing.py) at 256x256: every batch updates G here so that the extra loss terms are logged
+    from gan_inpainting_b200.experiment_list import _runner, wgan_perceptual_style_faceparsing as cfg4
+    big = []
+    for i in range(2):
+        g, m = synth.make_batch(2, 256, seed=50 + i)
+        big.append((g, m, torch.zeros(2, 256, 256, dtype=torch.long)))
+    st4 = dict(state, numepoch=0, imagedim=256)
+    with pytest.raises(NotImplementedError):
+        cfg4.begin(dict(st4, segmentation_model=object()), {"train": big, "test": big, "extra": big})
+    orig = _runner.wgan_g_schedule
+    _runner.wgan_g_schedule = lambda update_g_every=5: _runner.every_batch
+    try:
+        out = cfg4.begin(dict(st4, segmentation_model=object(), ignore_segmentation_model=True), {"train": big, "test": big, "extra": big})
+    finally:
+        _runner.wgan_g_schedule = orig
+    g4 = out["history"][0]["g"]
+    assert g4["update_count"] == 2 and all(g4[k] > 0 for k in ("recon", "recon_local", "tv", "perceptual", "style"))
 
 
 def test_device_prefetcher_feeds_identical_batches(dev):

@@ -1,6 +1,5 @@
 #!/bin/bash
-# One gpurun call of round 2 (kept for reproducibility): max-pool fused into the 3x3 convolution epilogue — tests, per-layer table, config-4 bench.
+# One gpurun call of round 2 (kept for reproducibility): full GPU suite with the config-4 additions + the C4 parity table.
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_vgg_gpu.py -q -x > gpurun_out/r2_vgg_tests.log 2>&1; echo rc=$?; tail -8 gpurun_out/r2_vgg_tests.log
-timeout 300 python tools/vgg_table.py > gpurun_out/r2_vgg_table.txt 2>&1; tail -34 gpurun_out/r2_vgg_table.txt
-timeout 600 python bench.py --recipe wgan_perceptual_style --steps 20 --warmup 5 > gpurun_out/r2_bench_config4_n1.json 2> gpurun_out/r2_bench_config4_n1.err; cut -c1-300 gpurun_out/r2_bench_config4_n1.json; tail -3 gpurun_out/r2_bench_config4_n1.err
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_gpu.log 2>&1; echo rc=$?; tail -6 gpurun_out/r2_pytest_gpu.log
+timeout 600 python -m tests.parity_report --cases C4 --out gpurun_out/parity_r2_c4.json > gpurun_out/parity_c4.log 2>&1; tail -3 gpurun_out/parity_c4.log
