@@ -88,6 +88,8 @@ struct IGemmParams {
   int sa;                // window slots of the activation ring (win)
   int tpb;               // filter taps (weight boxes) per stage of the weight ring (win); `stages` counts the weight stages
   const float* bias;     // MODE_CONV3: per-output-channel bias added before the ReLU of the epilogue
+  int bres;              // MODE_CONV3 with a single N tile whose whole weight sequence fits the weight ring: the ring is filled once (first
+                         // tile) and stays resident — no weight traffic, no weight-stage hand-shakes for the CTA's other tiles
   int pool;              // MODE_CONV3: 2 x 2 max-pool fused into the epilogue (the output tensor is [B, Hs/2, Ws/2, ldc])
   int gram;              // MODE_WGRAD without taps: the second operand is read at the SAME pixels as the first (tmB is a plain NHWC map),
                          // G[cs][cl] = sum_pixels S[pix][cs] * L[pix][cl]; one split per image gives the per-image Gram matrices of
@@ -486,6 +488,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             else tma_load_4d_w(sW, &tmA, &fullA_bar[sa], cc * 64, c.w0 + ph_q - 1, c.h0 + ph_p - 1, c.b0);
           }
           for (int tg = 0; tg < win_taps(WIN); tg += p.tpb) {
+            if (WIN == 3 && p.bres && t != tile0) break;  // resident weights: loaded by the first tile
             mbar_wait(&empty_bar[sb], parb ^ 1u);
             if (!PAIR || rank == 0) mbar_arrive_expect_tx_w(&full_bar[sb], b_tx);
             for (int u = 0; u < p.tpb; ++u) {
@@ -618,7 +621,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tc_fence_after();
           const uint32_t w_lo = desc_lo(smem_u32(smem + sa * win_slot_bytes(WIN)), 16u);
           for (int tg = 0; tg < win_taps(WIN); tg += p.tpb) {
-            mbar_wait(&full_bar[sb], parb);
+            const bool resident = WIN == 3 && p.bres;  // the weight ring holds the whole sequence of a tile and is never refilled
+            if (!resident || lt == 0) mbar_wait(&full_bar[sb], parb);
             tc_fence_after();
             const uint32_t b_lo0 = desc_lo(smem_u32(smem_b + sb * stage_bytes), 16u);
             for (int u = 0; u < p.tpb; ++u) {
@@ -637,8 +641,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 umma_bf16_lo_w<kDescHiSw128 | (win_sbo(WIN) >> 4), kDescHiSw128 | (1024 >> 4), PAIR>(d_ph, a_lo + 2 * k, b_lo + 2 * k, idesc,
                                                                                                         (wi > 0 || tp > 0 || k > 0) ? 1u : 0u);
             }
-            if (PAIR) umma_commit_2cta_w(&empty_bar[sb]);
-            else umma_commit_w(&empty_bar[sb]);
+            if (!resident) {
+              if (PAIR) umma_commit_2cta_w(&empty_bar[sb]);
+              else umma_commit_w(&empty_bar[sb]);
+            }
             if (++sb == p.stages) {
               sb = 0;
               parb ^= 1u;
@@ -1349,6 +1355,15 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const StoreMaps& s
     ring_a = p.sa * slot;
     p.stages = fits(extra, p.sa);
     if (p.stages > 12) p.stages = 12;
+    p.bres = 0;
+    static const int bres_env = env_int("B200_BRES", 1);
+    if (p.win == 3 && p.n_tiles == 1 && bres_env) {
+      // e.g. conv1_2 (64 -> 64): 74 KB of weights were re-read from L2 for every 128-pixel tile (96 KB per tile with the window =
+      // 10.9 TB/s of L2 -> SM traffic, the limit).  With the ring sized to exactly one tile's weight sequence the stage index
+      // sequence repeats tile after tile, so the first tile's loads serve all of them.
+      const int steps = (taps / p.tpb) * p.cpt;
+      if (steps >= 2 && steps <= p.stages) p.bres = 1, p.stages = steps;
+    }
     if (2 * p.sa + 2 * p.stages + 4 > (kBarrierBytes - 16) / 8) {
       b200_set_error("igemm: too many pipeline barriers");
       return B200_ERR_ARG;
