@@ -1,5 +1,6 @@
 #!/bin/bash
-# One gpurun call of round 2 (kept for reproducibility): full GPU suite with the config-4 additions + the C4 parity table.
+# One gpurun call of round 2 (kept for reproducibility): ncu --set full of the first 3x3 tensor-core layer (conv1_2, 64 -> 64 at 256x256, 64 images).
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_gpu.log 2>&1; echo rc=$?; tail -6 gpurun_out/r2_pytest_gpu.log
-timeout 600 python -m tests.parity_report --cases C4 --out gpurun_out/parity_r2_c4.json > gpurun_out/parity_c4.log 2>&1; tail -3 gpurun_out/parity_c4.log
+timeout 300 python tools/vgg_table.py --reps 1 > gpurun_out/vgg_pre.txt 2>&1; tail -1 gpurun_out/vgg_pre.txt
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:igemm -c 1 -o gpurun_out/r2_conv3_c64 -f python tools/vgg_table.py --reps 1 > gpurun_out/ncu_conv3.log 2>&1; tail -2 gpurun_out/ncu_conv3.log
+ls -la gpurun_out/*.ncu-rep
