@@ -322,6 +322,12 @@ __host__ __device__ inline uint32_t make_idesc_bf16(int M, int N, int a_mn_major
 }
 
 // ---------------------------------------------------------------- small math helpers
+// 32 contiguous, 32-byte aligned bytes as ONE store (sm_100: STG.E.256): a full DRAM sector per lane
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&o)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]),
+               "r"(o[7])
+               : "memory");
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(256, 3) conv_c1_fwd_kernel(const float* __rest
   }
 
   const int kh = q >> 1, kw = (q & 1) * 2;  // taps 2q, 2q+1 (and +8: kh + 2)
+  const bool wide2 = y2 && !(ld2 & 15) && !(off2 & 15) && !((uintptr_t)y2 & 31);  // 32-byte aligned rows in the concat buffer
   int buf = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
     const int next = tile + gridDim.x;
@@ -142,15 +143,19 @@ __global__ void __launch_bounds__(256, 3) conv_c1_fwd_kernel(const float* __rest
           uint32_t o[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] = pack_bf16x2(acc[j][2 * half], acc[j][2 * half + 1]);
-          uint4* dst = reinterpret_cast<uint4*>(y + pix * C + q * CPL + 2 * hn);
-          dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-          dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+          // a lane's 16 consecutive channels are one 32-byte sector: one 256-bit store (sm_100 STG.256) instead of two half-sector ones
+          st_global_256(y + pix * C + q * CPL + 2 * hn, o);
           if (y2) {  // relu copy into the decoder's concat buffer (skip connection)
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = pack_bf16x2(fmaxf(acc[j][2 * half], 0.f), fmaxf(acc[j][2 * half + 1], 0.f));
-            uint4* dst2 = reinterpret_cast<uint4*>(y2 + pix * ld2 + off2 + q * CPL + 2 * hn);
-            dst2[0] = make_uint4(o[0], o[1], o[2], o[3]);
-            dst2[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            __nv_bfloat16* d2 = y2 + pix * ld2 + off2 + q * CPL + 2 * hn;
+            if (wide2) {
+              st_global_256(d2, o);
+            } else {
+              uint4* dst2 = reinterpret_cast<uint4*>(d2);
+              dst2[0] = make_uint4(o[0], o[1], o[2], o[3]);
+              dst2[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            }
           }
         }
       }
@@ -607,8 +612,8 @@ int b200_conv_c1_fwd(const float* x, const float* xmul, int B, int H, int W, con
   int tow_shift = 5;  // 8 x 32 output tile; 16 x 16 when the image is only 16 pixels wide
   if (Wo < 32) tow_shift = 4;
   const int TOW = 1 << tow_shift, TOH = 256 >> tow_shift;
-  if ((C != 64 && C != 128) || (H & 1) || (W & 1) || B < 1 || ld2 % 8 || off2 % 8 || Wo % TOW || Ho % TOH) {
-    b200_set_error("conv_c1_fwd: C must be 64/128; output must tile by 8x32 (or 16x16); concat stride / offset multiples of 8");
+  if ((C != 64 && C != 128) || (H & 1) || (W & 1) || B < 1 || ld2 % 8 || off2 % 8 || Wo % TOW || Ho % TOH || ((uintptr_t)y & 31)) {
+    b200_set_error("conv_c1_fwd: C must be 64/128; output must tile by 8x32 (or 16x16); concat stride / offset multiples of 8; y 32-byte aligned");
     return B200_ERR_ARG;
   }
   const int ntiles = B * (Ho / TOH) * (Wo / TOW);

@@ -176,9 +176,15 @@ struct ApplyParams {
   const uint32_t* seed_ctr;  // optional device counter (b200_set_seed_counter)
 };
 
-__device__ __forceinline__ void bn_act_one(const ApplyParams& p, uint32_t seed, unsigned idx, unsigned cmask, const uint4 v) {
+__device__ __forceinline__ void load_coef8(const float* __restrict__ p, float (&o)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+  o[0] = a.x, o[1] = a.y, o[2] = a.z, o[3] = a.w, o[4] = b.x, o[5] = b.y, o[6] = b.z, o[7] = b.w;
+}
+
+// sc / sh: this thread's 8 channels of scale / shift.  A thread keeps its channel group for the whole grid-stride loop (the stride,
+// gridDim.x * 256, is a multiple of C / 8 <= 256), so they are loaded ONCE per thread instead of four 16-byte loads per 16 bytes of data.
+__device__ __forceinline__ void bn_act_one(const ApplyParams& p, uint32_t seed, unsigned idx, int c0, const float (&sc)[8], const float (&sh)[8], const uint4 v) {
   const size_t pix = idx >> p.cshift;
-  const int c0 = (int)(idx & cmask) * 8;
   const uint32_t u[4] = {v.x, v.y, v.z, v.w};
   float f[8];
 #pragma unroll
@@ -188,10 +194,6 @@ __device__ __forceinline__ void bn_act_one(const ApplyParams& p, uint32_t seed, 
     f[2 * i + 1] = t.y;
   }
   if (p.scale) {
-    const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + c0)), s1 = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + 4));
-    const float4 h0 = __ldg(reinterpret_cast<const float4*>(p.shift + c0)), h1 = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + 4));
-    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
     for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], sc[i], sh[i]);
   }
@@ -227,16 +229,22 @@ __global__ void __launch_bounds__(256) bn_act_kernel(const ApplyParams p) {
   // processed (up to 4 x 16 B outstanding per thread; 2048 threads x 16 B per SM is less than the bandwidth-latency product of HBM3e)
   const unsigned stride = gridDim.x * blockDim.x;
   unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = (int)(idx & cmask) * 8;  // loop-invariant: stride % (C / 8) == 0
+  float sc[8], sh[8];
+  if (p.scale) {
+    load_coef8(p.scale + c0, sc);
+    load_coef8(p.shift + c0, sh);
+  }
   auto ld = [&](unsigned i) {
-    return i < total ? __ldg(reinterpret_cast<const uint4*>(p.y + (size_t)(i >> p.cshift) * p.C + (int)(i & cmask) * 8)) : make_uint4(0u, 0u, 0u, 0u);
+    return i < total ? __ldg(reinterpret_cast<const uint4*>(p.y + (size_t)(i >> p.cshift) * p.C + c0)) : make_uint4(0u, 0u, 0u, 0u);
   };
   uint4 n0 = ld(idx), n1 = ld(idx + stride);
   for (; idx < total; idx += 2 * stride) {
     const uint4 v0 = n0, v1 = n1;
     n0 = ld(idx + 2 * stride);
     n1 = ld(idx + 3 * stride);
-    bn_act_one(p, seed, idx, cmask, v0);
-    if (idx + stride < total) bn_act_one(p, seed, idx + stride, cmask, v1);
+    bn_act_one(p, seed, idx, c0, sc, sh, v0);
+    if (idx + stride < total) bn_act_one(p, seed, idx + stride, c0, sc, sh, v1);
   }
 }
 
@@ -383,30 +391,61 @@ __global__ void __launch_bounds__(kFinThreads) bn_bwd_finalize_kernel(const floa
   coef[2 * C + c] = (float)(-a * db / count + a * rstd * mean * dg / count);
 }
 
-// dy = kdz*dz + ky*y + k0 with dz read as fp32 (the unrounded output of a fused GEMM epilogue)
-__global__ void __launch_bounds__(256) bn_bwd_apply_f32_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ dz, int lddz, int offdz, int P,
+// dy = kdz*dz + ky*y + k0 with dz read as fp32 (the unrounded output of a fused GEMM epilogue).  The 24 coefficients of the
+// thread's 8 channels live in registers (loop-invariant channel group); y and dz of the next element are in flight while this one is
+// finished (16 + 32 bytes per element and thread, dz as one 256-bit load).
+__device__ __forceinline__ void ldg256(const float* p, float (&o)[8]) {
+  uint32_t r[8];
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(256, 4) bn_bwd_apply_f32_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ dz, int lddz, int offdz, int P,
                                                                int C, int cshift, const float* __restrict__ coef, __nv_bfloat16* __restrict__ dy) {
   b200::pdl_enter();
   const unsigned total = (unsigned)P << cshift;
   const unsigned cmask = (1u << cshift) - 1u;
-  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+  const unsigned stride = gridDim.x * blockDim.x;
+  unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = (int)(idx & cmask) * 8;  // loop-invariant: stride % (C / 8) == 0
+  float ka[8], kb[8], kd[8];
+  load_coef8(coef + c0, ka);
+  load_coef8(coef + C + c0, kb);
+  load_coef8(coef + 2 * C + c0, kd);
+  const __nv_bfloat16* yp = y + c0;
+  const float* zp = dz + offdz + c0;
+  __nv_bfloat16* op = dy + c0;
+  uint4 yn = make_uint4(0u, 0u, 0u, 0u);
+  float zn[8];
+  if (idx < total) {
     const size_t pix = idx >> cshift;
-    const int c0 = (int)(idx & cmask) * 8;
-    float yv[8];
-    load8(y + pix * C + c0, yv);
-    const float4 z0 = __ldg(reinterpret_cast<const float4*>(dz + pix * lddz + offdz + c0)), z1 = __ldg(reinterpret_cast<const float4*>(dz + pix * lddz + offdz + c0 + 4));
-    const float* k = coef + c0;
-    const float4 a0 = __ldg(reinterpret_cast<const float4*>(k)), a1 = __ldg(reinterpret_cast<const float4*>(k + 4));
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(k + C)), b1 = __ldg(reinterpret_cast<const float4*>(k + C + 4));
-    const float4 d0 = __ldg(reinterpret_cast<const float4*>(k + 2 * C)), d1 = __ldg(reinterpret_cast<const float4*>(k + 2 * C + 4));
-    const float zz[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
-    const float ka[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const float kb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    const float kd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+    yn = __ldg(reinterpret_cast<const uint4*>(yp + pix * C));
+    ldg256(zp + pix * lddz, zn);
+  }
+  for (; idx < total; idx += stride) {
+    const size_t pix = idx >> cshift;
+    const uint4 yc = yn;
+    float zz[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) zz[i] = zn[i];
+    const unsigned nx = idx + stride;
+    if (nx < total) {
+      const size_t pn = nx >> cshift;
+      yn = __ldg(reinterpret_cast<const uint4*>(yp + pn * C));
+      ldg256(zp + pn * lddz, zn);
+    }
+    const uint32_t u[4] = {yc.x, yc.y, yc.z, yc.w};
     float o[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = fmaf(ka[i], zz[i], fmaf(kb[i], yv[i], kd[i]));
-    *reinterpret_cast<uint4*>(dy + pix * C + c0) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = unpack_bf16x2(u[i]);
+      o[2 * i] = fmaf(ka[2 * i], zz[2 * i], fmaf(kb[2 * i], t.x, kd[2 * i]));
+      o[2 * i + 1] = fmaf(ka[2 * i + 1], zz[2 * i + 1], fmaf(kb[2 * i + 1], t.y, kd[2 * i + 1]));
+    }
+    *reinterpret_cast<uint4*>(op + pix * C) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
   }
 }
 
@@ -566,7 +605,7 @@ int b200_bn_bwd_fused(const void* y, long long P, int C, const float* stats, con
                       const float* partial, int rows, int row_stride, int k_stride, float* coef, float* dgamma, float* dbeta, int accumulate, void* dy,
                       cudaStream_t stream) {
   const int cs = chunk_shift(C);
-  if (cs < 0 || !stats || lddz % 8 || offdz % 8 || rows < 1 || P * (C >> 3) >= (1LL << 31)) {
+  if (cs < 0 || !stats || lddz % 8 || offdz % 8 || rows < 1 || P * (C >> 3) >= (1LL << 31) || (dz_is_f32 && ((uintptr_t)dz & 31))) {
     b200_set_error("bn_bwd_fused: C must be a power of two in [8, 2048]; strides / offsets multiples of 8");
     return B200_ERR_ARG;
   }

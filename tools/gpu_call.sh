@@ -1,6 +1,12 @@
 #!/bin/bash
-# One gpurun call of round 2 (kept for reproducibility): ncu --set full of the first 3x3 tensor-core layer (conv1_2, 64 -> 64 at 256x256, 64 images).
+# One gpurun call of round 2 (kept for reproducibility): BatchNorm apply kernels with per-thread coefficient registers — kernel + step tests, bench.
 mkdir -p gpurun_out
-timeout 300 python tools/vgg_table.py --reps 1 > gpurun_out/vgg_pre.txt 2>&1; tail -1 gpurun_out/vgg_pre.txt
-timeout 600 ncu --set full --import-source on --clock-control none -k regex:igemm -c 1 -o gpurun_out/r2_conv3_c64 -f python tools/vgg_table.py --reps 1 > gpurun_out/ncu_conv3.log 2>&1; tail -2 gpurun_out/ncu_conv3.log
-ls -la gpurun_out/*.ncu-rep
+timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_steps_gpu.py -q -x > gpurun_out/r2_tail_tests.log 2>&1; echo rc=$?; tail -3 gpurun_out/r2_tail_tests.log
+timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-also > gpurun_out/r2_bench_tail.json 2> gpurun_out/r2_bench_tail.err; cut -c1-260 gpurun_out/r2_bench_tail.json; tail -2 gpurun_out/r2_bench_tail.err
+python - <<'P'
+import json
+d = json.loads([l for l in open("gpurun_out/r2_bench_tail.json").read().splitlines() if l.startswith("{")][-1])
+for k, v in sorted(d["tail"]["kernels"].items(), key=lambda kv: -kv[1]["ms"])[:8]:
+    print(k, v)
+print(d["clocks"])
+P
