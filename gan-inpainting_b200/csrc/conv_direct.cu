@@ -194,21 +194,6 @@ __global__ void __launch_bounds__(256, 2) convt_c1_fwd_kernel(const __nv_bfloat1
   // B fragments [group][k-step][n-tile] in shared memory (per lane): b0 = {w[ch][tap], w[ch+1][tap]}, b1 = {w[ch+2][tap], w[ch+3][tap]},
   // tap = nt*8 + g; entry ((gi*2 + s)*2 + nt)*4 + {hi b0, hi b1, lo b0, lo b1}
   __shared__ uint32_t bsm[NG * 16 * 32];
-  for (int e = threadIdx.x; e < NG * 4 * 32; e += 256) {
-    const int l = e & 31, grp = e >> 5;  // grp = (gi*2 + s)*2 + nt
-    const int nt = grp & 1, sk = (grp >> 1) & 1, gi = grp >> 2;
-    const int gg = l >> 2, qq = l & 3;
-    const float* wc = w + (size_t)(gi * 32 + qq * 8 + 4 * sk) * 16 + nt * 8 + gg;
-    uint32_t h0, l0, h1, l1;
-    split_bf16x2(__ldg(wc), __ldg(wc + 16), h0, l0);
-    split_bf16x2(__ldg(wc + 32), __ldg(wc + 48), h1, l1);
-    bsm[(grp * 4 + 0) * 32 + l] = h0;
-    bsm[(grp * 4 + 1) * 32 + l] = h1;
-    bsm[(grp * 4 + 2) * 32 + l] = l0;
-    bsm[(grp * 4 + 3) * 32 + l] = l1;
-  }
-  __syncthreads();
-
   constexpr int npix = kTH * kTH;
   constexpr int nmt = (npix + 15) / 16;
   auto load_rows = [&](int mt, uint4 (&qa)[NG], uint4 (&qb)[NG]) {
@@ -228,7 +213,22 @@ __global__ void __launch_bounds__(256, 2) convt_c1_fwd_kernel(const __nv_bfloat1
     }
   };
   uint4 qa[NG], qb[NG];
-  if (warp < nmt) load_rows(warp, qa, qb);
+  if (warp < nmt) load_rows(warp, qa, qb);  // the first activation rows travel while the filter fragments are built
+  for (int e = threadIdx.x; e < NG * 4 * 32; e += 256) {
+    const int l = e & 31, grp = e >> 5;  // grp = (gi*2 + s)*2 + nt
+    const int nt = grp & 1, sk = (grp >> 1) & 1, gi = grp >> 2;
+    const int gg = l >> 2, qq = l & 3;
+    const float* wc = w + (size_t)(gi * 32 + qq * 8 + 4 * sk) * 16 + nt * 8 + gg;
+    uint32_t h0, l0, h1, l1;
+    split_bf16x2(__ldg(wc), __ldg(wc + 16), h0, l0);
+    split_bf16x2(__ldg(wc + 32), __ldg(wc + 48), h1, l1);
+    bsm[(grp * 4 + 0) * 32 + l] = h0;
+    bsm[(grp * 4 + 1) * 32 + l] = h1;
+    bsm[(grp * 4 + 2) * 32 + l] = l0;
+    bsm[(grp * 4 + 3) * 32 + l] = l1;
+  }
+  __syncthreads();
+
   for (int mt = warp; mt < nmt; mt += 8) {
     uint4 na[NG], nb[NG];
     if (mt + 8 < nmt) load_rows(mt + 8, na, nb);  // next tile's rows are in flight while this one is multiplied
@@ -307,7 +307,9 @@ __global__ void __launch_bounds__(256, 2) convt_c1_fwd_kernel(const __nv_bfloat1
 // ------------------------------------------------------------------------------------------------
 constexpr int kWgTH = 4, kWgTW = 32, kWgStride = 2 * kWgTW + 4, kWgRows = 2 * kWgTH + 2;
 
-template <int C>
+// S: pipeline stages (S - 1 tiles in flight per block).  C = 64: three stages, three blocks per SM (96 KB of z in flight per SM; two
+// stages x two blocks = 32 KB was below the bandwidth-latency product of HBM3e: 2.9 TB/s); C = 128: two stages, two blocks.
+template <int C, int S>
 __global__ void __launch_bounds__(256) wgrad_c1_kernel(const __nv_bfloat16* __restrict__ z, int B, int H, int W, int ldz, const float* __restrict__ g,
                                                        const float* __restrict__ gmul, float* __restrict__ partial) {
   b200::pdl_enter();
@@ -316,8 +318,8 @@ __global__ void __launch_bounds__(256) wgrad_c1_kernel(const __nv_bfloat16* __re
   constexpr int ZBYTES = kWgTH * kWgTW * ROWB;   // one stage of z
   constexpr int GFLOATS = kWgRows * kWgStride;
   extern __shared__ __align__(16) uint8_t wsm[];
-  uint8_t* zs = wsm;                                   // [2][128][ROWB]
-  float* gs = reinterpret_cast<float*>(wsm + 2 * ZBYTES);  // [2][GFLOATS] image window, then [2][GFLOATS] mask window
+  uint8_t* zs = wsm;                                   // [S][128][ROWB]
+  float* gs = reinterpret_cast<float*>(wsm + S * ZBYTES);  // [S][GFLOATS] image window, then [S][GFLOATS] mask window
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gq = lane >> 2, q = lane & 3;
   const int Hg = 2 * H, Wg = 2 * W;
@@ -341,7 +343,7 @@ __global__ void __launch_bounds__(256) wgrad_c1_kernel(const __nv_bfloat16* __re
     const float* gb = g + (size_t)b * Hg * Wg;
     const float* mb = gmul ? gmul + (size_t)b * Hg * Wg : nullptr;
     float* gd = gs + buf * GFLOATS;
-    float* md = gs + (2 + buf) * GFLOATS;
+    float* md = gs + (S + buf) * GFLOATS;
     for (int e = threadIdx.x; e < kWgRows * (2 * kWgTW + 2); e += 256) {
       const int r = e / (2 * kWgTW + 2), cI = e - r * (2 * kWgTW + 2);
       const int ih = 2 * i0 - 1 + r, iw = 2 * j0 - 1 + cI;
@@ -357,21 +359,26 @@ __global__ void __launch_bounds__(256) wgrad_c1_kernel(const __nv_bfloat16* __re
 #pragma unroll
   for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
 
+  // one cp.async group per tile slot, committed even when the slot is empty, so that "all but the newest S - 1 groups" is always
+  // exactly "this iteration's tile has landed"
   int buf = 0;
-  if ((int)blockIdx.x < ntiles) stage_tile(blockIdx.x, 0);
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
-    const int next = tile + gridDim.x;
-    if (next < ntiles) {
-      stage_tile(next, buf ^ 1);  // the other buffer was released by the barrier that ended the previous iteration
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
+#pragma unroll
+  for (int i = 0; i < S - 1; ++i) {
+    const int t = blockIdx.x + i * gridDim.x;
+    if (t < ntiles) stage_tile(t, i);
+    else cp_async_commit();
+  }
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf = (buf + 1 == S ? 0 : buf + 1)) {
+    const int next = tile + (S - 1) * gridDim.x;
+    const int nbuf = buf == 0 ? S - 1 : buf - 1;  // (buf + S - 1) % S: released by the barrier that ended the previous iteration
+    if (next < ntiles) stage_tile(next, nbuf);
+    else cp_async_commit();
+    cp_async_wait<S - 1>();
     __syncthreads();
     // this warp's k-step: pixels (row = warp / 2, cols (warp & 1) * 16 + 0..15)
     const int r = warp >> 1, c0 = (warp & 1) * 16;
     const float* gd = gs + buf * GFLOATS;
-    const int moff = 2 * GFLOATS;  // mask window of the same buffer
+    const int moff = S * GFLOATS;  // mask window of the same buffer
     uint32_t ahi[4], alo[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -398,6 +405,7 @@ __global__ void __launch_bounds__(256) wgrad_c1_kernel(const __nv_bfloat16* __re
   }
 
   // cross-warp reduction in shared memory (reusing the staging buffers): red[warp][t][c]
+  cp_async_wait<0>();
   float* red = reinterpret_cast<float*>(wsm);
 #pragma unroll
   for (int j = 0; j < NT; ++j) {
@@ -641,7 +649,7 @@ int b200_convt_c1_fwd(const void* z, int B, int H, int W, int C, int ldz, const 
   return B200_OK;
 }
 
-int b200_wgrad_c1_blocks(void) { return 148 * 2; }
+int b200_wgrad_c1_blocks(void) { return 148 * 3; }  // upper bound of the partial rows b200_wgrad_c1 writes (scratch sizing)
 
 // partial: scratch of b200_wgrad_c1_blocks() * C * 16 floats
 int b200_wgrad_c1(const void* z, int B, int H, int W, int C, int ldz, const float* g, const float* gmul, float* partial, float* dw, int accumulate,
@@ -650,17 +658,18 @@ int b200_wgrad_c1(const void* z, int B, int H, int W, int C, int ldz, const floa
     b200_set_error("wgrad_c1: C must be 64/128, H % 4 == 0, W % 32 == 0");
     return B200_ERR_ARG;
   }
-  const int nblk = b200_wgrad_c1_blocks();
-  const size_t smem = 2 * (size_t)(kWgTH * kWgTW * (C + 8) * 2) + 4 * (size_t)(kWgRows * kWgStride) * sizeof(float);
+  const int stages = C == 64 ? 3 : 2;
+  const int nblk = C == 64 ? 148 * 3 : 148 * 2;  // resident blocks per SM (registers: 71 / 126 per thread)
+  const size_t smem = stages * (size_t)(kWgTH * kWgTW * (C + 8) * 2) + 2 * stages * (size_t)(kWgRows * kWgStride) * sizeof(float);
   static std::once_flag once;
   std::call_once(once, [] {
-    cudaFuncSetAttribute(wgrad_c1_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    cudaFuncSetAttribute(wgrad_c1_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(wgrad_c1_kernel<64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(wgrad_c1_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   });
   if (C == 64)
-    B200_LAUNCH((wgrad_c1_kernel<64>), nblk, 256, smem, stream, (const __nv_bfloat16*)z, B, H, W, ldz, g, gmul, partial);
+    B200_LAUNCH((wgrad_c1_kernel<64, 3>), nblk, 256, smem, stream, (const __nv_bfloat16*)z, B, H, W, ldz, g, gmul, partial);
   else
-    B200_LAUNCH((wgrad_c1_kernel<128>), nblk, 256, smem, stream, (const __nv_bfloat16*)z, B, H, W, ldz, g, gmul, partial);
+    B200_LAUNCH((wgrad_c1_kernel<128, 2>), nblk, 256, smem, stream, (const __nv_bfloat16*)z, B, H, W, ldz, g, gmul, partial);
   B200_CHECK_LAUNCH();
   B200_LAUNCH((partial_sum_kernel), (C * 16 + 31) / 32, 256, 0, stream, partial, nblk, C * 16, dw, accumulate);
   B200_CHECK_LAUNCH();
