@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256, 3) conv_c1_fwd_kernel(const float* __rest
   constexpr int CPL = C / 4;  // consecutive channels per lane
   __shared__ __align__(16) float xs[2][kXsFloats];
   __shared__ __align__(16) float xm[2][kXsFloats];
-  __shared__ uint32_t bsm[NT * 4 * 32];  // [n-tile][hi b0, hi b1, lo b0, lo b1][lane]
+  __shared__ __align__(16) uint32_t bsm[NT * 32 * 4];  // [n-tile][lane][hi b0, hi b1, lo b0, lo b1]: one 128-bit load per n-tile
   const int TOW = 1 << tow_shift, TOH = 256 >> tow_shift;
   const int Ho = H >> 1, Wo = W >> 1;
   const int tiles_w = Wo >> tow_shift, tiles_h = Ho / TOH;
@@ -55,13 +55,17 @@ __global__ void __launch_bounds__(256, 3) conv_c1_fwd_kernel(const float* __rest
     const int ih0 = 2 * (th_i * TOH) - 1, iw0 = 2 * (tw_i << tow_shift) - 1;
     const float* xb = x + (size_t)b * H * W;
     const float* mb = xmul ? xmul + (size_t)b * H * W : nullptr;
+    // element e = r * cols + cI walked in steps of 256 without a division per step (cols is 66 or 34: 256 = dq * cols + dr)
+    const int dq = 256 / cols, dr = 256 - dq * cols;
+    int r = (int)threadIdx.x / cols, cI = (int)threadIdx.x - r * cols;
     for (int e = threadIdx.x; e < rows * cols; e += 256) {
-      const int r = e / cols, cI = e - r * cols;
       const int ih = ih0 + r, iw = iw0 + cI;
       const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
       const size_t off = ok ? (size_t)ih * W + iw : 0;
       cp_async4_zfill(&xs[buf][r * xstride + cI], xb + off, ok);
       if (mb) cp_async4_zfill(&xm[buf][r * xstride + cI], mb + off, ok);
+      r += dq, cI += dr;
+      if (cI >= cols) cI -= cols, ++r;
     }
     cp_async_commit();
   };
@@ -77,10 +81,7 @@ __global__ void __launch_bounds__(256, 3) conv_c1_fwd_kernel(const float* __rest
     uint32_t h0, l0, h1, l1;
     split_bf16x2(w0.x, w0.y, h0, l0);
     split_bf16x2(w1.x, w1.y, h1, l1);
-    bsm[(j * 4 + 0) * 32 + l] = h0;
-    bsm[(j * 4 + 1) * 32 + l] = h1;
-    bsm[(j * 4 + 2) * 32 + l] = l0;
-    bsm[(j * 4 + 3) * 32 + l] = l1;
+    *reinterpret_cast<uint4*>(bsm + (j * 32 + l) * 4) = make_uint4(h0, h1, l0, l1);
   }
 
   const int kh = q >> 1, kw = (q & 1) * 2;  // taps 2q, 2q+1 (and +8: kh + 2)
@@ -124,8 +125,8 @@ __global__ void __launch_bounds__(256, 3) conv_c1_fwd_kernel(const float* __rest
         float acc[8][4];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const uint32_t* bj = bsm + ((hn + j) * 4) * 32 + lane;
-          const uint32_t h0 = bj[0], h1 = bj[32], l0 = bj[64], l1 = bj[96];
+          const uint4 bq = *reinterpret_cast<const uint4*>(bsm + ((hn + j) * 32 + lane) * 4);
+          const uint32_t h0 = bq.x, h1 = bq.y, l0 = bq.z, l1 = bq.w;
           acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
           mma_bf16_16816(acc[j], alo, h0, h1);
           mma_bf16_16816(acc[j], ahi, l0, l1);
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(256, 3) conv_c1_fwd_kernel(const float* __rest
 #pragma unroll
           for (int j = 0; j < 8; ++j)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) acc[j][i] = acc[j][i] > 0.f ? acc[j][i] : 0.2f * acc[j][i];
+            for (int i = 0; i < 4; ++i) acc[j][i] = fmaxf(acc[j][i], 0.2f * acc[j][i]);  // == x > 0 ? x : 0.2 x, two instructions
         }
 #pragma unroll
         for (int half = 0; half < 2; ++half) {  // pixel g (d0,d1) and pixel g+8 (d2,d3)
