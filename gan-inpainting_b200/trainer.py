@@ -350,6 +350,19 @@ class InpaintingTrainer:
             eD.backward(cR, self._adv(cR, 1.0, 1.0, "d_loss_real"), gD, accumulate=False)
             cF = eD.forward(inpainted, True, self.sigmoid)
             eD.backward(cF, self._adv(cF, 0.0, 1.0, "d_loss_fake"), gD, accumulate=True, on_ready=hook.ready if hook else None)
+        if update_g:
+            # loss values of the G step that depend on neither network's update: enqueued here, so that on N > 1 GPUs they run while
+            # the last discriminator bucket is still being all-reduced (the optimizer step below waits for it)
+            call("b200_recon_loss", self.recon, ptr(ground), ptr(inpainted), None, n, 1e-16, ptr(sc.recon), self._slot(RECON_SLOT), stream())
+            if self.local_recon >= 0:  # wgan_perceptual_style_faceparsing.py:209
+                call("b200_recon_loss", self.local_recon, ptr(ground), ptr(inpainted), ptr(mask_c), n, 1e-16, ptr(sc.recon), self._slot(RECON2_SLOT), stream())
+            if self.tv_weight:  # :219 — the value; its gradient is added to d g_loss / d inpainted below
+                part = torch.empty(2 * B * ground.shape[-2], dtype=torch.float32, device=dev)
+                call("b200_tv_loss", ptr(inpainted), B, ground.shape[-2], ground.shape[-1], self.tv_weight, ptr(part), self._slot(TV_SLOT), stream())
+            if self.feature_weights is not None:  # :216 — no gradient
+                from .lib.models import loss as _loss
+
+                _loss._feature_losses(inpainted, ground, True, True, dst=self.scalars[PERCEPTUAL_SLOT:STYLE_SLOT + 1], weights=self.feature_weights)
         self._reduce(self.fD, hooked=True)
         self._grad_log("d", self.fD)
         self.optD.step()
@@ -358,18 +371,8 @@ class InpaintingTrainer:
         if update_g:
             cA = eD.forward(inpainted, True, self.sigmoid)
             dadv = eD.backward(cA, self._adv(cA, 1.0, 1.0, "g_adv"), None, input_grad=True)
-            call("b200_recon_loss", self.recon, ptr(ground), ptr(inpainted), None, n, 1e-16, ptr(sc.recon), self._slot(RECON_SLOT), stream())
-            if self.local_recon >= 0:  # wgan_perceptual_style_faceparsing.py:209
-                call("b200_recon_loss", self.local_recon, ptr(ground), ptr(inpainted), ptr(mask_c), n, 1e-16, ptr(sc.recon), self._slot(RECON2_SLOT), stream())
-            if self.tv_weight:  # :219 — value into its slot, gradient added to d g_loss / d inpainted
-                R = ground.shape[-1]
-                part = torch.empty(2 * B * ground.shape[-2], dtype=torch.float32, device=dev)
-                call("b200_tv_loss", ptr(inpainted), B, ground.shape[-2], R, self.tv_weight, ptr(part), self._slot(TV_SLOT), stream())
-                call("b200_tv_loss_bwd", ptr(inpainted), B, ground.shape[-2], R, self.tv_weight, None, ptr(dadv), 1, stream())
-            if self.feature_weights is not None:  # :216 — no gradient
-                from .lib.models import loss as _loss
-
-                _loss._feature_losses(inpainted, ground, True, True, dst=self.scalars[PERCEPTUAL_SLOT:STYLE_SLOT + 1], weights=self.feature_weights)
+            if self.tv_weight:
+                call("b200_tv_loss_bwd", ptr(inpainted), B, ground.shape[-2], ground.shape[-1], self.tv_weight, None, ptr(dadv), 1, stream())
             dpre = torch.empty_like(ground)
             gG = self.fG.grad_map()
             bias = eG.uc[0].bias
