@@ -298,3 +298,21 @@ def test_flat_group_detects_and_repairs_a_detached_parameter():
     del fg, lin
     gc.collect()
     assert r() is None
+
+
+def test_nccl_group_options_and_trainer_argument_checks(monkeypatch):
+    """trainer.nccl_group_options: None unless a cap is asked for (argument or B200_NCCL_CTAS); the extra generator loss terms of
+    config 4 are rejected for the global_local recipe before anything touches a device."""
+    import pytest
+    from gan_inpainting_b200 import trainer
+
+    monkeypatch.delenv("B200_NCCL_CTAS", raising=False)
+    assert trainer.nccl_group_options() is None and trainer.nccl_group_options(0) is None
+    o = trainer.nccl_group_options(8)
+    assert o.config.max_ctas == 8 and o.config.min_ctas == 1
+    monkeypatch.setenv("B200_NCCL_CTAS", "4")
+    assert trainer.nccl_group_options().config.max_ctas == 4
+    with pytest.raises(ValueError):
+        trainer.InpaintingTrainer("global_local", None, None, net_D_local=object(), tv_weight=1.0)
+    with pytest.raises(ValueError):
+        trainer.InpaintingTrainer("nonsense", None, None)
