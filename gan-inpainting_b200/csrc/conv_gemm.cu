@@ -488,7 +488,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             else tma_load_4d_w(sW, &tmA, &fullA_bar[sa], cc * 64, c.w0 + ph_q - 1, c.h0 + ph_p - 1, c.b0);
           }
           for (int tg = 0; tg < win_taps(WIN); tg += p.tpb) {
-            if (WIN == 3 && p.bres && t != tile0) break;  // resident weights: loaded by the first tile
+            if ((WIN == 3 || WIN == 1) && p.bres && t != tile0) break;  // resident weights: loaded by the first tile
             mbar_wait(&empty_bar[sb], parb ^ 1u);
             if (!PAIR || rank == 0) mbar_arrive_expect_tx_w(&full_bar[sb], b_tx);
             for (int u = 0; u < p.tpb; ++u) {
@@ -621,7 +621,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tc_fence_after();
           const uint32_t w_lo = desc_lo(smem_u32(smem + sa * win_slot_bytes(WIN)), 16u);
           for (int tg = 0; tg < win_taps(WIN); tg += p.tpb) {
-            const bool resident = WIN == 3 && p.bres;  // the weight ring holds the whole sequence of a tile and is never refilled
+            const bool resident = (WIN == 3 || WIN == 1) && p.bres;  // the weight ring holds the whole sequence of a tile and is never refilled
             if (!resident || lt == 0) mbar_wait(&full_bar[sb], parb);
             tc_fence_after();
             const uint32_t b_lo0 = desc_lo(smem_u32(smem_b + sb * stage_bytes), 16u);
@@ -1357,12 +1357,19 @@ static int launch(const CUtensorMap& a, const CUtensorMap& b, const StoreMaps& s
     if (p.stages > 12) p.stages = 12;
     p.bres = 0;
     static const int bres_env = env_int("B200_BRES", 1);
-    if (p.win == 3 && p.n_tiles == 1 && bres_env) {
-      // e.g. conv1_2 (64 -> 64): 74 KB of weights were re-read from L2 for every 128-pixel tile (96 KB per tile with the window =
-      // 10.9 TB/s of L2 -> SM traffic, the limit).  With the ring sized to exactly one tile's weight sequence the stage index
-      // sequence repeats tile after tile, so the first tile's loads serve all of them.
-      const int steps = (taps / p.tpb) * p.cpt;
-      if (steps >= 2 && steps <= p.stages) p.bres = 1, p.stages = steps;
+    if ((p.win == 3 || (p.win == 1 && p.mode == MODE_CONV_S2)) && p.n_tiles == 1 && bres_env) {
+      // Single N tile: every tile of a CTA consumes the SAME weight sequence.  With the ring sized to exactly one tile's sequence the
+      // stage index sequence repeats tile after tile, so the first tile's loads serve all of them: no weight traffic and no
+      // weight-stage hand-shakes afterwards.  conv1_2 of VGG19 (64 -> 64): 74 KB re-read per 128-pixel tile; the 64 -> 128
+      // stride-2 convolutions (G d2, D c2): 131 KB per CTA and tile against 78 KB of activation windows.
+      const int planes = p.win == 1 ? 4 : 1;
+      const int steps = planes * (taps / p.tpb) * p.cpt;
+      int sa = p.sa;
+      while (sa > 3 && fits(extra, sa) < steps) --sa;  // give window slots to the weight ring if that makes it fit
+      if (steps >= 2 && steps <= 12 && fits(extra, sa) >= steps) {
+        p.bres = 1, p.stages = steps, p.sa = sa;
+        ring_a = p.sa * slot;
+      }
     }
     if (2 * p.sa + 2 * p.stages + 4 > (kBarrierBytes - 16) / 8) {
       b200_set_error("igemm: too many pipeline barriers");
