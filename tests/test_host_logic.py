@@ -316,3 +316,34 @@ def test_nccl_group_options_and_trainer_argument_checks(monkeypatch):
         trainer.InpaintingTrainer("global_local", None, None, net_D_local=object(), tv_weight=1.0)
     with pytest.raises(ValueError):
         trainer.InpaintingTrainer("nonsense", None, None)
+
+
+def test_vgg_feature_losses_host_side():
+    """Host logic of the VGG19 feature losses (loss.py:49-136): the engine's plan over vgg19.features[0..29] (13 convolutions, 4
+    max-pools, ReLUs fused), the first layer's channel-summed filters, and the loud failure on CPU tensors (no fallback)."""
+    import pytest
+    import torch
+    from gan_inpainting_b200 import _lib
+    from gan_inpainting_b200.engine import VGG_FEATURE_LAYERS, VggFeatureEngine
+    from gan_inpainting_b200.lib.models import loss, networks
+
+    w = networks.VGG19Wrapper()
+    eng = w._get_engine()
+    assert isinstance(eng, VggFeatureEngine) and eng is w._get_engine()
+    kinds = [k for k, _ in eng.plan]
+    assert kinds.count("conv") == 13 and kinds.count("pool") == 4 and kinds.count("relu") == 13 and max(i for _, i in eng.plan) == max(VGG_FEATURE_LAYERS)
+    assert all(eng.plan[n + 1][0] == "relu" for n, (k, _) in enumerate(eng.plan) if k == "conv")
+    with pytest.raises(_lib.B200Error):
+        eng.features_of(torch.rand(1, 1, 256, 256))
+    with pytest.raises(_lib.B200Error):
+        networks.VGG19Wrapper(pretrained=True)  # a download: trained weights come in through state_dict=
+    with pytest.raises(NotImplementedError):
+        w(torch.rand(1, 3, 32, 32))
+    loss.set_vgg(w)
+    try:
+        with pytest.raises(_lib.B200Error):
+            loss.perceptual_and_style_loss(torch.rand(1, 1, 256, 256), torch.rand(1, 1, 256, 256))
+        with pytest.raises(_lib.B200Error):
+            loss.gram_matrix(torch.rand(1, 64, 8, 8))
+    finally:
+        loss.set_vgg(None)
