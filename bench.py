@@ -516,7 +516,8 @@ def run_b200(args):
         "peak": peak, "peak_source": f"{peaks['source']} {peak_name}: SM clock {clocks.get('sm_mhz') if clocks else None} MHz during the timed region",
         "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
         "frac_of_burst": (achieved / peaks["tf_burst"]) if achieved else None, "frac_of_sustained": (achieved / peaks["tf_sustained"]) if achieved else None,
-        "traffic": traffic, "traffic_unit": f"DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/{traffic_src})",
+        "traffic": traffic, "traffic_unit": (f"DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/{traffic_src})" if traffic_src
+                                            else "no committed ncu capture for this recipe / shape"),
         "launches_per_step": gemm_calls, "avg_launch_ms": gemm_ms / max(gemm_calls, 1), "algorithmic_gflop_per_step": fl["tensor"] * B / 1e9,
         "share_of_step": gemm_ms / step_ms_instr if step_ms_instr else None,
         "step_breakdown_ms": {k: round(v, 4) for k, v in sorted(kernel_ms.items(), key=lambda kv: -kv[1])},
