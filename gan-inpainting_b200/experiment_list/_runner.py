@@ -66,8 +66,11 @@ def _logger(title: str, log_dir: str, to_file: bool = True) -> logging.Logger:
 
 
 def run(state: dict, loaders: dict, title: str, recipe: str, recon: str, schedule: Callable[[int, int], bool], local_d: bool = False,
-        lambdas=(300.0, 300.0), loss_terms: Optional[dict] = None) -> Dict[str, object]:
-    """``loss_terms``: extra generator loss terms for ``InpaintingTrainer`` (``tv_weight``, ``feature_weights``, ``local_recon``)."""
+        lambdas=(300.0, 300.0), loss_terms: Optional[dict] = None, log_ssim: Optional[bool] = None) -> Dict[str, object]:
+    """``loss_terms``: extra generator loss terms for ``InpaintingTrainer`` (``tv_weight``, ``feature_weights``, ``local_recon``).
+    ``log_ssim``: per-epoch mean SSIM of the inpainted batches (experiment1_global_local_D.py:209, experiment3_global_D.py:201;
+    default: the recipes with a local discriminator)."""
+    log_ssim = local_d if log_ssim is None else bool(log_ssim)
     state = state.copy()
     state.update({"title": title})
     train_loader, test_loader = loaders["train"], loaders.get("test")
@@ -122,7 +125,7 @@ def run(state: dict, loaders: dict, title: str, recipe: str, recon: str, schedul
             tr.step(ground, mask, update_g=upd)
             s = tr.read_scalars()
             d_iter += 1
-            if local_d:  # SSIM of the inpainted batch against the ground truth, logged per epoch (experiment1_global_local_D.py:209,216)
+            if log_ssim:  # SSIM of the inpainted batch against the ground truth, logged per epoch (experiment1_global_local_D.py:209,216)
                 ssim_acc += pytorch_ssim.ssim(ground, tr.last["inpainted"]) * ground.shape[0]
                 n_images += ground.shape[0]
             if upd:
@@ -162,7 +165,7 @@ def run(state: dict, loaders: dict, title: str, recipe: str, recon: str, schedul
                 ed[k] /= ed["update_count"]
             for n in d_names:
                 gh["avg_d"][n] /= ed["update_count"]
-        if local_d and n_images:
+        if log_ssim and n_images:
             eg["ssim"] = float(ssim_acc) / n_images
         training_epoch_hist.append({"g": eg, "d": ed, "gradients": gh})
 

@@ -1,6 +1,6 @@
 """The per-batch train step of the reference's experiment scripts, as one stream of CUDA kernels.
 
-Three recipes:
+Four recipes:
 
 * ``wgan``         experiment_list/wgan_l1.py:110-186 (recon 'l1') / wgan_rmse.py (recon 'rmse'):
                    ceil(mask) -> mask out -> G -> composite -> D step (mean heads, seeds +1/-1, RMSprop, clip
@@ -10,6 +10,8 @@ Three recipes:
 * ``global_local`` experiment_list/experiment1_global_local_D.py:139-200: G step first (no composite, mask not
                    ceil'ed, LSGAN heads of a global and a local discriminator, 300*RMSE + 300*masked RMSE), then one
                    D step over both discriminators with a single Adam.
+* ``global_d``     experiment_list/experiment3_global_D.py:140-196: the same order with the global discriminator only, BCE heads
+                   and 300*RMSE.
 
 Unlike the module API (``lib.models.networks`` + autograd) this path uses no autograd at all: the engines' forward
 and backward are called directly, gradients land in the flat gradient buffers of ``optim.flatten_parameters``, the
@@ -155,10 +157,12 @@ class InpaintingTrainer:
         wgan_perceptual_style_faceparsing.py:208-221 to the ``wgan`` / ``minimax`` recipes: ``tv_loss(inpainted, tv_weight)`` (with
         its gradient), the VGG19 perceptual + style losses (numbers only: the reference computes them under ``no_grad``, SURVEY.md
         D11) and ``LocalLoss(base)(ground, inpainted, mask)``.  That script's face-parsing term is not built."""
-        if recipe not in ("wgan", "minimax", "global_local"):
+        if recipe not in ("wgan", "minimax", "global_local", "global_d"):
             raise ValueError(recipe)
-        if recipe == "global_local" and (tv_weight or feature_weights or local_recon):
+        if recipe in ("global_local", "global_d") and (tv_weight or feature_weights or local_recon):
             raise ValueError("the extra generator loss terms belong to the wgan / minimax recipes")
+        if recipe == "global_d" and net_D_local is not None:
+            raise ValueError("global_d (experiment3_global_D.py) has no local discriminator")
         self.tv_weight = float(tv_weight)
         self.feature_weights = tuple(float(w) for w in feature_weights) if feature_weights is not None else None
         self.local_recon = {None: -1, "l1": RECON_LOCAL_L1, "mse": RECON_LOCAL_MSE}[local_recon]
@@ -179,6 +183,10 @@ class InpaintingTrainer:
             self.optD = optim.RMSprop(net_D.parameters(), lr=0.00005, clip=(-clip, clip))
             self.sigmoid, self.adv = False, ADV_WGAN
         elif recipe == "minimax":  # minimaxgan_rmse.py:64-65
+            self.optG = optim.Adam(net_G.parameters(), lr=0.0002, betas=(0.5, 0.999))
+            self.optD = optim.Adam(net_D.parameters(), lr=0.0002, betas=(0.5, 0.999))
+            self.sigmoid, self.adv = True, ADV_BCE
+        elif recipe == "global_d":  # experiment3_global_D.py:118-122: BCE heads, one Adam per network, G step first
             self.optG = optim.Adam(net_G.parameters(), lr=0.0002, betas=(0.5, 0.999))
             self.optD = optim.Adam(net_D.parameters(), lr=0.0002, betas=(0.5, 0.999))
             self.sigmoid, self.adv = True, ADV_BCE
@@ -283,12 +291,12 @@ class InpaintingTrainer:
             return self._step_graphed(ground, mask, bool(update_g))
         self.step_count += 1
         seed = self.step_count + self._seed_base if seed is None else seed
-        if self.recipe == "global_local":
+        if self.recipe in ("global_local", "global_d"):
             return self._step_global_local(ground.contiguous().float(), mask.contiguous().float(), seed)
         return self._step_gan(ground.contiguous().float(), mask.contiguous().float(), update_g, seed)
 
     def _run(self, ground, mask, update_g, seed):
-        if self.recipe == "global_local":
+        if self.recipe in ("global_local", "global_d"):
             return self._step_global_local(ground, mask, seed)
         return self._step_gan(ground, mask, update_g, seed)
 
@@ -391,7 +399,10 @@ class InpaintingTrainer:
         return self.scalars
 
     def _step_global_local(self, ground, mask, seed):
+        """experiment1_global_local_D.py:139-200 (global + local discriminator, LSGAN heads) and, without a local discriminator,
+        experiment3_global_D.py:140-196 (``global_d``: BCE heads, lambda1 * RMSE only)."""
         eG, eD, eDl, dev = self.eG, self.eD, self.eDl, self.device
+        local = eDl is not None
         n = ground.numel()
         sc = Scratch.get(dev)
         l1, l2 = self.lambdas
@@ -401,16 +412,18 @@ class InpaintingTrainer:
         cG = eG.forward(masked, True, seed=seed)
         inp = cG.g_out
         cg = eD.forward(inp, True, True)
-        cl = eDl.forward(inp, True, True, xmul=mask)
+        cl = eDl.forward(inp, True, True, xmul=mask) if local else None
         dg = eD.backward(cg, self._adv(cg, 1.0, 1.0, "g_adv"), None, input_grad=True)
-        dl = eDl.backward(cl, self._adv(cl, 1.0, 1.0, "g_adv_local"), None, input_grad=True)
+        dl = eDl.backward(cl, self._adv(cl, 1.0, 1.0, "g_adv_local"), None, input_grad=True) if local else None
         call("b200_recon_loss", RECON_RMSE, ptr(ground), ptr(inp), None, n, 1e-16, ptr(sc.recon), self._slot(RECON_SLOT), stream())
-        call("b200_recon_loss", RECON_MASKED_RMSE, ptr(ground), ptr(inp), ptr(mask), n, 1e-16, ptr(sc.recon), self._slot(RECON2_SLOT), stream())
+        if local:
+            call("b200_recon_loss", RECON_MASKED_RMSE, ptr(ground), ptr(inp), ptr(mask), n, 1e-16, ptr(sc.recon), self._slot(RECON2_SLOT), stream())
         dpre = torch.empty_like(ground)
         gG = self.fG.grad_map()
         bias = eG.uc[0].bias
-        call("b200_gstep_seed", ptr(ground), ptr(inp), ptr(cG.g_out), ptr(mask), ptr(dg), ptr(dl), RECON_RMSE, float(l1), self._slot(RECON_SLOT), RECON_MASKED_RMSE,
-             float(l2), self._slot(RECON2_SLOT), None, 0, n, ptr(dpre), None, ptr(sc.recon), ptr(gG[id(bias)]), 0, stream())
+        call("b200_gstep_seed", ptr(ground), ptr(inp), ptr(cG.g_out), ptr(mask), ptr(dg), ptr(dl) if local else None, RECON_RMSE, float(l1), self._slot(RECON_SLOT),
+             RECON_MASKED_RMSE if local else -1, float(l2) if local else 0.0, self._slot(RECON2_SLOT) if local else None, None, 0, n, ptr(dpre), None, ptr(sc.recon),
+             ptr(gG[id(bias)]), 0, stream())
         hook = self.buckets.get(id(self.fG))
         if hook:
             hook.ready(bias)
@@ -419,24 +432,31 @@ class InpaintingTrainer:
         self._grad_log("g", self.fG)
         self.optG.step()
         eG.refresh_weights(force=True)
-        # ---- D step (:178-200): four forwards, one summed loss, one Adam over chain(Dl, Dg)
-        gD, gDl = self.fD.grad_map(), self.fDl.grad_map()
+        # ---- D step (:178-200): two forwards per discriminator, one summed loss, one Adam (over chain(Dl, Dg) when there are two)
+        gD = self.fD.grad_map()
         c1 = eD.forward(ground, True, True)
         c2 = eD.forward(inp, True, True)
-        c3 = eDl.forward(ground, True, True, xmul=mask)
-        c4 = eDl.forward(inp, True, True, xmul=mask)
-        hg, hl = self.buckets.get(id(self.fD)), self.buckets.get(id(self.fDl))
-        eDl.backward(c3, self._adv(c3, 1.0, 1.0, "d_loss_real_local"), gDl, accumulate=False)
-        eDl.backward(c4, self._adv(c4, 0.0, 1.0, "d_loss_fake_local"), gDl, accumulate=True, on_ready=hl.ready if hl else None)
+        hg = self.buckets.get(id(self.fD))
+        c3 = c4 = None
+        if local:
+            gDl = self.fDl.grad_map()
+            c3 = eDl.forward(ground, True, True, xmul=mask)
+            c4 = eDl.forward(inp, True, True, xmul=mask)
+            hl = self.buckets.get(id(self.fDl))
+            eDl.backward(c3, self._adv(c3, 1.0, 1.0, "d_loss_real_local"), gDl, accumulate=False)
+            eDl.backward(c4, self._adv(c4, 0.0, 1.0, "d_loss_fake_local"), gDl, accumulate=True, on_ready=hl.ready if hl else None)
         eD.backward(c1, self._adv(c1, 1.0, 1.0, "d_loss_real"), gD, accumulate=False)
         eD.backward(c2, self._adv(c2, 0.0, 1.0, "d_loss_fake"), gD, accumulate=True, on_ready=hg.ready if hg else None)
-        self._reduce(self.fDl, hooked=True)
+        if local:
+            self._reduce(self.fDl, hooked=True)
         self._reduce(self.fD, hooked=True)
         self._grad_log("d", self.fD)
-        self._grad_log("d_local", self.fDl)
+        if local:
+            self._grad_log("d_local", self.fDl)
         self.optD.step()
         eD.refresh_weights(force=True)
-        eDl.refresh_weights(force=True)
+        if local:
+            eDl.refresh_weights(force=True)
         self.last = dict(inpainted=inp, g_out=cG.g_out, mask=mask, ctx=dict(G=cG, DgGen=cg, DlGen=cl, DgReal=c1, DgFake=c2, DlReal=c3, DlFake=c4))
         return self.scalars
 
@@ -450,6 +470,9 @@ class InpaintingTrainer:
         if self.recipe == "global_local":
             out["g_loss"] = out["g_adv"] + out["g_adv_local"] + self.lambdas[0] * out["recon"] + self.lambdas[1] * out["recon_local"]
             out["d_loss"] = out["d_loss_real"] + out["d_loss_fake"] + out["d_loss_real_local"] + out["d_loss_fake_local"]
+        elif self.recipe == "global_d":
+            out["g_loss"] = out["g_adv"] + self.lambdas[0] * out["recon"]
+            out["d_loss"] = out["d_loss_real"] + out["d_loss_fake"]
         else:
             out["g_tv"], out["g_perceptual"], out["g_style"] = v[TV_SLOT], v[PERCEPTUAL_SLOT], v[STYLE_SLOT]
             out["g_loss"] = out["g_adv"] + out["recon"]

@@ -238,6 +238,41 @@ def minimax_step(G: Params, D: Params, g_opt, d_opt, ground, mask, recon: str = 
     return out
 
 
+def global_d_step(G: Params, D: Params, g_opt, d_opt, ground, mask, lambda1: float = 300.0, dropout_masks: Optional[dict] = None, policy=None):
+    """experiment3_global_D.py:140-196: the global-discriminator-only sibling of ``global_local_step`` — G step first, no composite,
+    mask not ceil'ed, BCE heads on a sigmoid D, ``g_loss = BCE(D(G(x)), 1) + lambda1 * RMSE``; then ONE D backward of
+    ``BCE(D(ground), 1) + BCE(D(G(x).detach()), 0)``; Adam(2e-4, (0.5, 0.999)) for both (:121-122)."""
+    out = {}
+    masked = ground * (1 - mask)
+    set_requires_grad([D], False)
+    g_opt.zero_grad()
+    _scope(policy, "G")
+    inpainted = nets.unet_forward(G, masked, train=True, dropout_masks=dropout_masks, policy=policy)
+    out["inpainted"] = inpainted.detach()
+    _scope(policy, "DgGen")
+    pg = nets.patchgan_forward(D, inpainted, train=True, sigmoid=True, policy=policy).view(-1)
+    g_adv = losses.bce(pg, 1.0)
+    rec = losses.rmse(ground, inpainted)
+    g_loss = g_adv + lambda1 * rec
+    g_loss.backward()
+    out.update(g_adv=g_adv.item(), recon=rec.item(), g_loss=g_loss.item())
+    out["g_grads"] = grads_of(G)
+    g_opt.step()
+
+    set_requires_grad([D], True)
+    d_opt.zero_grad()
+    _scope(policy, "DgReal")
+    l_r = losses.bce(nets.patchgan_forward(D, ground, train=True, sigmoid=True, policy=policy).view(-1), 1.0)
+    _scope(policy, "DgFake")
+    l_f = losses.bce(nets.patchgan_forward(D, inpainted.detach(), train=True, sigmoid=True, policy=policy).view(-1), 0.0)
+    d_loss = l_r + l_f
+    d_loss.backward()
+    out.update(d_loss_real=l_r.item(), d_loss_fake=l_f.item(), d_loss=d_loss.item())
+    out["d_grads"] = grads_of(D)
+    d_opt.step()
+    return out
+
+
 def global_local_step(
     G: Params,
     Dg: Params,

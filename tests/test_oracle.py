@@ -202,3 +202,21 @@ def test_vgg_loss_oracle_matches_reference_golden():
     # the bf16-storage emulation stays close to fp32 (it bounds what the CUDA path may differ by)
     pe, se = vgg_losses.perceptual_and_style_loss(feats, c["output"], c["target"], 0.01, 0.01, bf16=True)
     assert abs(float(pe) - float(c["p"])) < 5e-2 * float(c["p"]) and abs(float(se) - float(c["s"])) < 1e-1 * float(c["s"])
+
+
+def test_global_d_step_matches_reference_modules():
+    """oracle.steps.global_d_step against the per-batch body of experiment3_global_D.py:140-196 executed over the reference's own
+    modules (oracle/pin_global_d_against_reference.py -> tests/golden/reference_global_d.pt)."""
+    import os
+
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_global_d.pt"))
+    G, D = steps.enable_grad(nets.init_unet(g["seed_g"])), steps.enable_grad(nets.init_patchgan(g["seed_d"], res=g["res"]))
+    o = steps.global_d_step(G, D, steps.make_optimizer("adam", G), steps.make_optimizer("adam", D), g["ground"], g["mask"])
+    assert rel(o["inpainted"], g["inpainted"]) < ORACLE_TOL
+    for k in ("g_adv", "recon", "d_loss_real", "d_loss_fake", "d_loss"):
+        assert abs(o[k] - g[k]) < ORACLE_TOL, (k, o[k], g[k])
+    assert abs(o["g_loss"] - g["g_loss"]) < 1e-5 * abs(g["g_loss"])
+    for name, grads in (("g_grads", o["g_grads"]), ("d_grads", o["d_grads"])):
+        for k, sm in g[name].items():
+            ne, _ = summary_close(grads[k], sm, 0)
+            assert ne < 1e-3, (name, k, ne)

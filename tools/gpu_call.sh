@@ -1,5 +1,4 @@
 #!/bin/bash
-# One gpurun call of round 2 (kept for reproducibility): the 4-GPU bench line (completes the 1 / 2 / 4 / 8 table).
+# One gpurun call of round 2 (kept for reproducibility): the global_d recipe (experiment3_global_D) — step tests, golden scalars, begin() surface.
 mkdir -p gpurun_out
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 4 --steps 20 --warmup 5 --no-cpu-baseline --no-also > gpurun_out/r2_bench_n4.json 2> gpurun_out/r2_bench_n4.err
-grep -o '"value": [0-9.]*, "unit": "images/s", "n_gpus": 4, "steps": 20, "warmup": 5, "ms_per_step": [0-9.]*' gpurun_out/r2_bench_n4.json | head -1; tail -2 gpurun_out/r2_bench_n4.err
+timeout 600 python -m pytest tests/test_steps_gpu.py -q -x -k "global_d or global_local or begin_call" > gpurun_out/r2_global_d_tests.log 2>&1; echo rc=$?; tail -12 gpurun_out/r2_global_d_tests.log
