@@ -347,3 +347,25 @@ def test_vgg_feature_losses_host_side():
             loss.gram_matrix(torch.rand(1, 64, 8, 8))
     finally:
         loss.set_vgg(None)
+
+
+def test_every_reference_experiment_script_has_a_drop_in():
+    """One module per script of the reference's experiment_list/ (names as of abeytheo/gan-inpainting), each with
+    ``begin(state, loaders)``; without CUDA they fail loudly instead of falling back to the CPU."""
+    import importlib
+
+    import pytest
+    import torch
+
+    names = ["wgan_l1", "wgan_rmse", "minimaxgan_rmse", "minimaxgan_l1", "wgan_perceptual_style_faceparsing", "experiment1_global_local_D",
+             "experiment3_global_D"]
+    for n in names:
+        m = importlib.import_module(f"gan_inpainting_b200.experiment_list.{n}")
+        assert callable(m.begin), n
+    if not torch.cuda.is_available():
+        import tempfile
+
+        from gan_inpainting_b200.experiment_list import wgan_l1
+
+        with tempfile.TemporaryDirectory() as d, pytest.raises(RuntimeError):
+            wgan_l1.begin(dict(numepoch=0, saveevery=1, evalevery=1, experiment_dir=d, log_dir=d), {"train": [], "test": []})
